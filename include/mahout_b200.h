@@ -1,0 +1,148 @@
+/*
+ * mahout_b200.h -- C ABI of libmahout_b200.so: the B200-native (sm_100a) replacement for the
+ * sketch-similarity hot path of jalhajj/mahout.  Plain `extern "C"`, opaque handles, plain
+ * pointers and sizes; no torch / C++ types.  This is exactly what a JNI (or cgo/ctypes) binding
+ * of the reference would bind -- see INTEGRATION.md for the Java/JNI stub.
+ *
+ * Every function returns an int status (MB200_OK == 0, negative == error class); the message
+ * of the last error on a context is available from mb200_last_error().  There is NO CPU
+ * fallback: without a CUDA device mb200_create() fails with MB200_ERR_NO_DEVICE.
+ *
+ * `file:line` cites are into the reference tree (mr/src/main/java/org/apache/mahout/...).
+ */
+#ifndef MAHOUT_B200_H
+#define MAHOUT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_VERSION 1
+
+/* status codes; the JNI glue maps BAD_ARG -> IllegalArgumentException (Guava Preconditions in
+ * DoubleCountMinSketch.java:117-118), CM_* -> AbstractCountMinSketch.CMException
+ * (AbstractCountMinSketch.java:21-27,71-76), everything else -> TasteException / IOException. */
+#define MB200_OK 0
+#define MB200_ERR_BAD_ARG (-1)
+#define MB200_ERR_CUDA (-2)
+#define MB200_ERR_OOM (-3)
+#define MB200_ERR_INEXACT (-4)   /* an increment is not a multiple of the bank's quantum 2^-frac_bits */
+#define MB200_ERR_RANGE (-5)     /* a counter left the range in which FP64 sums are exact         */
+#define MB200_ERR_NO_DEVICE (-6)
+#define MB200_ERR_CM_DELTA (-7)  /* "delta must be between 0 and 1, exclusive"                     */
+#define MB200_ERR_CM_EPSILON (-8)
+#define MB200_ERR_UNSUPPORTED (-9)
+
+#define MB200_MEM_HOST 0
+#define MB200_MEM_DEVICE 1
+
+#define MB200_MAX_DEPTH 16
+
+/* element type of the normalised sketch rows fed to the tensor cores */
+#define MB200_DTYPE_F16 0  /* rows scaled by 2^8; 11-bit significand (TF32-grade) at BF16 MMA rate */
+#define MB200_DTYPE_BF16 1
+
+/* cosine precision modes */
+#define MB200_PRECISION_TENSOR 0   /* similarities straight from the FP32 tensor accumulators      */
+#define MB200_PRECISION_RESCORED 1 /* tensor cores select k+margin candidates, which are re-scored
+                                      from the hi+lo split rows in FP64 (default)                  */
+
+typedef struct mb200_ctx mb200_ctx;
+typedef struct mb200_bank mb200_bank;
+
+/* ---- context ------------------------------------------------------------------------- */
+int mb200_create(int device, mb200_ctx** out);
+int mb200_destroy(mb200_ctx* ctx);
+const char* mb200_last_error(mb200_ctx* ctx); /* ctx may be NULL: error of the failed create */
+/* run all subsequent work of this context on `cuda_stream` (a cudaStream_t; NULL = the
+ * context's own stream).  Lets the caller bracket calls with its own CUDA events. */
+int mb200_set_stream(mb200_ctx* ctx, void* cuda_stream);
+int mb200_sync(mb200_ctx* ctx);
+
+/* kernel ids for mb200_kernel_time */
+#define MB200_K_UPDATE 0     /* K1 sketch update                 */
+#define MB200_K_NORMALIZE 1  /* K2 row norms + split conversion  */
+#define MB200_K_COSINE 2     /* K3 tcgen05 S.S^T + top-k epilogue */
+#define MB200_K_RESCORE 3    /* K5 merge + FP64 re-score + sort  */
+#define MB200_K_COUNT 4
+/* when profiling is on every launch of the kernels above is bracketed with CUDA events on the
+ * launching stream; mb200_kernel_time syncs and returns the accumulated ms and launch count
+ * since the last reset. */
+int mb200_set_profiling(mb200_ctx* ctx, int on);
+int mb200_kernel_time(mb200_ctx* ctx, int kernel_id, double* total_ms, int64_t* launches);
+int mb200_reset_profile(mb200_ctx* ctx);
+/* number of kernels this library has launched on the context since creation */
+int mb200_launch_count(mb200_ctx* ctx, int64_t* launches);
+
+/* ---- pinned host memory ---------------------------------------------------------------- */
+/* Page-locked host buffers for the MB200_MEM_HOST paths (a JNI binding wraps them with
+ * NewDirectByteBuffer, the way the reference's JavaCPP pointers own native memory,
+ * viennacl/.../javacpp/MatrixBase.scala:33-36).  Pageable buffers are accepted everywhere too;
+ * they just copy slower. */
+int mb200_host_alloc(int64_t bytes, void** out);
+int mb200_host_free(void* ptr);
+int mb200_host_register(void* ptr, int64_t bytes);
+int mb200_host_unregister(void* ptr);
+
+/* ---- hash family --------------------------------------------------------------------- */
+/* HashFunctionBuilder(seed): a[i], b[i] = abs(nextLong()), abs(nextLong()) from one
+ * java.util.Random(seed) (HashFunctionBuilder.java:23-28,40-60).  Host-side set-up. */
+int mb200_hash_params(int64_t seed, int depth, int64_t* a, int64_t* b);
+/* AbstractCountMinSketch(delta, epsilon): w = ceil(e/eps), d = ceil(ln(1/delta))
+ * (AbstractCountMinSketch.java:69-83); MB200_ERR_CM_DELTA / _EPSILON on the rejected ranges. */
+int mb200_cm_dims(double delta, double epsilon, int32_t* width, int32_t* depth);
+/* HashFunction.hash(key) = ((a*key + b) mod (2^63-25)) mod w for n keys, on the device
+ * (HashFunction.java:31-34). */
+int mb200_hash_keys(mb200_ctx* ctx, int64_t a, int64_t b, int32_t w, const int64_t* keys,
+                    int64_t n, int32_t* out, int mem);
+
+/* ---- sketch bank: E sketches of d x W counters, C[e][i][j], one hash family --------------- */
+/* Replaces `new DoubleCountMinSketch(w, d, hfBuilder)` per entity (DoubleCountMinSketch.java:32-36,
+ * CosineCM.java:41-58).  Counters are HBM-resident 64-bit fixed point with quantum 2^-frac_bits
+ * (0 <= frac_bits <= 40); they convert to the reference's FP64 counters bit-exactly as long as
+ * every increment is a multiple of the quantum (checked on the device, MB200_ERR_INEXACT) and
+ * |counter| < 2^53 quanta (MB200_ERR_RANGE). */
+int mb200_bank_create(mb200_ctx* ctx, int64_t entities, int32_t depth, int32_t width, int64_t seed,
+                      int32_t frac_bits, mb200_bank** out);
+/* same, with explicit hash parameters (sketches that must share one HashFunctionBuilder) */
+int mb200_bank_create_params(mb200_ctx* ctx, int64_t entities, int32_t depth, int32_t width,
+                             const int64_t* a, const int64_t* b, int32_t frac_bits,
+                             mb200_bank** out);
+int mb200_bank_destroy(mb200_bank* bank);
+int mb200_bank_clear(mb200_bank* bank);
+/* device pointer of the raw int64 counters (for an NCCL all-reduce of replica sketches) */
+int mb200_bank_counters(mb200_bank* bank, void** device_ptr, int64_t* cells);
+
+/* DoubleCountMinSketch.update(key, increment) for n events (DoubleCountMinSketch.java:72-80):
+ * C[entity[t]][i][h_i(key[t])] += inc[t] for i < d.  `entity` may be NULL when entities == 1.
+ * Pointers are host (chunked, double-buffered H2D inside the call) or device memory.
+ * Asynchronous for device memory; errors found on the device surface at the next
+ * mb200_bank_check / read / query / cosine call. */
+int mb200_bank_update(mb200_bank* bank, const int64_t* entity, const int64_t* key,
+                      const float* inc, int64_t n, int mem);
+int mb200_bank_update_f64(mb200_bank* bank, const int64_t* entity, const int64_t* key,
+                          const double* inc, int64_t n, int mem);
+/* synchronise and report MB200_ERR_INEXACT / _RANGE / _BAD_ARG (entity out of range) */
+int mb200_bank_check(mb200_bank* bank);
+
+/* counters of entities [e0, e1) as the reference's doubles, out[(e-e0)][i][j] */
+int mb200_bank_read(mb200_bank* bank, int64_t e0, int64_t e1, double* out, int mem);
+/* DoubleCountMinSketch.get(key): min_i C[e][i][h_i(key)] (DoubleCountMinSketch.java:94-103) */
+int mb200_bank_query(mb200_bank* bank, const int64_t* entity, const int64_t* key, int64_t n,
+                     double* out, int mem);
+/* DoubleCountMinSketch.cosine(a, b) for n entity pairs, FP64 (DoubleCountMinSketch.java:114-149):
+ * min over rows of AB/(sqrt(AA)*sqrt(BB)), rows with zero denominator skipped, NaN if none. */
+int mb200_bank_pair_cosine(mb200_bank* bank, const int64_t* ea, const int64_t* eb, int64_t n,
+                           double* out, int mem);
+/* same between the sketches of two banks (e.g. two single-sketch banks = two
+ * DoubleCountMinSketch objects); MB200_ERR_BAD_ARG with the reference's message when widths or
+ * depths differ (Preconditions.checkArgument, DoubleCountMinSketch.java:117-118). */
+int mb200_bank_cross_cosine(mb200_bank* bank_a, const int64_t* ea, mb200_bank* bank_b,
+                            const int64_t* eb, int64_t n, double* out, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAHOUT_B200_H */

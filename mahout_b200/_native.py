@@ -1,0 +1,122 @@
+"""ctypes binding of libmahout_b200.so (the C ABI declared in include/mahout_b200.h).
+
+There is no fallback of any kind: if the library is missing, or the process has no sm_100
+device, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmahout_b200.so")
+
+OK = 0
+ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_INEXACT, ERR_RANGE = -1, -2, -3, -4, -5
+ERR_NO_DEVICE, ERR_CM_DELTA, ERR_CM_EPSILON, ERR_UNSUPPORTED = -6, -7, -8, -9
+MEM_HOST, MEM_DEVICE = 0, 1
+DTYPE_F16, DTYPE_BF16 = 0, 1
+PRECISION_TENSOR, PRECISION_RESCORED = 0, 1
+K_UPDATE, K_NORMALIZE, K_COSINE, K_RESCORE = 0, 1, 2, 3
+MAX_DEPTH = 16
+
+
+class NativeError(RuntimeError):
+    """A non-zero status from libmahout_b200 that is not an argument error."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libmahout_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CMException(Exception):
+    """AbstractCountMinSketch.CMException (AbstractCountMinSketch.java:21-27)."""
+
+
+class InexactError(NativeError):
+    """An increment / counter cannot be represented exactly by the bank (MB200_ERR_INEXACT/RANGE)."""
+
+
+i64, i32, f64, vp = C.c_int64, C.c_int32, C.c_double, C.c_void_p
+
+_PROTOS = {
+    "mb200_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "mb200_destroy": (C.c_int, [vp]),
+    "mb200_last_error": (C.c_char_p, [vp]),
+    "mb200_set_stream": (C.c_int, [vp, vp]),
+    "mb200_sync": (C.c_int, [vp]),
+    "mb200_set_profiling": (C.c_int, [vp, C.c_int]),
+    "mb200_kernel_time": (C.c_int, [vp, C.c_int, C.POINTER(f64), C.POINTER(i64)]),
+    "mb200_reset_profile": (C.c_int, [vp]),
+    "mb200_launch_count": (C.c_int, [vp, C.POINTER(i64)]),
+    "mb200_host_alloc": (C.c_int, [i64, C.POINTER(vp)]),
+    "mb200_host_free": (C.c_int, [vp]),
+    "mb200_host_register": (C.c_int, [vp, i64]),
+    "mb200_host_unregister": (C.c_int, [vp]),
+    "mb200_hash_params": (C.c_int, [i64, C.c_int, vp, vp]),
+    "mb200_cm_dims": (C.c_int, [f64, f64, C.POINTER(i32), C.POINTER(i32)]),
+    "mb200_hash_keys": (C.c_int, [vp, i64, i64, i32, vp, i64, vp, C.c_int]),
+    "mb200_bank_create": (C.c_int, [vp, i64, i32, i32, i64, i32, C.POINTER(vp)]),
+    "mb200_bank_create_params": (C.c_int, [vp, i64, i32, i32, vp, vp, i32, C.POINTER(vp)]),
+    "mb200_bank_destroy": (C.c_int, [vp]),
+    "mb200_bank_clear": (C.c_int, [vp]),
+    "mb200_bank_counters": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+    "mb200_bank_update": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
+    "mb200_bank_update_f64": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
+    "mb200_bank_check": (C.c_int, [vp]),
+    "mb200_bank_read": (C.c_int, [vp, i64, i64, vp, C.c_int]),
+    "mb200_bank_query": (C.c_int, [vp, vp, vp, i64, vp, C.c_int]),
+    "mb200_bank_pair_cosine": (C.c_int, [vp, vp, vp, i64, vp, C.c_int]),
+    "mb200_bank_cross_cosine": (C.c_int, [vp, vp, vp, vp, i64, vp, C.c_int]),
+    # bench / test support (mahout_b200/csrc/synth.h)
+    "mb200_synth_events": (C.c_int, [vp, C.c_uint64, i64, i64, i64, vp, i64, vp, vp, vp, vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m mahout_b200.build` "
+                "(nvcc, sm_100a).  mahout_b200 has no CPU or PyTorch fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name, None)
+            if fn is None:
+                continue  # optional symbols are checked by tests/test_abi.py against the header
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def register(name: str, restype, argtypes) -> None:
+    _PROTOS[name] = (restype, argtypes)
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+
+
+def last_error(ctx=None) -> str:
+    s = lib().mb200_last_error(ctx)
+    return s.decode("utf-8", "replace") if s else ""
+
+
+def check(rc: int, ctx=None) -> None:
+    """Map a status code to the exception the reference would raise at the same place."""
+    if rc == OK:
+        return
+    msg = last_error(ctx)
+    if rc == ERR_BAD_ARG:
+        raise ValueError(msg)  # IllegalArgumentException (Guava Preconditions)
+    if rc in (ERR_CM_DELTA, ERR_CM_EPSILON):
+        raise CMException(msg)
+    if rc == ERR_OOM:
+        raise MemoryError(msg)
+    if rc in (ERR_INEXACT, ERR_RANGE):
+        raise InexactError(rc, msg)
+    raise NativeError(rc, msg)

@@ -1,0 +1,88 @@
+// common.cuh -- context / bank structures and error plumbing shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mahout_b200.h"
+#include "cm_hash.cuh"
+
+struct HashFamily {
+  uint64_t a[MB200_MAX_DEPTH];  // residues mod p
+  uint64_t b[MB200_MAX_DEPTH];
+  uint32_t w;
+  uint32_t wmask;  // w-1 when w is a power of two, else 0
+  int32_t d;
+};
+
+// device-side status words (one set per bank)
+enum { FLAG_INEXACT = 0, FLAG_MAXABS = 1, FLAG_BAD_ENTITY = 2, FLAG_RANGE = 3, FLAG_WORDS = 4 };
+
+struct ProfSpan {
+  int kernel_id;
+  cudaEvent_t beg, end;
+};
+
+struct mb200_ctx {
+  int device = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t stream = nullptr;  // stream in use (own_stream or the caller's)
+  std::mutex mu;
+  std::string err;
+  int64_t launches = 0;
+  bool profiling = false;
+  std::vector<ProfSpan> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[MB200_K_COUNT] = {0, 0, 0, 0};
+  int64_t prof_n[MB200_K_COUNT] = {0, 0, 0, 0};
+  // host-path staging (device) buffers, grown on demand
+  void* stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};
+  cudaEvent_t stage_full[2] = {nullptr, nullptr};
+};
+
+struct mb200_bank {
+  mb200_ctx* ctx = nullptr;
+  int64_t E = 0;
+  int32_t d = 0, W = 0, frac_bits = 0;
+  HashFamily hf;
+  int64_t a_raw[MB200_MAX_DEPTH], b_raw[MB200_MAX_DEPTH];
+  long long* counters = nullptr;  // [E][d][W] fixed point
+  unsigned long long* flags = nullptr;  // FLAG_WORDS
+  double events_total = 0;  // for the conservative range bound
+};
+
+int mb200_fail(mb200_ctx* ctx, int code, const char* fmt, ...);
+void mb200_set_global_error(const char* msg);
+
+#define MB_CUDA(ctx, expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return mb200_fail((ctx), _e == cudaErrorMemoryAllocation ? MB200_ERR_OOM : MB200_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define MB_CHECK(call)          \
+  do {                          \
+    int _rc = (call);           \
+    if (_rc != MB200_OK) return _rc; \
+  } while (0)
+
+// profiling helpers: bracket a kernel launch with events when profiling is on
+struct ProfScope {
+  mb200_ctx* ctx;
+  int idx = -1;
+  ProfScope(mb200_ctx* c, int kernel_id);
+  ~ProfScope();
+};
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

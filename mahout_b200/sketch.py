@@ -1,0 +1,340 @@
+"""Host-side mirror of the reference's sketch operator API over the C ABI.
+
+Same names, argument meaning and error behaviour as the fork's Java classes
+(mr/src/main/java/org/apache/mahout/cf/taste/impl/common/):
+
+  HashFunctionBuilder(seed)                      HashFunctionBuilder.java:23-60
+  HashFunction.hash(key)                         HashFunction.java:31-34
+  DoubleCountMinSketch(w, d, hfb) / (delta, eps, hfb)
+      .update(key, inc) .get(key) .cosine(a, b)  DoubleCountMinSketch.java:32-149
+  SketchBank: E sketches sharing one builder     CosineCM.java:41-67 (one sketch per entity)
+
+Everything computes on the GPU through libmahout_b200.so; nothing here has a CPU path.
+Array arguments may be numpy arrays (host memory) or torch CUDA tensors (device memory).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _native as N
+
+_tls = threading.local()
+
+
+class Context:
+    """One mb200_ctx (one GPU, one stream set).  Calls on a context are serialised by the library."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = N.lib().mb200_create(int(device), C.byref(h))
+        if rc != N.OK:
+            N.check(rc, None)
+        self._h = h
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise ValueError("context is closed")
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            N.lib().mb200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        N.check(N.lib().mb200_sync(self.handle), self.handle)
+
+    def set_stream(self, cuda_stream: int | None):
+        N.check(N.lib().mb200_set_stream(self.handle, C.c_void_p(cuda_stream or 0)), self.handle)
+
+    def set_profiling(self, on: bool):
+        N.check(N.lib().mb200_set_profiling(self.handle, int(on)), self.handle)
+
+    def reset_profile(self):
+        N.check(N.lib().mb200_reset_profile(self.handle), self.handle)
+
+    def kernel_time(self, kernel_id: int):
+        ms, n = C.c_double(), C.c_int64()
+        N.check(N.lib().mb200_kernel_time(self.handle, kernel_id, C.byref(ms), C.byref(n)), self.handle)
+        return ms.value, n.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        N.check(N.lib().mb200_launch_count(self.handle, C.byref(n)), self.handle)
+        return n.value
+
+
+def default_context() -> Context:
+    ctx = getattr(_tls, "ctx", None)
+    if ctx is None or ctx._h is None:
+        dev = 0
+        try:
+            import torch
+            if torch.cuda.is_available():
+                dev = torch.cuda.current_device()
+        except Exception:
+            pass
+        ctx = Context(dev)
+        _tls.ctx = ctx
+    return ctx
+
+
+# --------------------------------------------------------------------------------------------
+# argument marshalling: numpy (host) or torch.cuda (device)
+# --------------------------------------------------------------------------------------------
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _Arg:
+    """Pointer + memory space of one array argument; keeps the converted array alive."""
+
+    def __init__(self, x, np_dtype, torch_dtype_name, allow_none=False):
+        self.keep = None
+        self.ptr = None
+        self.mem = None
+        self.n = 0
+        if x is None:
+            if not allow_none:
+                raise ValueError("array argument is None")
+            return
+        if _is_torch(x):
+            import torch
+            want = getattr(torch, torch_dtype_name)
+            if not x.is_cuda:
+                x = x.numpy()
+            else:
+                if x.dtype != want:
+                    x = x.to(want)
+                x = x.contiguous()
+                self.keep, self.ptr, self.mem, self.n = x, C.c_void_p(x.data_ptr()), N.MEM_DEVICE, x.numel()
+                return
+        a = np.ascontiguousarray(x, dtype=np_dtype)
+        self.keep, self.ptr, self.mem, self.n = a, C.c_void_p(a.ctypes.data), N.MEM_HOST, a.size
+
+
+def _same_mem(*args):
+    mems = {a.mem for a in args if a.mem is not None}
+    if len(mems) > 1:
+        raise ValueError("array arguments must all be host (numpy) or all device (torch.cuda)")
+    return mems.pop() if mems else N.MEM_HOST
+
+
+def _out(shape, np_dtype, torch_dtype_name, mem, device):
+    if mem == N.MEM_DEVICE:
+        import torch
+        t = torch.empty(shape, dtype=getattr(torch, torch_dtype_name), device=f"cuda:{device}")
+        return t, C.c_void_p(t.data_ptr())
+    a = np.empty(shape, dtype=np_dtype)
+    return a, C.c_void_p(a.ctypes.data)
+
+
+# --------------------------------------------------------------------------------------------
+# hash family
+# --------------------------------------------------------------------------------------------
+BIG_PRIME = 9223372036854775783  # HashFunctionBuilder.java:24
+
+
+class HashFunctionBuilder:
+    """`new HashFunctionBuilder(seed)`: parameters a_i, b_i = abs(nextLong()), abs(nextLong())
+    drawn lazily, in iteration order, from one java.util.Random(seed)."""
+
+    def __init__(self, seed: int):
+        self.seed = int(seed)
+        self._a = np.zeros(0, np.int64)
+        self._b = np.zeros(0, np.int64)
+
+    def params(self, depth: int):
+        if depth > self._a.shape[0]:
+            # the parameter stream is a pure function of (seed, index): regenerate the prefix
+            a = np.zeros(depth, np.int64)
+            b = np.zeros(depth, np.int64)
+            N.check(N.lib().mb200_hash_params(self.seed, depth, a.ctypes.data_as(C.c_void_p),
+                                              b.ctypes.data_as(C.c_void_p)))
+            self._a, self._b = a, b
+        return self._a[:depth].copy(), self._b[:depth].copy()
+
+    def getHashFunction(self, iteration: int, size: int) -> "HashFunction":
+        a, b = self.params(iteration + 1)
+        return HashFunction(int(a[iteration]), int(b[iteration]), int(size))
+
+
+class HashFunction:
+    """h(key) = ((a*key + b) mod (2^63-25)) mod w, evaluated on the GPU."""
+
+    def __init__(self, a: int, b: int, w: int, ctx: Context | None = None):
+        self.a, self.b, self.w = int(a), int(b), int(w)
+        self._ctx = ctx
+
+    def hash(self, key):
+        ctx = self._ctx or default_context()
+        scalar = np.isscalar(key)
+        k = _Arg(np.atleast_1d(key) if not _is_torch(key) else key, np.int64, "int64")
+        out, optr = _out((k.n,), np.int32, "int32", k.mem, ctx.device)
+        N.check(N.lib().mb200_hash_keys(ctx.handle, self.a, self.b, self.w, k.ptr, k.n, optr, k.mem),
+                ctx.handle)
+        return int(out[0]) if scalar else out
+
+
+def cm_dims(delta: float, epsilon: float):
+    """(w, d) of AbstractCountMinSketch(delta, epsilon); raises CMException on the rejected ranges."""
+    w, d = C.c_int32(), C.c_int32()
+    N.check(N.lib().mb200_cm_dims(float(delta), float(epsilon), C.byref(w), C.byref(d)))
+    return w.value, d.value
+
+
+# --------------------------------------------------------------------------------------------
+# sketch bank
+# --------------------------------------------------------------------------------------------
+class SketchBank:
+    """E count-min sketches of d x W counters sharing one HashFunctionBuilder, HBM-resident.
+
+    frac_bits: counters are exact multiples of 2^-frac_bits (1 covers MovieLens-style
+    half-star prefs); increments that are not raise InexactError at the next check."""
+
+    def __init__(self, entities: int, width: int, depth: int, hfBuilder: HashFunctionBuilder | int = 42,
+                 frac_bits: int = 1, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        if not isinstance(hfBuilder, HashFunctionBuilder):
+            hfBuilder = HashFunctionBuilder(int(hfBuilder))
+        self.hfBuilder = hfBuilder
+        if not (0 < int(depth) <= N.MAX_DEPTH):
+            raise ValueError(f"depth must be in (0, {N.MAX_DEPTH}] (got {depth})")
+        a, b = hfBuilder.params(int(depth))
+        self.a, self.b = a, b
+        h = C.c_void_p()
+        N.check(N.lib().mb200_bank_create_params(
+            self.ctx.handle, int(entities), int(depth), int(width), a.ctypes.data_as(C.c_void_p),
+            b.ctypes.data_as(C.c_void_p), int(frac_bits), C.byref(h)), self.ctx.handle)
+        self._h = h
+        self.E, self.w, self.d, self.frac_bits = int(entities), int(width), int(depth), int(frac_bits)
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise ValueError("bank is closed")
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self.ctx._h is not None:
+            N.lib().mb200_bank_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def clear(self):
+        N.check(N.lib().mb200_bank_clear(self.handle), self.ctx.handle)
+
+    def update(self, entity, key, inc):
+        """C[entity[t]][i][h_i(key[t])] += inc[t]; entity may be None when E == 1."""
+        k = _Arg(key, np.int64, "int64")
+        e = _Arg(entity, np.int64, "int64", allow_none=True)
+        f64 = (inc.dtype == np.float64) if isinstance(inc, np.ndarray) else (
+            _is_torch(inc) and str(inc.dtype) == "torch.float64")
+        v = _Arg(inc, np.float64 if f64 else np.float32, "float64" if f64 else "float32")
+        if v.n != k.n or (e.ptr is not None and e.n != k.n):
+            raise ValueError("entity, key and inc must have the same length")
+        mem = _same_mem(k, e, v)
+        fn = N.lib().mb200_bank_update_f64 if f64 else N.lib().mb200_bank_update
+        N.check(fn(self.handle, e.ptr, k.ptr, v.ptr, k.n, mem), self.ctx.handle)
+
+    def check(self):
+        N.check(N.lib().mb200_bank_check(self.handle), self.ctx.handle)
+
+    def read(self, e0: int = 0, e1: int | None = None, device: bool = False):
+        """Counters of entities [e0, e1) as the reference's doubles, shape [e1-e0, d, w]."""
+        e1 = self.E if e1 is None else e1
+        if not (0 <= e0 <= e1 <= self.E):
+            raise ValueError(f"bad entity range [{e0},{e1}) of {self.E}")
+        out, optr = _out((e1 - e0, self.d, self.w), np.float64, "float64",
+                         N.MEM_DEVICE if device else N.MEM_HOST, self.ctx.device)
+        N.check(N.lib().mb200_bank_read(self.handle, e0, e1, optr,
+                                        N.MEM_DEVICE if device else N.MEM_HOST), self.ctx.handle)
+        return out
+
+    def query(self, entity, key):
+        """DoubleCountMinSketch.get for n (entity, key) pairs."""
+        k = _Arg(key, np.int64, "int64")
+        e = _Arg(entity, np.int64, "int64", allow_none=True)
+        mem = _same_mem(k, e)
+        out, optr = _out((k.n,), np.float64, "float64", mem, self.ctx.device)
+        N.check(N.lib().mb200_bank_query(self.handle, e.ptr, k.ptr, k.n, optr, mem), self.ctx.handle)
+        return out
+
+    def pair_cosine(self, ea, eb):
+        """DoubleCountMinSketch.cosine(sketch[ea[t]], sketch[eb[t]]) in FP64."""
+        a = _Arg(ea, np.int64, "int64")
+        b = _Arg(eb, np.int64, "int64")
+        if a.n != b.n:
+            raise ValueError("ea and eb must have the same length")
+        mem = _same_mem(a, b)
+        out, optr = _out((a.n,), np.float64, "float64", mem, self.ctx.device)
+        N.check(N.lib().mb200_bank_pair_cosine(self.handle, a.ptr, b.ptr, a.n, optr, mem),
+                self.ctx.handle)
+        return out
+
+    def counters_ptr(self):
+        p, n = C.c_void_p(), C.c_int64()
+        N.check(N.lib().mb200_bank_counters(self.handle, C.byref(p), C.byref(n)), self.ctx.handle)
+        return p.value, n.value
+
+
+class DoubleCountMinSketch:
+    """One sketch: `new DoubleCountMinSketch(w, d, hfBuilder)` or `(delta, epsilon, hfBuilder)`."""
+
+    def __init__(self, width_or_delta, depth_or_epsilon, hfBuilder: HashFunctionBuilder,
+                 frac_bits: int = 1, ctx: Context | None = None):
+        if isinstance(width_or_delta, float) or isinstance(depth_or_epsilon, float):
+            w, d = cm_dims(float(width_or_delta), float(depth_or_epsilon))
+        else:
+            w, d = int(width_or_delta), int(depth_or_epsilon)
+        self.w, self.d = w, d
+        self._bank = SketchBank(1, w, d, hfBuilder, frac_bits, ctx)
+        self.hashFunctions = [hfBuilder.getHashFunction(i, w) for i in range(d)]
+
+    def update(self, key, increment):
+        k = np.atleast_1d(np.asarray(key, dtype=np.int64))
+        v = np.atleast_1d(np.asarray(increment, dtype=np.float64))
+        self._bank.update(None, k, np.broadcast_to(v, k.shape))
+
+    def get(self, key):
+        scalar = np.isscalar(key)
+        out = self._bank.query(None, np.atleast_1d(np.asarray(key, dtype=np.int64)))
+        return float(out[0]) if scalar else out
+
+    def counts(self) -> np.ndarray:
+        return self._bank.read()[0]
+
+    @staticmethod
+    def cosine(a: "DoubleCountMinSketch", b: "DoubleCountMinSketch") -> float:
+        z = np.zeros(1, np.int64)
+        out = np.empty(1, np.float64)
+        N.check(N.lib().mb200_bank_cross_cosine(
+            a._bank.handle, z.ctypes.data_as(C.c_void_p), b._bank.handle, z.ctypes.data_as(C.c_void_p),
+            1, out.ctypes.data_as(C.c_void_p), N.MEM_HOST), a._bank.ctx.handle)
+        return float(out[0])
+
+
+def _as_tensor(ptr: int, n: int, device: int):
+    """View n int64 device words at `ptr` as a torch tensor (plumbing only)."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+    return torch.as_tensor(h, device=f"cuda:{device}")

@@ -1,0 +1,222 @@
+"""GPU parity of the sketch stage (K1 update, hash, point query, pair cosine) against the CPU
+oracle, through the C ABI.  Bar: bit-exact counters / hashes / point queries; FP64 pair cosine
+within 1e-12 relative (summation order differs from the reference's sequential loop)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import mahout_b200
+    return mahout_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(mb):
+    c = mb.Context(0)
+    yield c
+    c.close()
+
+
+def _events(rng, n, E, key_lo, key_hi, halves=True):
+    ent = rng.integers(0, E, n).astype(np.int64)
+    key = rng.integers(key_lo, key_hi, n).astype(np.int64)
+    inc = (rng.integers(1, 11, n) * (0.5 if halves else 1.0)).astype(np.float32)
+    return ent, key, inc
+
+
+def test_hash_matches_oracle_and_survey_anchors(mb, ctx):
+    hfb = mb.HashFunctionBuilder(42)
+    keys = np.array([0, 1, 2, 1682, 10 ** 12, -1, 2 ** 63 - 1, -2 ** 63, 2 ** 63 - 25, -(2 ** 63 - 25)],
+                    np.int64)
+    want0 = [671704, 767226, 862723, 888455, 1047010, 576207]
+    h0 = hfb.getHashFunction(0, 1 << 20)
+    h0._ctx = ctx
+    assert h0.hash(keys)[:6].tolist() == want0
+    rng = np.random.Generator(np.random.PCG64(11))
+    big = rng.integers(-2 ** 63, 2 ** 63 - 1, 100000, dtype=np.int64)
+    oa, ob = orc.hash_params(42, 4)
+    for i in range(4):
+        for w in (1 << 20, 4096, 4099, 1, 2 ** 31 - 1):
+            hf = mb.HashFunction(int(oa[i]), int(ob[i]), w, ctx)
+            for ks in (keys, big):
+                assert (hf.hash(ks) == orc.hash_many(oa[i], ob[i], w, ks)).all()
+    # Math.abs(Long.MIN_VALUE) < 0 corner of the parameters
+    hf = mb.HashFunction(-2 ** 63, -2 ** 63, 4096, ctx)
+    assert (hf.hash(big[:1000]) == orc.hash_many(-2 ** 63, -2 ** 63, 4096, big[:1000])).all()
+
+
+def test_golden_fixture_counters_bit_exact(mb, ctx):
+    g = json.load(open(os.path.join(GOLD, "sketch_small.json")))
+    bank = mb.SketchBank(g["E"], g["w"], g["d"], mb.HashFunctionBuilder(g["seed"]), 1, ctx)
+    bank.update(np.array(g["entity"]), np.array(g["key"]), np.array(g["inc"], np.float32))
+    got = bank.read().ravel()
+    want = np.zeros_like(got)
+    want[np.array(g["nonzero_cells"])] = g["nonzero_values"]
+    assert got.tobytes() == want.tobytes()
+    bank.close()
+
+
+@pytest.mark.parametrize("E,d,w,n", [(1, 4, 1 << 20, 300000), (1, 4, 4096, 100001), (1, 3, 1000, 7),
+                                      (1682, 4, 4096, 100000), (37, 5, 129, 50003), (5, 16, 64, 1000)])
+def test_update_bit_exact_host_and_device(mb, ctx, E, d, w, n):
+    import torch
+    rng = np.random.Generator(np.random.PCG64(1000 + E + d + w))
+    ent, key, inc = _events(rng, n, E, -1000, 1000000)
+    if E == 1:
+        # heavy skew: exercises the shared-memory hot-key cache
+        key = np.minimum(rng.zipf(1.1, n), 10 ** 7).astype(np.int64)
+    a, b = orc.hash_params(42, d)
+    want = np.zeros((E, d, w))
+    orc.bank_update(want, d, w, a, b, ent if E > 1 else None, key, inc)
+    for where in ("host", "device"):
+        bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+        if where == "host":
+            bank.update(ent if E > 1 else None, key, inc)
+        else:
+            te = torch.from_numpy(ent).cuda() if E > 1 else None
+            bank.update(te, torch.from_numpy(key).cuda(), torch.from_numpy(inc).cuda())
+        got = bank.read()
+        assert got.tobytes() == want.tobytes(), where
+        # point queries (DoubleCountMinSketch.get), including keys never inserted
+        qk = np.concatenate([key[:500], rng.integers(-50, 50, 100)]).astype(np.int64)
+        qe = np.concatenate([ent[:500], rng.integers(0, E, 100)]).astype(np.int64)
+        q = bank.query(qe if E > 1 else None, qk)
+        assert q.tobytes() == orc.bank_query(want, d, w, a, b, qe if E > 1 else None, qk).tobytes()
+        bank.close()
+
+
+def test_update_unaligned_and_tail(mb, ctx):
+    """odd offsets defeat the 16-byte vector loads; n % 4 != 0 exercises the tail."""
+    import torch
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 4099
+    ent, key, inc = _events(rng, n + 1, 9, 0, 500)
+    a, b = orc.hash_params(42, 4)
+    want = np.zeros((9, 4, 256))
+    orc.bank_update(want, 4, 256, a, b, ent[1:], key[1:], inc[1:])
+    bank = mb.SketchBank(9, 256, 4, 42, 1, ctx)
+    bank.update(torch.from_numpy(ent).cuda()[1:], torch.from_numpy(key).cuda()[1:],
+                torch.from_numpy(inc).cuda()[1:])
+    assert bank.read().tobytes() == want.tobytes()
+    bank.close()
+
+
+def test_empty_update_and_clear(mb, ctx):
+    bank = mb.SketchBank(3, 64, 2, 42, 1, ctx)
+    bank.update(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32))
+    assert not bank.read().any()
+    bank.update(np.array([1]), np.array([5]), np.array([2.5], np.float32))
+    assert bank.read().sum() == 5.0
+    bank.clear()
+    assert not bank.read().any()
+    bank.close()
+
+
+def test_negative_and_f64_increments(mb, ctx):
+    rng = np.random.Generator(np.random.PCG64(6))
+    n = 20000
+    ent = rng.integers(0, 4, n).astype(np.int64)
+    key = rng.integers(-30, 30, n).astype(np.int64)
+    inc = (rng.integers(-20, 21, n) * 0.125)
+    a, b = orc.hash_params(7, 4)
+    want = np.zeros((4, 4, 32))
+    for e in range(4):
+        m = ent == e
+        orc.cm_update(want[e], 32, 4, a, b, key[m], inc[m])
+    bank = mb.SketchBank(4, 32, 4, 7, 3, ctx)
+    bank.update(ent, key, inc.astype(np.float64))
+    assert bank.read().tobytes() == want.tobytes()
+    bank.close()
+
+
+def test_inexact_increment_is_an_error_not_a_rounding(mb, ctx):
+    bank = mb.SketchBank(1, 64, 2, 42, 1, ctx)
+    bank.update(None, np.array([1, 2]), np.array([0.5, 0.3], np.float32))
+    with pytest.raises(mb.InexactError):
+        bank.check()
+    bank.close()
+
+
+def test_bad_entity_and_bad_args(mb, ctx):
+    bank = mb.SketchBank(4, 64, 2, 42, 1, ctx)
+    bank.update(np.array([0, 4]), np.array([1, 2]), np.array([1.0, 1.0], np.float32))
+    with pytest.raises(ValueError):
+        bank.check()
+    bank.close()
+    with pytest.raises(ValueError):
+        mb.SketchBank(4, 0, 2, 42, 1, ctx)
+    with pytest.raises(ValueError):
+        mb.SketchBank(4, 16, 0, 42, 1, ctx)
+    with pytest.raises(mb.CMException):
+        mb.DoubleCountMinSketch(0.9, 0.01, mb.HashFunctionBuilder(1))
+
+
+def test_double_count_min_sketch_api(mb, ctx):
+    """Reads like a test of the Java class: update / get / cosine, widths must agree."""
+    hfb = mb.HashFunctionBuilder(42)
+    x = [0, 2, 0, 0, 8, 3, 0, 6, 0, 1, 2, 2, 0]
+    y = [3, 0, 0, 0, 7, 0, 2, 2, 1, 3, 2, 1, 1]
+    # wide enough that the 13 keys do not collide in any row -> sketch cosine == exact cosine,
+    # which the reference pins (VectorSimilarityMeasuresTest.testCosineSimilarity: 0.769846046)
+    cma = mb.DoubleCountMinSketch(1 << 16, 4, hfb, ctx=ctx)
+    cmb = mb.DoubleCountMinSketch(1 << 16, 4, hfb, ctx=ctx)
+    for k, (xa, xb) in enumerate(zip(x, y)):
+        if xa:
+            cma.update(k, float(xa))
+        if xb:
+            cmb.update(k, float(xb))
+    assert cma.get(4) == 8.0 and cmb.get(4) == 7.0 and cma.get(0) == 0.0
+    cos = mb.DoubleCountMinSketch.cosine(cma, cmb)
+    assert abs(cos - 0.769846046) < 1e-6
+    assert abs(cos - orc.cm_cosine(cma.counts(), cmb.counts(), 1 << 16, 4)) < 1e-14
+    other = mb.DoubleCountMinSketch(1 << 10, 4, hfb, ctx=ctx)
+    with pytest.raises(ValueError, match="Widths of a"):
+        mb.DoubleCountMinSketch.cosine(cma, other)
+    empty = mb.DoubleCountMinSketch(1 << 16, 4, hfb, ctx=ctx)
+    assert math.isnan(mb.DoubleCountMinSketch.cosine(cma, empty))
+
+
+def test_pair_cosine_matches_oracle(mb, ctx):
+    rng = np.random.Generator(np.random.PCG64(8))
+    E, d, w, n = 20, 4, 512, 30000
+    ent, key, inc = _events(rng, n, E - 1, 0, 3000)   # entity E-1 stays empty -> NaN
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((E, d, w))
+    orc.bank_update(ref, d, w, a, b, ent, key, inc)
+    bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+    bank.update(ent, key, inc)
+    ea = rng.integers(0, E, 200).astype(np.int64)
+    eb = rng.integers(0, E, 200).astype(np.int64)
+    got = bank.pair_cosine(ea, eb)
+    want = np.array([orc.cm_cosine(ref[x], ref[y], w, d) for x, y in zip(ea, eb)])
+    assert (np.isnan(got) == np.isnan(want)).all()
+    m = ~np.isnan(want)
+    assert np.max(np.abs(got[m] - want[m]) / np.abs(want[m])) < 1e-12
+    bank.close()
+
+
+def test_synth_stream_device_equals_numpy(mb, ctx):
+    import torch
+    from mahout_b200 import synth
+    cdf = synth.zipf_cdf(100000, 1.1)
+    perm = synth.rank_permutation(100000, 3)
+    cd = torch.from_numpy(cdf).cuda()
+    pd = torch.from_numpy(perm).cuda()
+    u, i, p = synth.events_device(ctx, 20240002, 12345, 200001, 943, cd, pd)
+    hu, hi, hp = synth.events_numpy(20240002, 12345, 200001, 943, cdf, perm)
+    assert (u.cpu().numpy() == hu).all() and (i.cpu().numpy() == hi).all()
+    assert (p.cpu().numpy() == hp).all()
+    # Zipf head really is heavy
+    top = perm[0]
+    assert (hi == top).mean() > 0.05
