@@ -190,7 +190,9 @@ def run_ours(args):
     peaks = _peaks()
 
     ctx = mb.Context(local)
-    stream = torch.cuda.current_stream(dev)
+    # one non-default stream carries everything: the library's kernels, NCCL and the timing events
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     n = int(args.events)
     cdf = synth.zipf_cdf(ITEMS, ZIPF_S)
