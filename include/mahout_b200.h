@@ -142,6 +142,72 @@ int mb200_bank_pair_cosine(mb200_bank* bank, const int64_t* ea, const int64_t* e
 int mb200_bank_cross_cosine(mb200_bank* bank_a, const int64_t* ea, mb200_bank* bank_b,
                             const int64_t* eb, int64_t n, double* out, int mem);
 
+/* ---- all-pairs cosine + per-row top-k ----------------------------------------------------- */
+/* Single-GPU convenience: normalise the bank's rows (K2), compute every pair's sketch cosine
+ * -- min over depth of the per-row cosines, DoubleCountMinSketch.cosine -- on the tensor cores
+ * with the top-k fused into the epilogue (K3), merge / re-score (K5).  Keeps, per entity, the k
+ * best under the total order (similarity desc, index asc).  Semantics of RowSimilarityJob with
+ * CosineSimilarity (RowSimilarityJob.java:478-501,515-559; TopElementsQueue.java:26-59): a
+ * similarity is kept iff sim >= threshold and sim > Double.MIN_VALUE; NaN (no comparable row)
+ * never; the diagonal is dropped when exclude_self.  Pass threshold <= 0 for "no threshold"
+ * (RowSimilarityJob.NO_THRESHOLD).
+ * out_idx / out_sim are [entities][k] (unused slots: -1 / 0), out_cnt [entities]. */
+int mb200_bank_cosine_topk(mb200_bank* bank, int32_t k, double threshold, int exclude_self,
+                           int dtype, int precision, int64_t* out_idx, double* out_sim,
+                           int32_t* out_cnt, int mem);
+
+/* Building blocks of the item-sharded multi-GPU path (one process per GPU; the all-gather of
+ * the normalised rows between the two calls is the caller's NCCL collective).  All pointers
+ * are DEVICE pointers.
+ *
+ * Normalised rows: rows16 is [d][rows][ld] 16-bit elements, ld = mb200_row_ld(width), holding
+ * x / ||x||_2 * 2^12 (F16) or x / ||x||_2 (BF16), zero padded to ld.  valid is
+ * [d][mb200_valid_words(rows)] uint32 bit masks: bit e set <=> sketch row (e, depth) has a
+ * non-zero norm (rows with zero denominator are skipped by the reference,
+ * DoubleCountMinSketch.java:138). */
+int64_t mb200_row_ld(int32_t width);
+int64_t mb200_valid_words(int64_t rows);
+int mb200_bank_normalize(mb200_bank* bank, int dtype, void* rows16, uint32_t* valid);
+
+typedef struct mb200_cosine_args {
+  /* A side: the entities this GPU answers for */
+  const void* a_rows;      /* [d][a_count][ld] */
+  const uint32_t* a_valid; /* [d][valid_words(a_count)] */
+  int64_t a_count;
+  int64_t a_id_mul, a_id_off; /* global index of local row r = r * a_id_mul + a_id_off */
+  /* B side: b_blocks gathered blocks of b_count rows each, block g laid out [d][b_count][ld] at
+   * b_rows + g * d * b_count * ld (what all_gather_into_tensor of the shards produces) */
+  const void* b_rows;
+  const uint32_t* b_valid; /* [b_blocks][d][valid_words(b_count)] */
+  int64_t b_count;
+  int32_t b_blocks;
+  int64_t b_id_mul, b_id_add; /* global index of row l of block g = l * b_id_mul + g * b_id_add */
+  int32_t depth, width;
+  int32_t dtype, precision;
+  int32_t k;
+  double threshold;
+  int32_t exclude_self;
+  int32_t block_n; /* 0 = auto; N tile of the tensor-core kernel (128 or 256) */
+  /* MB200_PRECISION_RESCORED only: the raw fixed-point counters the candidates are re-scored
+   * from, a_counters [a_count][d][width], b_counters [b_blocks][b_count][d][width] */
+  const int64_t* a_counters;
+  const int64_t* b_counters;
+  /* outputs (device): [a_count][k], [a_count][k], [a_count] */
+  int64_t* out_idx;
+  double* out_sim;
+  int32_t* out_cnt;
+  /* debug / parity: if non-NULL the tensor-core similarities (after min over depth, NaN where no
+   * row was comparable) are also written densely, [a_count][dense_ld] floats, column = position
+   * of the B row (block g, row l) -> g * tiles_per_block * block_n + l */
+  float* dense_out;
+  int64_t dense_ld;
+} mb200_cosine_args;
+
+int mb200_cosine_topk(mb200_ctx* ctx, const mb200_cosine_args* args);
+/* rows whose top-k could not be certified from the tensor-core candidates and went through the
+ * exact full-row path during the last mb200_cosine_topk / mb200_bank_cosine_topk on ctx */
+int mb200_cosine_last_fallback_rows(mb200_ctx* ctx, int64_t* rows);
+
 #ifdef __cplusplus
 }
 #endif

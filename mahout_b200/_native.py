@@ -39,6 +39,21 @@ class InexactError(NativeError):
 
 i64, i32, f64, vp = C.c_int64, C.c_int32, C.c_double, C.c_void_p
 
+class CosineArgs(C.Structure):
+    """struct mb200_cosine_args (include/mahout_b200.h)."""
+    _fields_ = [
+        ("a_rows", C.c_void_p), ("a_valid", C.c_void_p), ("a_count", C.c_int64),
+        ("a_id_mul", C.c_int64), ("a_id_off", C.c_int64),
+        ("b_rows", C.c_void_p), ("b_valid", C.c_void_p), ("b_count", C.c_int64),
+        ("b_blocks", C.c_int32), ("b_id_mul", C.c_int64), ("b_id_add", C.c_int64),
+        ("depth", C.c_int32), ("width", C.c_int32), ("dtype", C.c_int32), ("precision", C.c_int32),
+        ("k", C.c_int32), ("threshold", C.c_double), ("exclude_self", C.c_int32), ("block_n", C.c_int32),
+        ("a_counters", C.c_void_p), ("b_counters", C.c_void_p),
+        ("out_idx", C.c_void_p), ("out_sim", C.c_void_p), ("out_cnt", C.c_void_p),
+        ("dense_out", C.c_void_p), ("dense_ld", C.c_int64),
+    ]
+
+
 _PROTOS = {
     "mb200_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "mb200_destroy": (C.c_int, [vp]),
@@ -68,6 +83,12 @@ _PROTOS = {
     "mb200_bank_query": (C.c_int, [vp, vp, vp, i64, vp, C.c_int]),
     "mb200_bank_pair_cosine": (C.c_int, [vp, vp, vp, i64, vp, C.c_int]),
     "mb200_bank_cross_cosine": (C.c_int, [vp, vp, vp, vp, i64, vp, C.c_int]),
+    "mb200_bank_cosine_topk": (C.c_int, [vp, i32, f64, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int]),
+    "mb200_row_ld": (i64, [i32]),
+    "mb200_valid_words": (i64, [i64]),
+    "mb200_bank_normalize": (C.c_int, [vp, C.c_int, vp, vp]),
+    "mb200_cosine_topk": (C.c_int, [vp, C.POINTER(CosineArgs)]),
+    "mb200_cosine_last_fallback_rows": (C.c_int, [vp, C.POINTER(i64)]),
     # bench / test support (mahout_b200/csrc/synth.h)
     "mb200_synth_events": (C.c_int, [vp, C.c_uint64, i64, i64, i64, vp, i64, vp, vp, vp, vp]),
 }

@@ -1,0 +1,1280 @@
+// cosine.cu -- all-pairs sketch cosine + per-row top-k.
+//
+// Reference semantics:
+//   DoubleCountMinSketch.cosine (DoubleCountMinSketch.java:114-149): per depth row i,
+//     cos_i = AB / (sqrt(AA) * sqrt(BB)); rows with a zero denominator are skipped; the result is
+//     the min over the remaining rows, NaN if none.
+//   RowSimilarityJob with CosineSimilarity (RowSimilarityJob.java:478-501,515-559;
+//     TopElementsQueue.java:26-59): keep sim >= threshold, drop the diagonal, per-row top-k where
+//     a candidate must exceed Double.MIN_VALUE.  Ties: lower index wins (north star).
+//
+// Kernels:
+//   K2 k_normalize   counters -> unit-norm 16-bit rows [d][E][ld] + validity bit masks (HBM-bound)
+//   K3 k_cosine      TMA -> smem -> tcgen05.mma (FP32 accumulators in TMEM); the epilogue warps take
+//                    the running min over depth (kept in TMEM) and select per-row candidates, so the
+//                    similarity matrix never reaches HBM
+//   K5 k_merge       merges the per-(row, column-chunk) candidate lists; k_rescore recomputes the
+//                    kept candidates exactly from the integer counters (bit-equal to the reference's
+//                    FP64 arithmetic) and certifies the top-k; k_exact_rows is the exact full-row
+//                    path for rows that could not be certified
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+// ------------------------------------------------------------------------------------------------
+// constants shared by host and device
+// ------------------------------------------------------------------------------------------------
+static constexpr int BM = 128;            // rows of A per tile (TMEM lanes)
+static constexpr int BK = 64;             // K elements per pipeline stage (one 128-byte swizzle row)
+static constexpr int CAP = 256;           // candidate-list capacity per (row, column chunk, half)
+static constexpr int COS_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+static constexpr float F16_SCALE = 4096.0f;  // rows are stored as x/||x|| * 2^12 in FP16
+
+struct CosParams {
+  const int2* items;        // work items (m block, column chunk)
+  int32_t num_items;
+  int32_t chunk_tiles, total_tiles, tiles_per_block;
+  int32_t depth, kblocks, stages;
+  int64_t a_count;
+  const uint32_t* a_valid;
+  int64_t a_vw;
+  const uint32_t* b_valid;
+  int64_t b_vw;
+  uint32_t a_id_mul, a_id_off, b_id_mul, b_id_add;
+  int32_t exclude_self, nonstrict;
+  float thr_init;
+  int32_t ksel;
+  uint2* lists;             // [item][half][128][CAP] (value bits, index)
+  int32_t* list_cnt;        // [item][half][128]
+  float* list_bound;        // [item][half][128]: every candidate not in the list has value <= bound
+  float* dense_out;
+  int64_t dense_ld;
+  float inv_scale2;
+  uint32_t idesc;
+};
+
+// ------------------------------------------------------------------------------------------------
+// K2: row norms + conversion
+// ------------------------------------------------------------------------------------------------
+template <typename OutT>
+__device__ __forceinline__ OutT to_out(float v);
+template <>
+__device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__ counters, long long E,
+                                                   int d, int W, int ld, float scale,
+                                                   OutT* __restrict__ out, uint32_t* __restrict__ valid,
+                                                   long long vw) {
+  __shared__ double red[8];
+  const long long bid = blockIdx.x;
+  const long long e = bid / d;
+  const int i = (int)(bid % d);
+  const long long* row = counters + (size_t)bid * W;
+  double ss = 0.0;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    double x = (double)row[j];
+    ss += x * x;
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) tot += red[w];
+  const double nrm = sqrt(tot);
+  const double inv = nrm > 0.0 ? (double)scale / nrm : 0.0;
+  OutT* o = out + ((size_t)i * E + e) * ld;
+  for (int j = threadIdx.x; j < ld; j += blockDim.x) {
+    float v = j < W ? (float)((double)row[j] * inv) : 0.0f;
+    o[j] = to_out<OutT>(v);
+  }
+  if (threadIdx.x == 0 && nrm > 0.0) atomicOr(&valid[(size_t)i * vw + (e >> 5)], 1u << (e & 31));
+}
+
+// ------------------------------------------------------------------------------------------------
+// candidate keys: (value desc, index asc) as one descending 64-bit order
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(uint32_t u) { return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u); }
+__device__ __forceinline__ uint32_t ord2f(uint32_t o) { return o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu); }
+__device__ __forceinline__ unsigned long long make_key(uint32_t vbits, uint32_t id) {
+  return ((unsigned long long)f2ord(vbits) << 32) | (unsigned long long)(~id);
+}
+__device__ __forceinline__ uint2 key_entry(unsigned long long k) {
+  return make_uint2(ord2f((uint32_t)(k >> 32)), ~(uint32_t)k);
+}
+
+// Bitonic sort, descending, of 32*NPL keys held NPL per lane; element e = s*32 + lane.
+template <int NPL>
+__device__ __forceinline__ void warp_sort_desc(unsigned long long (&key)[NPL], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * NPL; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int js = j >> 5;
+#pragma unroll
+        for (int s = 0; s < NPL; s++) {
+          if ((s & js) == 0) {
+            const int e = s * 32;  // lane bits do not reach bit k when k > 32... they never matter here
+            const bool desc = (((e) & k) == 0);
+            unsigned long long a = key[s], b = key[s | js];
+            unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+            key[s] = desc ? hi : lo;
+            key[s | js] = desc ? lo : hi;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < NPL; s++) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[s], j);
+          const int e = s * 32 + lane;
+          const bool lower = (lane & j) == 0;
+          const bool desc = ((e & k) == 0);
+          const bool keep_max = (lower == desc);
+          const unsigned long long mx = key[s] > other ? key[s] : other;
+          const unsigned long long mn = key[s] > other ? other : key[s];
+          key[s] = keep_max ? mx : mn;
+        }
+      }
+    }
+  }
+}
+
+// Warp-cooperative compaction of one candidate list: keep the ksel best of its n entries, sorted.
+// Returns (to every lane) the value bits of the ksel-th entry, or 0xFFFFFFFF if n < ksel.
+__device__ __noinline__ uint32_t warp_compact_list(uint2* list, int n, int ksel, int lane) {
+  unsigned long long key[CAP / 32];
+#pragma unroll
+  for (int s = 0; s < CAP / 32; s++) {
+    const int e = s * 32 + lane;
+    key[s] = 0ull;
+    if (e < n) {
+      const uint2 x = __ldcg(list + e);
+      key[s] = make_key(x.x, x.y);
+    }
+  }
+  warp_sort_desc<CAP / 32>(key, lane);
+  const int keep = n < ksel ? n : ksel;
+  uint32_t kth = 0xFFFFFFFFu;
+#pragma unroll
+  for (int s = 0; s < CAP / 32; s++) {
+    const int e = s * 32 + lane;
+    if (e < keep) __stcg(list + e, key_entry(key[s]));
+    // the ksel-th entry lives in slot s = (ksel-1)/32 of lane (ksel-1)%32
+    const uint32_t v = ord2f((uint32_t)(key[s] >> 32));
+    const uint32_t got = __shfl_sync(0xffffffffu, v, (ksel - 1) & 31);
+    if (s == ((ksel - 1) >> 5) && n >= ksel) kth = got;
+  }
+  return kth;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: Sketch . Sketch^T on tcgen05 with fused min-over-depth and candidate selection
+// ------------------------------------------------------------------------------------------------
+// TMEM columns: ACC_STAGES accumulators of BN FP32 columns, then (HAS_MIN) the running min.
+template <int BN, int ACC_STAGES, bool HAS_MIN>
+__global__ void __launch_bounds__(COS_THREADS, 1)
+k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+         const CosParams p) {
+  static_assert((ACC_STAGES + (HAS_MIN ? 1 : 0)) * BN <= 512, "TMEM budget");
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int MAX_STAGES = 8;
+  constexpr int HALF = BN / 2;        // columns per epilogue thread
+  constexpr int CHUNKS = HALF / 32;   // 32-column TMEM loads per thread per step
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_tfull[ACC_STAGES];
+  __shared__ __align__(8) uint64_t bar_tempty[ACC_STAGES];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stages = p.stages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; s++) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < ACC_STAGES; s++) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 8);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tmem_base_slot), 512);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one elected lane) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+        const int2 it = p.items[w];
+        const int t0 = it.y * p.chunk_tiles;
+        const int t1 = min(p.total_tiles, t0 + p.chunk_tiles);
+        for (int t = t0; t < t1; t++) {
+          const int g = t / p.tiles_per_block;
+          const int l0 = (t - g * p.tiles_per_block) * BN;
+          for (int dep = 0; dep < p.depth; dep++) {
+            for (int kb = 0; kb < p.kblocks; kb++) {
+              mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+              const uint32_t full = smem_u32(&bar_full[stage]);
+              const uint32_t sa = smem_base + (uint32_t)stage * STAGE_BYTES;
+              mbar_expect_tx(full, STAGE_BYTES);
+              tma_load_3d(sa, &tmA, full, kb * BK, it.x * BM, dep);
+              tma_load_4d(sa + A_BYTES, &tmB, full, kb * BK, l0, dep, g);
+              if (++stage == stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t q = 0;  // accumulation steps issued by this CTA
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+      const int2 it = p.items[w];
+      const int t0 = it.y * p.chunk_tiles;
+      const int t1 = min(p.total_tiles, t0 + p.chunk_tiles);
+      for (int t = t0; t < t1; t++) {
+        for (int dep = 0; dep < p.depth; dep++, q++) {
+          const uint32_t as = q % ACC_STAGES;
+          const uint32_t aphase = (q / ACC_STAGES) & 1u;
+          mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
+          fence_after_sync();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          for (int kb = 0; kb < p.kblocks; kb++) {
+            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            fence_after_sync();
+            if (lane == 0) {
+              const uint32_t sa = smem_base + (uint32_t)stage * STAGE_BYTES;
+              const uint64_t da = umma_desc_k128(sa);
+              const uint64_t db = umma_desc_k128(sa + A_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / 16; k++) {
+                // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(smem_u32(&bar_empty[stage]));
+              if (kb == p.kblocks - 1) umma_commit(smem_u32(&bar_tfull[as]));
+            }
+            __syncwarp();
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: min over depth + candidate selection =====================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    const int half = ew >> 2;      // column half of the tile this thread scans
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint32_t q = 0;
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+      const int2 it = p.items[w];
+      const int t0 = it.y * p.chunk_tiles;
+      const int t1 = min(p.total_tiles, t0 + p.chunk_tiles);
+      const long long grow = (long long)it.x * BM + row;
+      const bool row_ok = grow < p.a_count;
+      const uint32_t my_id = (row_ok && p.exclude_self) ? (uint32_t)grow * p.a_id_mul + p.a_id_off : 0xFFFFFFFFu;
+      uint32_t rv = 0;  // bit dep set <=> (my row, dep) has a non-zero norm
+      if (row_ok) {
+        for (int dep = 0; dep < p.depth; dep++)
+          rv |= ((__ldg(p.a_valid + (size_t)dep * p.a_vw + (grow >> 5)) >> (grow & 31)) & 1u) << dep;
+      }
+      const size_t slot = ((size_t)w * 2 + half) * BM + row;
+      uint2* list = p.lists + slot * CAP;
+      int cnt = 0;
+      float thr = p.thr_init;
+      float bound = -INFINITY;
+      for (int t = t0; t < t1; t++) {
+        const int g = t / p.tiles_per_block;
+        const int l0 = (t - g * p.tiles_per_block) * BN + half * HALF;
+        for (int dep = 0; dep < p.depth; dep++, q++) {
+          const uint32_t as = q % ACC_STAGES;
+          const uint32_t aphase = (q / ACC_STAGES) & 1u;
+          // column validity of my 32-column chunks (uniform per warp), fetched ahead of the wait
+          uint32_t cm[CHUNKS];
+          const uint32_t* bv = p.b_valid + ((size_t)g * p.depth + dep) * p.b_vw + (l0 >> 5);
+#pragma unroll
+          for (int c = 0; c < CHUNKS; c++) cm[c] = __ldg(bv + c);
+          const bool my_valid = (rv >> dep) & 1u;
+          const bool last = dep == p.depth - 1;
+          mbar_wait(smem_u32(&bar_tfull[as]), aphase);
+          fence_after_sync();
+          const uint32_t acc_addr = tmem_base + lane_addr + as * BN + half * HALF;
+          const uint32_t min_addr = tmem_base + lane_addr + ACC_STAGES * BN + half * HALF;
+#pragma unroll
+          for (int c = 0; c < CHUNKS; c++) {
+            uint32_t v[32];
+            uint32_t m[32];
+            tmem_ld32(acc_addr + c * 32, v);
+            if (HAS_MIN && dep > 0) tmem_ld32(min_addr + c * 32, m);
+            tmem_wait_ld();
+            const uint32_t cmask = my_valid ? cm[c] : 0u;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              float x = ((cmask >> j) & 1u) ? __uint_as_float(v[j]) : __int_as_float(0x7FC00000);
+              // fminf returns the non-NaN operand: NaN is the identity of the running min
+              if (HAS_MIN && dep > 0) x = fminf(__uint_as_float(m[j]), x);
+              v[j] = __float_as_uint(x);
+            }
+            if (!last) {
+              if (HAS_MIN) tmem_st32(min_addr + c * 32, v);
+            } else {
+              if (p.dense_out != nullptr && row_ok) {
+                float* dst = p.dense_out + (size_t)grow * p.dense_ld + (size_t)t * BN + half * HALF + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j++) dst[j] = __uint_as_float(v[j]) * p.inv_scale2;
+              }
+              const uint32_t id0 = (uint32_t)(l0 + c * 32) * p.b_id_mul + (uint32_t)g * p.b_id_add;
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                const float x = __uint_as_float(v[j]);
+                if (x > thr) {  // NaN never passes
+                  const uint32_t id = id0 + (uint32_t)j * p.b_id_mul;
+                  if (id != my_id) {
+                    __stcg(list + cnt, make_uint2(v[j], id));
+                    cnt++;
+                  }
+                }
+              }
+              // keep 32 free slots for the next chunk; compaction is warp-cooperative
+              unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+              while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                __syncwarp();
+                uint2* l2 = (uint2*)__shfl_sync(0xffffffffu, (unsigned long long)list, src);
+                const int n2 = __shfl_sync(0xffffffffu, cnt, src);
+                const uint32_t kth = warp_compact_list(l2, n2, p.ksel, lane);
+                if (lane == src) {
+                  cnt = min(n2, p.ksel);
+                  if (kth != 0xFFFFFFFFu) {
+                    const float kv = __uint_as_float(kth);
+                    bound = fmaxf(bound, kv);
+                    // ties at the k-th value may still win on the index unless the scan order is
+                    // index-monotone: admit them by stepping the threshold one ulp down
+                    thr = p.nonstrict ? __uint_as_float(f2ord(kth) > 0 ? ord2f(f2ord(kth) - 1) : kth) : kv;
+                    thr = fmaxf(thr, p.thr_init);
+                  }
+                }
+                __syncwarp();
+              }
+            }
+          }
+          if (HAS_MIN && !last) tmem_wait_st();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+        }
+      }
+      // final compaction: sorted, at most ksel entries per list
+      {
+        unsigned need = __ballot_sync(0xffffffffu, cnt > 0);
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          __syncwarp();
+          uint2* l2 = (uint2*)__shfl_sync(0xffffffffu, (unsigned long long)list, src);
+          const int n2 = __shfl_sync(0xffffffffu, cnt, src);
+          const uint32_t kth = warp_compact_list(l2, n2, p.ksel, lane);
+          if (lane == src) {
+            if (n2 > p.ksel && kth != 0xFFFFFFFFu) bound = fmaxf(bound, __uint_as_float(kth));
+            cnt = min(n2, p.ksel);
+          }
+          __syncwarp();
+        }
+        p.list_cnt[slot] = cnt;
+        p.list_bound[slot] = bound;
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5a: merge the candidate lists of one row (all column chunks, both halves); one warp per row.
+// TENSOR precision: write the top-k straight from the tensor-core values.
+// RESCORED: write the merged candidates for k_rescore.
+// ------------------------------------------------------------------------------------------------
+struct MergeParams {
+  const uint2* lists;
+  const int32_t* list_cnt;
+  const float* list_bound;
+  const int32_t* slot_of;  // [num_m][S] -> item slot
+  int32_t S;
+  int64_t a_count;
+  int32_t ksel, k;
+  double threshold;        // admitted iff sim >= threshold && sim > 0
+  float inv_scale2;
+  int32_t rescored;
+  // TENSOR outputs
+  long long* out_idx;
+  double* out_sim;
+  int32_t* out_cnt;
+  // RESCORED outputs
+  uint32_t* cand_id;       // [a_count][CAP]
+  int32_t* cand_cnt;       // [a_count]
+  float* cand_bound;       // [a_count] (scaled tensor value; -inf = nothing was ever dropped)
+};
+
+__global__ void __launch_bounds__(256) k_merge(const MergeParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= p.a_count) return;
+  const int m = (int)(r / BM), rr = (int)(r % BM);
+  unsigned long long key[2 * CAP / 32];
+#pragma unroll
+  for (int s = 0; s < 2 * CAP / 32; s++) key[s] = 0ull;
+  float bound = -INFINITY;
+  for (int s = 0; s < p.S; s++) {
+    const int w = p.slot_of[(size_t)m * p.S + s];
+    for (int h = 0; h < 2; h++) {
+      const size_t slot = ((size_t)w * 2 + h) * BM + rr;
+      const int n = p.list_cnt[slot];
+      bound = fmaxf(bound, p.list_bound[slot]);
+      const uint2* list = p.lists + slot * CAP;
+#pragma unroll
+      for (int u = 0; u < CAP / 32; u++) {
+        const int e = u * 32 + lane;
+        unsigned long long kk = 0ull;
+        if (e < n) {
+          const uint2 x = __ldcg(list + e);
+          kk = make_key(x.x, x.y);
+        }
+        key[CAP / 32 + u] = kk;
+      }
+      warp_sort_desc<2 * CAP / 32>(key, lane);
+      // truncate to ksel; remember the best value dropped here
+#pragma unroll
+      for (int u = 0; u < CAP / 32; u++) {
+        const int e = u * 32 + lane;
+        const uint32_t v = ord2f((uint32_t)(key[u] >> 32));
+        const unsigned long long kfirst = __shfl_sync(0xffffffffu, key[u], p.ksel & 31);
+        if (u == (p.ksel >> 5) && p.ksel < CAP && kfirst != 0ull)
+          bound = fmaxf(bound, __uint_as_float(ord2f((uint32_t)(kfirst >> 32))));
+        (void)v;
+        if (e >= p.ksel) key[u] = 0ull;
+      }
+    }
+  }
+  // key[0 .. CAP/32) now holds the row's best <= ksel candidates, sorted (value desc, index asc)
+  if (p.rescored) {
+    int n = 0;
+#pragma unroll
+    for (int u = 0; u < CAP / 32; u++) {
+      const int e = u * 32 + lane;
+      const bool have = key[u] != 0ull;
+      p.cand_id[(size_t)r * CAP + e] = have ? ~(uint32_t)key[u] : 0xFFFFFFFFu;
+      n += __popc(__ballot_sync(0xffffffffu, have));
+    }
+    if (lane == 0) {
+      p.cand_cnt[r] = n;
+      p.cand_bound[r] = bound;
+    }
+    return;
+  }
+  int admitted = 0;
+#pragma unroll
+  for (int u = 0; u < CAP / 32; u++) {
+    const int e = u * 32 + lane;
+    const uint2 x = key_entry(key[u]);
+    const double sim = (double)(__uint_as_float(x.x) * p.inv_scale2);
+    const bool ok = key[u] != 0ull && e < p.k && sim >= p.threshold && sim > 0.0;
+    if (e < p.k) {
+      p.out_idx[(size_t)r * p.k + e] = ok ? (long long)x.y : -1LL;
+      p.out_sim[(size_t)r * p.k + e] = ok ? sim : 0.0;
+    }
+    admitted += __popc(__ballot_sync(0xffffffffu, ok));
+  }
+  if (lane == 0) p.out_cnt[r] = admitted;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b: exact re-score of the merged candidates.  One CTA per row.
+//
+// The reference sums xa*xa, xb*xb, xa*xb sequentially in FP64.  Counters are integers (in quanta),
+// so while sum|xa*xb| < 2^53 every partial sum is an exactly representable integer and the
+// order of summation cannot matter: the integer dot products below reproduce the reference's
+// three sums bit for bit, and sqrt / mul / div are IEEE-correct on both sides.  Rows where that
+// precondition fails are flagged and go through k_exact_rows (sequential FP64).
+// ------------------------------------------------------------------------------------------------
+struct RescoreParams {
+  const long long* a_counters;  // [a_count][d][W]
+  const long long* b_counters;  // [blocks][b_count][d][W]
+  int64_t a_count, b_count;
+  int32_t d, W, blocks;
+  uint32_t a_id_mul, a_id_off, b_id_mul, b_id_add;
+  const uint32_t* cand_id;
+  const int32_t* cand_cnt;
+  const float* cand_bound;
+  float inv_scale2;
+  float eps_rel;               // relative error bound of the tensor-core values
+  int32_t k;
+  double threshold;
+  long long* out_idx;
+  double* out_sim;
+  int32_t* out_cnt;
+  int32_t* row_flag;           // [a_count]: 1 = needs the exact full-row path
+  int32_t* flag_count;
+};
+
+__device__ __forceinline__ void b_locate(const RescoreParams& p, uint32_t id, long long& g, long long& l) {
+  if (p.b_id_add == 1 && p.b_id_mul != 1) {  // interleaved shards: id = l * G + g
+    g = id % p.b_id_mul;
+    l = id / p.b_id_mul;
+  } else {                                   // contiguous blocks: id = l + g * b_count
+    g = p.b_id_add ? id / p.b_id_add : 0;
+    l = id - g * p.b_id_add;
+  }
+}
+
+#define TWO53 9007199254740992.0
+#define JAVA_MAX_DOUBLE 1.7976931348623157e308
+
+__global__ void __launch_bounds__(256) k_rescore(const RescoreParams p) {
+  extern __shared__ long long s_a[];          // one depth row of A: W counters
+  __shared__ double s_min[CAP];                // running min of cos_i per candidate
+  __shared__ double s_red[8];
+  __shared__ long long s_redi[8];
+  __shared__ int s_bad;
+  const long long r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.cand_cnt[r];
+  for (int c = tid; c < CAP; c += blockDim.x) s_min[c] = JAVA_MAX_DOUBLE;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  const long long* arow = p.a_counters + (size_t)r * p.d * p.W;
+  for (int i = 0; i < p.d && n > 0; i++) {
+    // A row of this depth -> smem, AA exactly
+    long long aa = 0;
+    double amag = 0.0;
+    int bad = 0;
+    for (int j = tid; j < p.W; j += blockDim.x) {
+      const long long x = arow[(size_t)i * p.W + j];
+      s_a[j] = x;
+      if (x >= (1LL << 31) || x <= -(1LL << 31)) bad = 1;
+      aa += x * x;
+      amag += (double)x * (double)x;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      aa += __shfl_xor_sync(0xffffffffu, aa, o);
+      amag += __shfl_xor_sync(0xffffffffu, amag, o);
+    }
+    if (lane == 0) {
+      s_redi[warp] = aa;
+      s_red[warp] = amag;
+    }
+    if (bad) s_bad = 1;
+    __syncthreads();
+    long long AA = 0;
+    double AAm = 0.0;
+    for (int w = 0; w < 8; w++) {
+      AA += s_redi[w];
+      AAm += s_red[w];
+    }
+    if (AAm >= TWO53 * 0.5 && tid == 0) s_bad = 1;
+    const double sqa = sqrt((double)AA);
+    for (int c = warp; c < n; c += 8) {
+      const uint32_t id = p.cand_id[(size_t)r * CAP + c];
+      long long g, l;
+      b_locate(p, id, g, l);
+      const long long* brow = p.b_counters + (((size_t)g * p.b_count + l) * p.d + i) * p.W;
+      long long bb = 0, ab = 0;
+      double mag = 0.0;
+      int badb = 0;
+      for (int j = lane; j < p.W; j += 32) {
+        const long long y = __ldg(brow + j);
+        const long long x = s_a[j];
+        if (y >= (1LL << 31) || y <= -(1LL << 31)) badb = 1;
+        bb += y * y;
+        ab += x * y;
+        mag += fabs((double)y * (double)y) + fabs((double)x * (double)y);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        bb += __shfl_xor_sync(0xffffffffu, bb, o);
+        ab += __shfl_xor_sync(0xffffffffu, ab, o);
+        mag += __shfl_xor_sync(0xffffffffu, mag, o);
+        badb |= __shfl_xor_sync(0xffffffffu, badb, o);
+      }
+      if (lane == 0) {
+        if (badb || mag >= TWO53 * 0.5) s_bad = 1;
+        const double den = __dmul_rn(sqa, sqrt((double)bb));
+        if (den != 0.0) {
+          const double cs = __ddiv_rn((double)ab, den);
+          s_min[c] = cs < s_min[c] ? cs : s_min[c];  // Math.min, no NaN possible here
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // warp 0: order the candidates by (exact sim desc, index asc), certify, write the top-k
+  if (warp != 0) return;
+  double sim[CAP / 32];
+  uint32_t idv[CAP / 32];
+#pragma unroll
+  for (int u = 0; u < CAP / 32; u++) {
+    const int c = u * 32 + lane;
+    sim[u] = -INFINITY;
+    idv[u] = 0xFFFFFFFFu;
+    if (c < n) {
+      const double s = s_min[c];
+      idv[u] = p.cand_id[(size_t)r * CAP + c];
+      // admitted iff not NaN (no comparable row), >= threshold and > Double.MIN_VALUE
+      if (s != JAVA_MAX_DOUBLE && s >= p.threshold && s > 4.9e-324) sim[u] = s;
+    }
+  }
+  // bitonic sort on (sim desc, id asc) with 96-bit keys
+#pragma unroll
+  for (int k = 2; k <= CAP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int js = j >> 5;
+#pragma unroll
+        for (int s = 0; s < CAP / 32; s++) {
+          if ((s & js) == 0) {
+            const bool desc = (((s * 32) & k) == 0);
+            const bool a_first = sim[s] > sim[s | js] || (sim[s] == sim[s | js] && idv[s] <= idv[s | js]);
+            if (a_first != desc) {
+              double ts = sim[s]; sim[s] = sim[s | js]; sim[s | js] = ts;
+              uint32_t ti = idv[s]; idv[s] = idv[s | js]; idv[s | js] = ti;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < CAP / 32; s++) {
+          const double os = __shfl_xor_sync(0xffffffffu, sim[s], j);
+          const uint32_t oi = __shfl_xor_sync(0xffffffffu, idv[s], j);
+          const int e = s * 32 + lane;
+          const bool lower = (lane & j) == 0;
+          const bool desc = ((e & k) == 0);
+          const bool mine_first = sim[s] > os || (sim[s] == os && idv[s] <= oi);
+          const bool keep_first = (lower == desc);
+          if (mine_first != keep_first) {
+            sim[s] = os;
+            idv[s] = oi;
+          }
+        }
+      }
+    }
+  }
+  int admitted = 0;
+  double kth = -INFINITY;  // exact value of the k-th result (or -inf if fewer than k)
+#pragma unroll
+  for (int u = 0; u < CAP / 32; u++) {
+    const int e = u * 32 + lane;
+    const bool ok = sim[u] > -INFINITY && e < p.k;
+    if (e < p.k) {
+      p.out_idx[(size_t)r * p.k + e] = ok ? (long long)idv[u] : -1LL;
+      p.out_sim[(size_t)r * p.k + e] = ok ? sim[u] : 0.0;
+    }
+    admitted += __popc(__ballot_sync(0xffffffffu, ok));
+    const double v = __shfl_sync(0xffffffffu, sim[u], (p.k - 1) & 31);
+    if (u == ((p.k - 1) >> 5)) kth = v;
+  }
+  if (lane == 0) {
+    p.out_cnt[r] = admitted;
+    // every candidate that is not in the merged list has tensor value <= bound, hence exact value
+    // <= bound * (1 + eps) (+ eps absolute for values near zero).  The top-k is certain iff the
+    // k-th exact value clears that.
+    const float b = p.cand_bound[r];
+    int flag = s_bad;
+    if (b > -INFINITY) {
+      const double ub = (double)(b * p.inv_scale2) * (1.0 + (double)p.eps_rel) + (double)p.eps_rel * 1e-3;
+      if (!(kth > ub)) flag = 1;
+    }
+    p.row_flag[r] = flag;
+    if (flag) atomicAdd(p.flag_count, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5c: exact full-row path for flagged rows: every column in sequential FP64, exactly the loop of
+// DoubleCountMinSketch.cosine.  One CTA per flagged row, one thread per column (strided).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_exact_rows(const RescoreParams p, const int32_t* flagged_rows,
+                                                    double inv_qa, double inv_qb, double* scratch,
+                                                    int64_t total_cols) {
+  const long long r = flagged_rows[blockIdx.x];
+  const long long* arow = p.a_counters + (size_t)r * p.d * p.W;
+  const uint32_t my_id = (uint32_t)r * p.a_id_mul + p.a_id_off;
+  double* out = scratch + (size_t)blockIdx.x * total_cols;
+  for (long long col = threadIdx.x; col < total_cols; col += blockDim.x) {
+    const long long g = col / p.b_count, l = col % p.b_count;
+    const long long* brow = p.b_counters + ((size_t)g * p.b_count + l) * p.d * p.W;
+    double mn = JAVA_MAX_DOUBLE;
+    for (int i = 0; i < p.d; i++) {
+      double va = 0.0, vb = 0.0, vab = 0.0;
+      for (int j = 0; j < p.W; j++) {
+        const double xa = (double)arow[(size_t)i * p.W + j] * inv_qa;
+        const double xb = (double)brow[(size_t)i * p.W + j] * inv_qb;
+        va = __dadd_rn(va, __dmul_rn(xa, xa));
+        vb = __dadd_rn(vb, __dmul_rn(xb, xb));
+        vab = __dadd_rn(vab, __dmul_rn(xa, xb));
+      }
+      const double den = __dmul_rn(sqrt(va), sqrt(vb));
+      if (den != 0.0) {
+        const double cs = __ddiv_rn(vab, den);
+        mn = cs < mn ? cs : mn;
+      }
+    }
+    (void)my_id;
+    out[col] = mn == JAVA_MAX_DOUBLE ? nan("") : mn;
+  }
+}
+
+// top-k of one flagged row's exact similarities (scratch), one CTA per row: k rounds of arg-max
+__global__ void __launch_bounds__(256) k_exact_topk(const RescoreParams p, const int32_t* flagged_rows,
+                                                    const double* scratch, int64_t total_cols,
+                                                    int exclude_self) {
+  __shared__ double s_v[256];
+  __shared__ uint32_t s_i[256];
+  const long long r = flagged_rows[blockIdx.x];
+  const uint32_t my_id = exclude_self ? (uint32_t)r * p.a_id_mul + p.a_id_off : 0xFFFFFFFFu;
+  const double* v = scratch + (size_t)blockIdx.x * total_cols;
+  double last_v = INFINITY;
+  uint32_t last_id = 0;
+  bool first = true;
+  int admitted = 0;
+  for (int t = 0; t < p.k; t++) {
+    double best = -INFINITY;
+    uint32_t best_id = 0xFFFFFFFFu;
+    for (long long col = threadIdx.x; col < total_cols; col += blockDim.x) {
+      const long long g = col / p.b_count, l = col % p.b_count;
+      const uint32_t id = (uint32_t)l * p.b_id_mul + (uint32_t)g * p.b_id_add;
+      const double s = v[col];
+      if (!(s >= p.threshold) || !(s > 4.9e-324) || id == my_id) continue;  // NaN fails the first test
+      // strictly after (last_v, last_id) in the order (sim desc, id asc)
+      if (!first && !(s < last_v || (s == last_v && id > last_id))) continue;
+      if (s > best || (s == best && id < best_id)) {
+        best = s;
+        best_id = id;
+      }
+    }
+    s_v[threadIdx.x] = best;
+    s_i[threadIdx.x] = best_id;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        const double ov = s_v[threadIdx.x + o];
+        const uint32_t oi = s_i[threadIdx.x + o];
+        if (ov > s_v[threadIdx.x] || (ov == s_v[threadIdx.x] && oi < s_i[threadIdx.x])) {
+          s_v[threadIdx.x] = ov;
+          s_i[threadIdx.x] = oi;
+        }
+      }
+      __syncthreads();
+    }
+    best = s_v[0];
+    best_id = s_i[0];
+    __syncthreads();
+    const bool ok = best > -INFINITY;
+    if (threadIdx.x == 0) {
+      p.out_idx[(size_t)r * p.k + t] = ok ? (long long)best_id : -1LL;
+      p.out_sim[(size_t)r * p.k + t] = ok ? best : 0.0;
+    }
+    if (ok) {
+      admitted++;
+      last_v = best;
+      last_id = best_id;
+      first = false;
+    } else {
+      // nothing left: fill the rest
+      for (int u = t + 1 + threadIdx.x; u < p.k; u += blockDim.x) {
+        p.out_idx[(size_t)r * p.k + u] = -1LL;
+        p.out_sim[(size_t)r * p.k + u] = 0.0;
+      }
+      break;
+    }
+  }
+  if (threadIdx.x == 0) p.out_cnt[r] = admitted;
+}
+
+__global__ void k_collect_flagged(const int32_t* row_flag, long long n, int32_t* flagged, int32_t* count) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n && row_flag[r]) flagged[atomicAdd(count, 1)] = (int32_t)r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn(mb200_ctx* ctx) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+    mb200_fail(ctx, MB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver (%s)",
+               e != cudaSuccess ? cudaGetErrorString(e) : "symbol not found");
+    return nullptr;
+  }
+  fn = (EncodeTiledFn)ptr;
+  return fn;
+}
+
+static int make_tmap(mb200_ctx* ctx, CUtensorMap* tm, int dtype, const void* base, int rank,
+                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn(ctx);
+  if (!fn) return MB200_ERR_CUDA;
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; i++) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; i++) gs[i] = strides_bytes[i];
+  CUresult r = fn(tm, dtype == MB200_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return mb200_fail(ctx, MB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+  return MB200_OK;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(mb200_ctx* ctx, size_t bytes) {
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return mb200_fail(ctx, MB200_ERR_OOM, "cosine: cannot allocate %zu bytes of workspace: %s", bytes,
+                        cudaGetErrorString(e));
+    }
+    return MB200_OK;
+  }
+};
+
+template <int BN, int ACC, bool HM>
+static int launch_cosine(mb200_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, CosParams& p,
+                         int grid) {
+  const size_t stage_bytes = (size_t)(BM + BN) * BK * 2;
+  int stages = (int)((ctx->smem_optin - 2048 - 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "cosine: not enough shared memory for 2 stages");
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  MB_CUDA(ctx, cudaFuncSetAttribute(k_cosine<BN, ACC, HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_cosine<BN, ACC, HM><<<grid, COS_THREADS, smem, ctx->stream>>>(tmA, tmB, p);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MB200_OK;
+}
+
+static int64_t g_last_fallback_rows = 0;
+
+extern "C" {
+
+int64_t mb200_row_ld(int32_t width) { return ((int64_t)width + BK - 1) / BK * BK; }
+int64_t mb200_valid_words(int64_t rows) { return (rows + 255) / 256 * 8; }
+
+int mb200_cosine_last_fallback_rows(mb200_ctx* ctx, int64_t* rows) {
+  if (!ctx || !rows) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_last_fallback_rows: NULL argument");
+  *rows = g_last_fallback_rows;
+  return MB200_OK;
+}
+
+static int normalize_locked(mb200_bank* bk, int dtype, void* rows16, uint32_t* valid) {
+  mb200_ctx* ctx = bk->ctx;
+  if (dtype != MB200_DTYPE_F16 && dtype != MB200_DTYPE_BF16)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_normalize: dtype must be MB200_DTYPE_F16 or _BF16");
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t vw = mb200_valid_words(bk->E);
+  const int ld = (int)mb200_row_ld(bk->W);
+  MB_CUDA(ctx, cudaMemsetAsync(valid, 0, (size_t)bk->d * vw * sizeof(uint32_t), ctx->stream));
+  const long long blocks = bk->E * (long long)bk->d;
+  if (blocks > 0x7FFFFFFFLL) return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_bank_normalize: too many sketch rows");
+  {
+    ProfScope prof(ctx, MB200_K_NORMALIZE);
+    if (dtype == MB200_DTYPE_F16)
+      k_normalize<__half><<<(unsigned)blocks, 256, 0, ctx->stream>>>(bk->counters, bk->E, bk->d, bk->W, ld, F16_SCALE,
+                                                                     (__half*)rows16, valid, vw);
+    else
+      k_normalize<__nv_bfloat16><<<(unsigned)blocks, 256, 0, ctx->stream>>>(bk->counters, bk->E, bk->d, bk->W, ld, 1.0f,
+                                                                            (__nv_bfloat16*)rows16, valid, vw);
+  }
+  ctx->launches++;
+  MB_CUDA(ctx, cudaGetLastError());
+  return MB200_OK;
+}
+
+int mb200_bank_normalize(mb200_bank* bk, int dtype, void* rows16, uint32_t* valid) {
+  if (!bk || !rows16 || !valid) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_normalize: NULL argument");
+  std::lock_guard<std::mutex> g(bk->ctx->mu);
+  return normalize_locked(bk, dtype, rows16, valid);
+}
+
+static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
+  if (!a) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: args is NULL");
+  if (!a->a_rows || !a->a_valid || !a->b_rows || !a->b_valid || !a->out_idx || !a->out_sim || !a->out_cnt)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: NULL pointer argument");
+  if (a->a_count <= 0 || a->b_count <= 0 || a->b_blocks <= 0 || a->depth <= 0 || a->depth > MB200_MAX_DEPTH ||
+      a->width <= 0)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad shape (a_count=%lld b_count=%lld blocks=%d d=%d w=%d)",
+                      (long long)a->a_count, (long long)a->b_count, a->b_blocks, a->depth, a->width);
+  if (a->k <= 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: k must be positive (got %d)", a->k);
+  if (a->dtype != MB200_DTYPE_F16 && a->dtype != MB200_DTYPE_BF16)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad dtype %d", a->dtype);
+  if (a->precision != MB200_PRECISION_TENSOR && a->precision != MB200_PRECISION_RESCORED)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad precision %d", a->precision);
+  const bool rescored = a->precision == MB200_PRECISION_RESCORED;
+  if (rescored && (!a->a_counters || !a->b_counters))
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: MB200_PRECISION_RESCORED needs a_counters and b_counters");
+  const int64_t total_b = a->b_count * a->b_blocks;
+  const int64_t max_id = std::max((a->a_count - 1) * a->a_id_mul + a->a_id_off,
+                                  (a->b_count - 1) * a->b_id_mul + (a->b_blocks - 1) * a->b_id_add);
+  if (a->a_id_mul <= 0 || a->b_id_mul <= 0 || a->a_id_off < 0 || a->b_id_add < 0 || max_id >= 0xFFFFFFFFLL)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: index mapping out of the 32-bit range");
+  const bool contiguous = a->b_id_mul == 1 && (a->b_blocks == 1 || a->b_id_add == a->b_count);
+  const bool interleaved = a->b_id_add == 1 && a->b_id_mul == a->b_blocks && a->b_blocks > 1;
+  if (!contiguous && !interleaved)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG,
+                      "mb200_cosine_topk: B indices must be contiguous blocks (mul=1, add=b_count) or interleaved "
+                      "shards (mul=b_blocks, add=1)");
+  // candidates kept per row: k + margin, at most CAP - 32
+  int margin = rescored ? std::max(14, a->k / 4) : 0;
+  int ksel = a->k + margin;
+  ksel = (ksel + 31) / 32 * 32;
+  if (ksel > CAP - 32) ksel = CAP - 32;
+  if (a->k > ksel)
+    return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_cosine_topk: k = %d exceeds the fused top-k capacity %d", a->k, CAP - 32);
+  const int BN = a->block_n == 128 ? 128 : 256;
+  if (a->block_n != 0 && a->block_n != 128 && a->block_n != 256)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: block_n must be 0, 128 or 256");
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  const int ld = (int)mb200_row_ld(a->width);
+  const int tpb = (int)((a->b_count + BN - 1) / BN);
+  const int T = tpb * a->b_blocks;
+  const int num_m = (int)((a->a_count + BM - 1) / BM);
+  if (a->dense_out && a->dense_ld < (int64_t)T * BN)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: dense_ld must be >= %lld", (long long)T * BN);
+  // column chunks: enough items to fill the SMs in whole waves
+  const int P = ctx->num_sms;
+  int S = 1;
+  {
+    double best = -1.0;
+    const int smax = std::min(T, 32);
+    for (int s = 1; s <= smax; s++) {
+      const long long items = (long long)num_m * s;
+      const long long waves = (items + P - 1) / P;
+      double eff = (double)items / (double)(waves * P);
+      const int ct = (T + s - 1) / s;
+      if (ct < 2 && s > 1) break;
+      // fewer, longer sweeps amortise list handling: only move to more chunks for a clear gain
+      if (eff > best + 0.03) {
+        best = eff;
+        S = s;
+      }
+    }
+  }
+  const int chunk_tiles = (T + S - 1) / S;
+  S = (T + chunk_tiles - 1) / chunk_tiles;
+  const int num_items = num_m * S;
+  // item order: groups of Gm row blocks x all S chunks run together, so the CTAs of one wave share
+  // A blocks and sweep the same B tiles (L2 reuse)
+  const int Gm = std::max(1, P / S);
+  std::vector<int2> items((size_t)num_items);
+  std::vector<int32_t> slot_of((size_t)num_m * S);
+  {
+    int w = 0;
+    for (int m0 = 0; m0 < num_m; m0 += Gm) {
+      const int m1 = std::min(num_m, m0 + Gm);
+      for (int s = 0; s < S; s++)
+        for (int m = m0; m < m1; m++) {
+          items[w] = make_int2(m, s);
+          slot_of[(size_t)m * S + s] = w;
+          w++;
+        }
+    }
+  }
+  DevBuf d_items, d_slot, d_lists, d_cnt, d_bound;
+  MB_CHECK(d_items.alloc(ctx, items.size() * sizeof(int2)));
+  MB_CHECK(d_slot.alloc(ctx, slot_of.size() * sizeof(int32_t)));
+  const size_t nlists = (size_t)num_items * 2 * BM;
+  MB_CHECK(d_lists.alloc(ctx, nlists * CAP * sizeof(uint2)));
+  MB_CHECK(d_cnt.alloc(ctx, nlists * sizeof(int32_t)));
+  MB_CHECK(d_bound.alloc(ctx, nlists * sizeof(float)));
+  MB_CUDA(ctx, cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  MB_CUDA(ctx, cudaMemcpyAsync(d_slot.p, slot_of.data(), slot_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+  // tensor maps
+  alignas(64) CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[3] = {(uint64_t)ld, (uint64_t)a->a_count, (uint64_t)a->depth};
+    const uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)a->a_count * ld * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    MB_CHECK(make_tmap(ctx, &tmA, a->dtype, a->a_rows, 3, dims, str, box));
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)ld, (uint64_t)a->b_count, (uint64_t)a->depth, (uint64_t)a->b_blocks};
+    const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)a->b_count * ld * 2, (uint64_t)a->depth * a->b_count * ld * 2};
+    const uint32_t box[4] = {BK, (uint32_t)BN, 1, 1};
+    MB_CHECK(make_tmap(ctx, &tmB, a->dtype, a->b_rows, 4, dims, str, box));
+  }
+
+  const float scale = a->dtype == MB200_DTYPE_F16 ? F16_SCALE : 1.0f;
+  const float scale2 = scale * scale;
+  const float eps_rel = a->dtype == MB200_DTYPE_F16 ? 0x1.0p-10f : 0x1.0p-6f;
+  CosParams p;
+  memset(&p, 0, sizeof(p));
+  p.items = (const int2*)d_items.p;
+  p.num_items = num_items;
+  p.chunk_tiles = chunk_tiles;
+  p.total_tiles = T;
+  p.tiles_per_block = tpb;
+  p.depth = a->depth;
+  p.kblocks = ld / BK;
+  p.a_count = a->a_count;
+  p.a_valid = a->a_valid;
+  p.a_vw = mb200_valid_words(a->a_count);
+  p.b_valid = a->b_valid;
+  p.b_vw = mb200_valid_words(a->b_count);
+  p.a_id_mul = (uint32_t)a->a_id_mul;
+  p.a_id_off = (uint32_t)a->a_id_off;
+  p.b_id_mul = (uint32_t)a->b_id_mul;
+  p.b_id_add = (uint32_t)a->b_id_add;
+  p.exclude_self = a->exclude_self ? 1 : 0;
+  p.nonstrict = (a->b_blocks > 1 && interleaved) ? 1 : 0;
+  {
+    const double thr = a->threshold > 0.0 ? a->threshold : 0.0;
+    const double slack = rescored ? (1.0 - (double)eps_rel) : (1.0 - 1e-6);
+    p.thr_init = (float)(thr * slack * (double)scale2);
+    if (thr > 0.0) p.thr_init = nextafterf(p.thr_init, -INFINITY);
+  }
+  p.ksel = ksel;
+  p.lists = (uint2*)d_lists.p;
+  p.list_cnt = (int32_t*)d_cnt.p;
+  p.list_bound = (float*)d_bound.p;
+  p.dense_out = a->dense_out;
+  p.dense_ld = a->dense_ld;
+  p.inv_scale2 = 1.0f / scale2;
+  p.idesc = umma_idesc_f16(a->dtype == MB200_DTYPE_BF16 ? 1 : 0, BM, BN);
+  const int grid = std::min(num_items, P);
+  {
+    ProfScope prof(ctx, MB200_K_COSINE);
+    if (a->depth == 1) {
+      if (BN == 256) MB_CHECK((launch_cosine<256, 2, false>(ctx, tmA, tmB, p, grid)));
+      else MB_CHECK((launch_cosine<128, 2, false>(ctx, tmA, tmB, p, grid)));
+    } else {
+      if (BN == 256) MB_CHECK((launch_cosine<256, 1, true>(ctx, tmA, tmB, p, grid)));
+      else MB_CHECK((launch_cosine<128, 2, true>(ctx, tmA, tmB, p, grid)));
+    }
+  }
+  ctx->launches++;
+
+  // merge (+ re-score)
+  DevBuf d_cand, d_ccnt, d_cbound, d_flag, d_fcount;
+  MergeParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.lists = p.lists;
+  mp.list_cnt = p.list_cnt;
+  mp.list_bound = p.list_bound;
+  mp.slot_of = (const int32_t*)d_slot.p;
+  mp.S = S;
+  mp.a_count = a->a_count;
+  mp.ksel = ksel;
+  mp.k = a->k;
+  mp.threshold = a->threshold > 0.0 ? a->threshold : 0.0;
+  mp.inv_scale2 = p.inv_scale2;
+  mp.rescored = rescored ? 1 : 0;
+  mp.out_idx = (long long*)a->out_idx;
+  mp.out_sim = a->out_sim;
+  mp.out_cnt = a->out_cnt;
+  if (rescored) {
+    MB_CHECK(d_cand.alloc(ctx, (size_t)a->a_count * CAP * sizeof(uint32_t)));
+    MB_CHECK(d_ccnt.alloc(ctx, (size_t)a->a_count * sizeof(int32_t)));
+    MB_CHECK(d_cbound.alloc(ctx, (size_t)a->a_count * sizeof(float)));
+    MB_CHECK(d_flag.alloc(ctx, (size_t)a->a_count * sizeof(int32_t)));
+    MB_CHECK(d_fcount.alloc(ctx, 2 * sizeof(int32_t)));
+    MB_CUDA(ctx, cudaMemsetAsync(d_fcount.p, 0, 2 * sizeof(int32_t), ctx->stream));
+    mp.cand_id = (uint32_t*)d_cand.p;
+    mp.cand_cnt = (int32_t*)d_ccnt.p;
+    mp.cand_bound = (float*)d_cbound.p;
+  }
+  g_last_fallback_rows = 0;
+  {
+    ProfScope prof(ctx, MB200_K_RESCORE);
+    k_merge<<<(unsigned)((a->a_count + 7) / 8), 256, 0, ctx->stream>>>(mp);
+    ctx->launches++;
+    MB_CUDA(ctx, cudaGetLastError());
+    if (rescored) {
+      RescoreParams rp;
+      memset(&rp, 0, sizeof(rp));
+      rp.a_counters = (const long long*)a->a_counters;
+      rp.b_counters = (const long long*)a->b_counters;
+      rp.a_count = a->a_count;
+      rp.b_count = a->b_count;
+      rp.d = a->depth;
+      rp.W = a->width;
+      rp.blocks = a->b_blocks;
+      rp.a_id_mul = p.a_id_mul;
+      rp.a_id_off = p.a_id_off;
+      rp.b_id_mul = p.b_id_mul;
+      rp.b_id_add = contiguous ? (uint32_t)a->b_count : 1u;
+      rp.cand_id = mp.cand_id;
+      rp.cand_cnt = mp.cand_cnt;
+      rp.cand_bound = mp.cand_bound;
+      rp.inv_scale2 = p.inv_scale2;
+      rp.eps_rel = eps_rel;
+      rp.k = a->k;
+      rp.threshold = mp.threshold;
+      rp.out_idx = (long long*)a->out_idx;
+      rp.out_sim = a->out_sim;
+      rp.out_cnt = a->out_cnt;
+      rp.row_flag = (int32_t*)d_flag.p;
+      rp.flag_count = (int32_t*)d_fcount.p;
+      const size_t smem = (size_t)a->width * sizeof(long long);
+      if (smem > ctx->smem_optin - 8192)
+        return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_cosine_topk: width %d too large for the re-score kernel", a->width);
+      MB_CUDA(ctx, cudaFuncSetAttribute(k_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_rescore<<<(unsigned)a->a_count, 256, smem, ctx->stream>>>(rp);
+      ctx->launches++;
+      MB_CUDA(ctx, cudaGetLastError());
+      int32_t nflag = 0;
+      MB_CUDA(ctx, cudaMemcpyAsync(&nflag, d_fcount.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      g_last_fallback_rows = nflag;
+      if (nflag > 0) {
+        // exact full-row path, in batches bounded by scratch memory
+        rp.b_id_add = p.b_id_add;  // forward mapping for k_exact_*
+        DevBuf d_rows, d_scratch;
+        MB_CHECK(d_rows.alloc(ctx, (size_t)nflag * sizeof(int32_t)));
+        k_collect_flagged<<<(unsigned)((a->a_count + 255) / 256), 256, 0, ctx->stream>>>(
+            rp.row_flag, a->a_count, (int32_t*)d_rows.p, rp.flag_count + 1);
+        ctx->launches++;
+        const int batch = (int)std::max<int64_t>(1, std::min<int64_t>(nflag, (1LL << 30) / (total_b * 8)));
+        MB_CHECK(d_scratch.alloc(ctx, (size_t)batch * total_b * sizeof(double)));
+        for (int off = 0; off < nflag; off += batch) {
+          const int m = std::min(batch, nflag - off);
+          k_exact_rows<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, 1.0, 1.0, (double*)d_scratch.p, total_b);
+          k_exact_topk<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (const double*)d_scratch.p, total_b,
+                                                   p.exclude_self);
+          ctx->launches += 2;
+          MB_CUDA(ctx, cudaGetLastError());
+        }
+      }
+    }
+  }
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // workspaces are freed on return
+  return MB200_OK;
+}
+
+int mb200_bank_cosine_topk(mb200_bank* bk, int32_t k, double threshold, int exclude_self, int dtype,
+                           int precision, int64_t* out_idx, double* out_sim, int32_t* out_cnt, int mem) {
+  if (!bk) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_cosine_topk: bank is NULL");
+  mb200_ctx* ctx = bk->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (k <= 0 || !out_idx || !out_sim || !out_cnt)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_cosine_topk: bad arguments (k=%d)", k);
+  if (mem != MB200_MEM_HOST && mem != MB200_MEM_DEVICE)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_cosine_topk: mem must be MB200_MEM_HOST or MB200_MEM_DEVICE");
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t ld = mb200_row_ld(bk->W), vw = mb200_valid_words(bk->E);
+  DevBuf rows, valid, o_idx, o_sim, o_cnt;
+  MB_CHECK(rows.alloc(ctx, (size_t)bk->d * bk->E * ld * 2));
+  MB_CHECK(valid.alloc(ctx, (size_t)bk->d * vw * sizeof(uint32_t)));
+  MB_CHECK(normalize_locked(bk, dtype, rows.p, (uint32_t*)valid.p));
+  mb200_cosine_args a;
+  memset(&a, 0, sizeof(a));
+  a.a_rows = a.b_rows = rows.p;
+  a.a_valid = a.b_valid = (const uint32_t*)valid.p;
+  a.a_count = a.b_count = bk->E;
+  a.a_id_mul = 1;
+  a.a_id_off = 0;
+  a.b_blocks = 1;
+  a.b_id_mul = 1;
+  a.b_id_add = bk->E;
+  a.depth = bk->d;
+  a.width = bk->W;
+  a.dtype = dtype;
+  a.precision = precision;
+  a.k = k;
+  a.threshold = threshold;
+  a.exclude_self = exclude_self;
+  a.a_counters = a.b_counters = (const int64_t*)bk->counters;
+  if (mem == MB200_MEM_HOST) {
+    MB_CHECK(o_idx.alloc(ctx, (size_t)bk->E * k * 8));
+    MB_CHECK(o_sim.alloc(ctx, (size_t)bk->E * k * 8));
+    MB_CHECK(o_cnt.alloc(ctx, (size_t)bk->E * 4));
+    a.out_idx = (int64_t*)o_idx.p;
+    a.out_sim = (double*)o_sim.p;
+    a.out_cnt = (int32_t*)o_cnt.p;
+  } else {
+    a.out_idx = out_idx;
+    a.out_sim = out_sim;
+    a.out_cnt = out_cnt;
+  }
+  MB_CHECK(cosine_topk_locked(ctx, &a));
+  if (mem == MB200_MEM_HOST) {
+    MB_CUDA(ctx, cudaMemcpyAsync(out_idx, o_idx.p, (size_t)bk->E * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(ctx, cudaMemcpyAsync(out_sim, o_sim.p, (size_t)bk->E * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(ctx, cudaMemcpyAsync(out_cnt, o_cnt.p, (size_t)bk->E * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return MB200_OK;
+}
+
+int mb200_cosine_topk(mb200_ctx* ctx, const mb200_cosine_args* args) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_cosine_topk: ctx is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return cosine_topk_locked(ctx, args);
+}
+
+}  // extern "C"

@@ -286,10 +286,91 @@ class SketchBank:
                 self.ctx.handle)
         return out
 
+    # ---- all-pairs cosine + top-k (RowSimilarityJob / ItemSimilarityJob semantics) --------------
+    def cosine_topk(self, k: int, threshold: float | None = None, exclude_self: bool = True,
+                    dtype: str = "f16", precision: str = "rescored", device: bool = False):
+        """Per entity, the k most similar entities under sketch cosine (min over depth rows).
+
+        Returns (idx [E,k] int64, sim [E,k] float64, cnt [E] int32); unused slots are -1 / 0.
+        threshold None == RowSimilarityJob.NO_THRESHOLD."""
+        mem = N.MEM_DEVICE if device else N.MEM_HOST
+        idx, pi = _out((self.E, k), np.int64, "int64", mem, self.ctx.device)
+        sim, ps = _out((self.E, k), np.float64, "float64", mem, self.ctx.device)
+        cnt, pc = _out((self.E,), np.int32, "int32", mem, self.ctx.device)
+        N.check(N.lib().mb200_bank_cosine_topk(
+            self.handle, int(k), float(threshold) if threshold is not None else 0.0, int(exclude_self),
+            _DTYPES[dtype], _PRECISIONS[precision], pi, ps, pc, mem), self.ctx.handle)
+        return idx, sim, cnt
+
+    def normalize(self, dtype: str = "f16"):
+        """K2: unit-norm 16-bit rows [d, E, ld] and validity words [d, valid_words(E)] (torch, device)."""
+        import torch
+        ld = int(N.lib().mb200_row_ld(self.w))
+        vw = int(N.lib().mb200_valid_words(self.E))
+        dev = f"cuda:{self.ctx.device}"
+        rows = torch.empty((self.d, self.E, ld), dtype=torch.float16 if dtype == "f16" else torch.bfloat16,
+                           device=dev)
+        valid = torch.empty((self.d, vw), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(self.ctx.device)
+        N.check(N.lib().mb200_bank_normalize(self.handle, _DTYPES[dtype], C.c_void_p(rows.data_ptr()),
+                                             C.c_void_p(valid.data_ptr())), self.ctx.handle)
+        self.ctx.sync()
+        return rows, valid
+
+    def counters_tensor(self):
+        """The raw int64 fixed-point counters [E, d, w] as a torch view (plumbing: collectives)."""
+        p, n = self.counters_ptr()
+        return _as_tensor(p, n, self.ctx.device).view(self.E, self.d, self.w)
+
     def counters_ptr(self):
         p, n = C.c_void_p(), C.c_int64()
         N.check(N.lib().mb200_bank_counters(self.handle, C.byref(p), C.byref(n)), self.ctx.handle)
         return p.value, n.value
+
+
+_DTYPES = {"f16": N.DTYPE_F16, "bf16": N.DTYPE_BF16}
+_PRECISIONS = {"tensor": N.PRECISION_TENSOR, "rescored": N.PRECISION_RESCORED}
+
+
+def cosine_topk_blocks(ctx: Context, a_rows, a_valid, b_rows, b_valid, depth: int, width: int, k: int,
+                       a_id=(1, 0), b_id=(1, 0), threshold: float | None = None, exclude_self: bool = True,
+                       dtype: str = "f16", precision: str = "tensor", a_counters=None, b_counters=None,
+                       block_n: int = 0, want_dense: bool = False):
+    """mb200_cosine_topk over device tensors: A rows [d, a_count, ld] against b_blocks gathered blocks
+    B [blocks, d, b_count, ld].  Returns torch device tensors (idx, sim, cnt[, dense])."""
+    import torch
+    dev = f"cuda:{ctx.device}"
+    a_count = a_rows.shape[1]
+    blocks, b_count = b_rows.shape[0], b_rows.shape[2]
+    idx = torch.empty((a_count, k), dtype=torch.int64, device=dev)
+    sim = torch.empty((a_count, k), dtype=torch.float64, device=dev)
+    cnt = torch.empty((a_count,), dtype=torch.int32, device=dev)
+    args = N.CosineArgs()
+    args.a_rows, args.a_valid, args.a_count = a_rows.data_ptr(), a_valid.data_ptr(), a_count
+    args.a_id_mul, args.a_id_off = a_id
+    args.b_rows, args.b_valid, args.b_count, args.b_blocks = b_rows.data_ptr(), b_valid.data_ptr(), b_count, blocks
+    args.b_id_mul, args.b_id_add = b_id
+    args.depth, args.width, args.dtype, args.precision = depth, width, _DTYPES[dtype], _PRECISIONS[precision]
+    args.k, args.threshold, args.exclude_self, args.block_n = k, (threshold or 0.0), int(exclude_self), block_n
+    args.a_counters = a_counters.data_ptr() if a_counters is not None else None
+    args.b_counters = b_counters.data_ptr() if b_counters is not None else None
+    args.out_idx, args.out_sim, args.out_cnt = idx.data_ptr(), sim.data_ptr(), cnt.data_ptr()
+    dense = None
+    if want_dense:
+        bn = block_n or 256
+        ldc = blocks * ((b_count + bn - 1) // bn) * bn
+        dense = torch.full((a_count, ldc), float("nan"), dtype=torch.float32, device=dev)
+        args.dense_out, args.dense_ld = dense.data_ptr(), ldc
+    torch.cuda.synchronize(ctx.device)
+    N.check(N.lib().mb200_cosine_topk(ctx.handle, C.byref(args)), ctx.handle)
+    ctx.sync()
+    return (idx, sim, cnt, dense) if want_dense else (idx, sim, cnt)
+
+
+def last_fallback_rows(ctx: Context) -> int:
+    n = C.c_int64()
+    N.check(N.lib().mb200_cosine_last_fallback_rows(ctx.handle, C.byref(n)), ctx.handle)
+    return n.value
 
 
 class DoubleCountMinSketch:

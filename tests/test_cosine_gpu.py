@@ -1,0 +1,189 @@
+"""GPU parity of the cosine stage (K2 normalise, K3 tcgen05 S.S^T + fused min/top-k, K5 merge and
+exact re-score) against the CPU oracle, through the C ABI.
+
+Bars: tensor-core similarities within 1e-3 relative of the oracle's FP64 cosine (BASELINE.json
+north_star); re-scored similarities bit-equal; top-k index lists equal under (sim desc, index asc)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import mahout_b200
+    return mahout_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(mb):
+    c = mb.Context(0)
+    yield c
+    c.close()
+
+
+def _make_bank(mb, ctx, E, d, w, n, seed, users=943, empty=(), zipf=1.2, frac_bits=1):
+    """item-similarity mode: entity = item, key = user, inc = pref."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    item = (np.minimum(rng.zipf(zipf, n), E) - 1).astype(np.int64)
+    item = (item * 7919) % E                       # spread the popular items over the index range
+    if len(empty):
+        keep = ~np.isin(item, np.array(empty))
+        item = item[keep]
+    user = rng.integers(1, users + 1, item.shape[0]).astype(np.int64)
+    pref = (rng.integers(1, 11, item.shape[0]) * 0.5).astype(np.float32)
+    bank = mb.SketchBank(E, w, d, 42, frac_bits, ctx)
+    bank.update(item, user, pref)
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((E, d, w))
+    orc.bank_update(ref, d, w, a, b, item, user, pref)
+    assert bank.read().tobytes() == ref.tobytes()
+    return bank, ref
+
+
+def _dense(mb, ctx, bank, dtype="f16", block_n=0):
+    from mahout_b200.sketch import cosine_topk_blocks
+    rows, valid = bank.normalize(dtype)
+    idx, sim, cnt, dense = cosine_topk_blocks(
+        ctx, rows, valid, rows.unsqueeze(0), valid.unsqueeze(0), bank.d, bank.w, 8,
+        b_id=(1, bank.E), dtype=dtype, precision="tensor", block_n=block_n, want_dense=True)
+    return dense.cpu().numpy()[:, :bank.E]
+
+
+@pytest.mark.parametrize("E,d,w,block_n", [(300, 4, 512, 0), (300, 1, 512, 0), (300, 4, 512, 128),
+                                            (300, 1, 512, 128), (515, 3, 1000, 0), (130, 2, 64, 128)])
+def test_tensor_core_similarities_match_oracle(mb, ctx, E, d, w, block_n):
+    bank, ref = _make_bank(mb, ctx, E, d, w, 40 * E, seed=E + d + w, empty=(3, E - 1))
+    got = _dense(mb, ctx, bank, block_n=block_n)
+    want = orc.bank_cosine_dense(ref)
+    assert (np.isnan(got) == np.isnan(want)).all(), "NaN pattern (no comparable row) differs"
+    m = ~np.isnan(want) & (want != 0)
+    rel = np.abs(got[m] - want[m]) / np.abs(want[m])
+    assert rel.max() <= REL_TOL, rel.max()
+    assert (got[~np.isnan(want) & (want == 0)] == 0).all()
+    bank.close()
+
+
+def test_bf16_rows_within_bf16_tolerance(mb, ctx):
+    bank, ref = _make_bank(mb, ctx, 260, 2, 512, 20000, seed=77)
+    got = _dense(mb, ctx, bank, dtype="bf16")
+    want = orc.bank_cosine_dense(ref)
+    m = ~np.isnan(want) & (want != 0)
+    assert (np.abs(got[m] - want[m]) / np.abs(want[m])).max() <= 2.0 ** -6
+    bank.close()
+
+
+@pytest.mark.parametrize("E,d,w,k", [(300, 4, 512, 10), (1000, 4, 4096, 50), (257, 1, 256, 100), (129, 2, 192, 5)])
+def test_topk_rescored_equals_oracle_exactly(mb, ctx, E, d, w, k):
+    from mahout_b200.sketch import last_fallback_rows
+    bank, ref = _make_bank(mb, ctx, E, d, w, 60 * E, seed=3 * E + k, empty=(0, 17))
+    idx, sim, cnt = bank.cosine_topk(k)
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    assert (cnt == ocnt).all()
+    assert (idx == oidx).all(), f"{(idx != oidx).sum()} index mismatches"
+    assert sim.tobytes() == osim.tobytes(), "re-scored similarities are not bit-equal to the oracle"
+    assert last_fallback_rows(ctx) <= E
+    bank.close()
+
+
+def test_topk_tensor_precision_within_tolerance(mb, ctx):
+    E, d, w, k = 400, 4, 1024, 20
+    bank, ref = _make_bank(mb, ctx, E, d, w, 80 * E, seed=5)
+    idx, sim, cnt = bank.cosine_topk(k, precision="tensor")
+    dense = orc.bank_cosine_dense(ref)
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    assert (cnt == ocnt).all()
+    for r in range(E):
+        for t in range(cnt[r]):
+            c = idx[r, t]
+            assert c != r and c >= 0
+            assert abs(sim[r, t] - dense[r, c]) <= REL_TOL * abs(dense[r, c])
+        # every returned item is within tolerance of the true k-th value
+        if cnt[r] == k:
+            assert sim[r, :k].min() >= osim[r, k - 1] * (1 - 2 * REL_TOL)
+    bank.close()
+
+
+def test_golden_fixture_topk(mb, ctx):
+    g = json.load(open(os.path.join(GOLD, "sketch_small.json")))
+    bank = mb.SketchBank(g["E"], g["w"], g["d"], mb.HashFunctionBuilder(g["seed"]), 1, ctx)
+    bank.update(np.array(g["entity"]), np.array(g["key"]), np.array(g["inc"], np.float32))
+    idx, sim, cnt = bank.cosine_topk(g["k"])
+    assert cnt.tolist() == g["topk_cnt"]
+    assert idx.tolist() == g["topk_idx"]
+    assert np.allclose(sim, np.array(g["topk_sim"]), rtol=0, atol=0)
+    bank.close()
+
+
+def test_threshold_self_and_ties(mb, ctx):
+    """identical sketches tie exactly: the lower index must win; threshold and self handling."""
+    E, d, w, k = 140, 2, 128, 3
+    bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+    ent = np.repeat(np.arange(E), 3).astype(np.int64)
+    key = np.tile(np.array([5, 9, 11]), E).astype(np.int64)
+    key[3 * 100:] += 1000                            # items 100.. use different users
+    inc = np.tile(np.array([1.0, 2.0, 0.5], np.float32), E)
+    bank.update(ent, key, inc)
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((E, d, w))
+    orc.bank_update(ref, d, w, a, b, ent, key, inc)
+    for kwargs in (dict(), dict(exclude_self=False), dict(threshold=0.5)):
+        idx, sim, cnt = bank.cosine_topk(k, **kwargs)
+        oidx, osim, ocnt = orc.bank_cosine_topk(
+            ref, k, threshold=kwargs.get("threshold", orc.NO_THRESHOLD),
+            exclude_self=kwargs.get("exclude_self", True))
+        assert (cnt == ocnt).all() and (idx == oidx).all(), kwargs
+        assert sim.tobytes() == osim.tobytes()
+    idx, _, _ = bank.cosine_topk(k)
+    assert idx[0].tolist() == [1, 2, 3] and idx[2].tolist() == [0, 1, 3]
+    bank.close()
+
+
+def test_sharded_blocks_on_one_gpu(mb, ctx):
+    """Item-hash sharding (owner = index % G) emulated on one GPU: shard banks are normalised
+    separately, concatenated like an all-gather, and every shard computes its block row."""
+    import torch
+    from mahout_b200.sketch import cosine_topk_blocks
+    E, d, w, k, G = 600, 4, 512, 12, 3
+    full, ref = _make_bank(mb, ctx, E, d, w, 50 * E, seed=9, empty=(5,))
+    counters = full.counters_tensor()                     # [E, d, w] int64
+    per = E // G
+    rows, valid, cnts = [], [], []
+    for g in range(G):
+        sh = mb.SketchBank(per, w, d, 42, 1, ctx)
+        sh.counters_tensor().copy_(counters[g::G])
+        torch.cuda.synchronize()
+        r, v = sh.normalize()
+        rows.append(r)
+        valid.append(v)
+        cnts.append(sh.counters_tensor().clone())
+        sh.close()
+    b_rows = torch.stack(rows)                            # [G, d, per, ld]
+    b_valid = torch.stack(valid)
+    b_cnt = torch.stack(cnts)                             # [G, per, d, w]
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    for g in range(G):
+        idx, sim, cnt = cosine_topk_blocks(ctx, rows[g], valid[g], b_rows, b_valid, d, w, k,
+                                           a_id=(G, g), b_id=(G, 1), precision="rescored",
+                                           a_counters=cnts[g], b_counters=b_cnt)
+        assert (cnt.cpu().numpy() == ocnt[g::G]).all()
+        assert (idx.cpu().numpy() == oidx[g::G]).all()
+        assert sim.cpu().numpy().tobytes() == osim[g::G].tobytes()
+    full.close()
+
+
+def test_bad_arguments(mb, ctx):
+    bank = mb.SketchBank(10, 64, 2, 42, 1, ctx)
+    with pytest.raises(ValueError):
+        bank.cosine_topk(0)
+    with pytest.raises(mb.NativeError):
+        bank.cosine_topk(1000)          # beyond the fused top-k capacity
+    bank.close()
