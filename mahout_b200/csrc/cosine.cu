@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,10 +57,12 @@ struct CosParams {
   uint2* lists;             // [item][half][128][CAP] (value bits, index)
   int32_t* list_cnt;        // [item][half][128]
   float* list_bound;        // [item][half][128]: every candidate not in the list has value <= bound
+  uint32_t* row_thr;        // [a rows padded]: best published lower bound of the row's ksel-th value (ordered uint)
   float* dense_out;
   int64_t dense_ld;
   float inv_scale2;
   uint32_t idesc;
+  uint64_t policy_a, policy_b;  // L2 eviction priority of the A / B tile loads
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -180,6 +183,50 @@ __device__ __noinline__ uint32_t warp_compact_list(uint2* list, int n, int ksel,
   return kth;
 }
 
+// Warp-cooperative threshold raise of one candidate list (the common path; no sort): a bitwise
+// radix search finds a value T with ksel <= #{v >= T} <= ksel + 32 (or the exact ksel-th value when
+// ties make that impossible), entries below T are dropped and the survivors are packed to the front,
+// unsorted.  Never cuts inside a group of equal values, so ties need no index rule here.
+// Returns T in the ordered-uint domain; *new_n = survivors.
+__device__ __noinline__ uint32_t warp_select_list(uint2* list, int n, int ksel, int lane, int* new_n) {
+  uint32_t ord[CAP / 32], idv[CAP / 32];
+#pragma unroll
+  for (int s = 0; s < CAP / 32; s++) {
+    const int e = s * 32 + lane;
+    ord[s] = 0u;
+    idv[s] = 0u;
+    if (e < n) {
+      const uint2 x = __ldcg(list + e);
+      ord[s] = f2ord(x.x);
+      idv[s] = x.y;
+    }
+  }
+  uint32_t T = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; bit--) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int s = 0; s < CAP / 32; s++) c += (ord[s] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= ksel) {
+      T = cand;
+      if (c <= ksel + 32) break;
+    }
+  }
+  __syncwarp();
+  int base = 0;
+#pragma unroll
+  for (int s = 0; s < CAP / 32; s++) {
+    const bool keep = ord[s] >= T && ord[s] != 0u;
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (keep) __stcg(list + base + __popc(b & ((1u << lane) - 1u)), make_uint2(ord2f(ord[s]), idv[s]));
+    base += __popc(b);
+  }
+  *new_n = base;
+  return T;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: Sketch . Sketch^T on tcgen05 with fused min-over-depth and candidate selection
 // ------------------------------------------------------------------------------------------------
@@ -248,8 +295,8 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
               const uint32_t full = smem_u32(&bar_full[stage]);
               const uint32_t sa = smem_base + (uint32_t)stage * STAGE_BYTES;
               mbar_expect_tx(full, STAGE_BYTES);
-              tma_load_3d(sa, &tmA, full, kb * BK, it.x * BM, dep);
-              tma_load_4d(sa + A_BYTES, &tmB, full, kb * BK, l0, dep, g);
+              tma_load_3d(sa, &tmA, full, kb * BK, it.x * BM, dep, p.policy_a);
+              tma_load_4d(sa + A_BYTES, &tmB, full, kb * BK, l0, dep, g, p.policy_b);
               if (++stage == stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -325,9 +372,16 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       int cnt = 0;
       float thr = p.thr_init;
       float bound = -INFINITY;
+      bool published = false;
+      uint32_t* my_row_thr = p.row_thr + (size_t)it.x * BM + row;
       for (int t = t0; t < t1; t++) {
         const int g = t / p.tiles_per_block;
         const int l0 = (t - g * p.tiles_per_block) * BN + half * HALF;
+        {
+          // lower bounds published by the other lists of this row (other half, other column chunks)
+          const uint32_t gt = __ldcg(my_row_thr);
+          if (gt != 0u) thr = fmaxf(thr, __uint_as_float(ord2f(gt)));
+        }
         for (int dep = 0; dep < p.depth; dep++, q++) {
           const uint32_t as = q % ACC_STAGES;
           const uint32_t aphase = (q / ACC_STAGES) & 1u;
@@ -377,24 +431,40 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                   }
                 }
               }
-              // keep 32 free slots for the next chunk; compaction is warp-cooperative
-              unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+              // keep 32 free slots for the next chunk; raise the threshold early once so that the
+              // other lists of the row can use it.  Threshold raises are warp-cooperative.
+              unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - 32 || (!published && cnt >= 2 * p.ksel));
               while (need) {
                 const int src = __ffs(need) - 1;
                 need &= need - 1;
                 __syncwarp();
                 uint2* l2 = (uint2*)__shfl_sync(0xffffffffu, (unsigned long long)list, src);
                 const int n2 = __shfl_sync(0xffffffffu, cnt, src);
-                const uint32_t kth = warp_compact_list(l2, n2, p.ksel, lane);
+                int n3 = 0;
+                const uint32_t T = warp_select_list(l2, n2, p.ksel, lane, &n3);
+                uint32_t kth = 0xFFFFFFFFu;
+                if (n3 > p.ksel + 32) {  // a large group of equal values: cut it by index (exact sort)
+                  __syncwarp();
+                  kth = warp_compact_list(l2, n3, p.ksel, lane);
+                }
                 if (lane == src) {
-                  cnt = min(n2, p.ksel);
+                  published = true;
                   if (kth != 0xFFFFFFFFu) {
+                    cnt = min(n3, p.ksel);
                     const float kv = __uint_as_float(kth);
                     bound = fmaxf(bound, kv);
                     // ties at the k-th value may still win on the index unless the scan order is
                     // index-monotone: admit them by stepping the threshold one ulp down
-                    thr = p.nonstrict ? __uint_as_float(f2ord(kth) > 0 ? ord2f(f2ord(kth) - 1) : kth) : kv;
-                    thr = fmaxf(thr, p.thr_init);
+                    const uint32_t ko = f2ord(kth);
+                    const uint32_t to = p.nonstrict && ko > 0 ? ko - 1 : ko;
+                    thr = fmaxf(thr, __uint_as_float(ord2f(to)));
+                    // other lists of the row scan other index ranges: they must keep admitting ties
+                    atomicMax(my_row_thr, ko > 0 ? ko - 1 : 0u);
+                  } else if (T != 0u) {
+                    cnt = n3;
+                    bound = fmaxf(bound, __uint_as_float(ord2f(T)));
+                    thr = fmaxf(thr, __uint_as_float(ord2f(T - 1)));  // x > thr  <=>  x >= T
+                    atomicMax(my_row_thr, T - 1);
                   }
                 }
                 __syncwarp();
@@ -407,25 +477,9 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
         }
       }
-      // final compaction: sorted, at most ksel entries per list
-      {
-        unsigned need = __ballot_sync(0xffffffffu, cnt > 0);
-        while (need) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          __syncwarp();
-          uint2* l2 = (uint2*)__shfl_sync(0xffffffffu, (unsigned long long)list, src);
-          const int n2 = __shfl_sync(0xffffffffu, cnt, src);
-          const uint32_t kth = warp_compact_list(l2, n2, p.ksel, lane);
-          if (lane == src) {
-            if (n2 > p.ksel && kth != 0xFFFFFFFFu) bound = fmaxf(bound, __uint_as_float(kth));
-            cnt = min(n2, p.ksel);
-          }
-          __syncwarp();
-        }
-        p.list_cnt[slot] = cnt;
-        p.list_bound[slot] = bound;
-      }
+      // the list stays unsorted (<= CAP entries); K5 merges and orders
+      p.list_cnt[slot] = cnt;
+      p.list_bound[slot] = bound;
     }
   }
 
@@ -991,9 +1045,9 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
   int margin = rescored ? std::max(14, a->k / 4) : 0;
   int ksel = a->k + margin;
   ksel = (ksel + 31) / 32 * 32;
-  if (ksel > CAP - 32) ksel = CAP - 32;
+  if (ksel > CAP - 64) ksel = CAP - 64;
   if (a->k > ksel)
-    return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_cosine_topk: k = %d exceeds the fused top-k capacity %d", a->k, CAP - 32);
+    return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_cosine_topk: k = %d exceeds the fused top-k capacity %d", a->k, CAP - 64);
   const int BN = a->block_n == 128 ? 128 : 256;
   if (a->block_n != 0 && a->block_n != 128 && a->block_n != 256)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: block_n must be 0, 128 or 256");
@@ -1005,24 +1059,28 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
   const int num_m = (int)((a->a_count + BM - 1) / BM);
   if (a->dense_out && a->dense_ld < (int64_t)T * BN)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: dense_ld must be >= %lld", (long long)T * BN);
-  // column chunks: enough items to fill the SMs in whole waves
+  // Column chunks per row block.  Work items (row block, chunk) are dealt round-robin to one CTA per
+  // SM; a CTA's time is (waves) x (tiles per chunk + ~1.5 tiles of list warm-up per item), and the
+  // merge kernel's work grows with the number of chunks: take the cheapest, fewest chunks on ties.
   const int P = ctx->num_sms;
   int S = 1;
   {
-    double best = -1.0;
+    double best = 1e300;
     const int smax = std::min(T, 32);
     for (int s = 1; s <= smax; s++) {
       const long long items = (long long)num_m * s;
       const long long waves = (items + P - 1) / P;
-      double eff = (double)items / (double)(waves * P);
       const int ct = (T + s - 1) / s;
-      if (ct < 2 && s > 1) break;
-      // fewer, longer sweeps amortise list handling: only move to more chunks for a clear gain
-      if (eff > best + 0.03) {
-        best = eff;
+      const double cost = (double)waves * ((double)ct + 1.5) * (1.0 + 0.004 * s);
+      if (cost < best * 0.999) {
+        best = cost;
         S = s;
       }
     }
+  }
+  if (const char* ev = getenv("MB200_COS_CHUNKS")) {  // tuning override
+    const int s = atoi(ev);
+    if (s >= 1 && s <= T) S = s;
   }
   const int chunk_tiles = (T + S - 1) / S;
   S = (T + chunk_tiles - 1) / chunk_tiles;
@@ -1044,7 +1102,9 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
         }
     }
   }
-  DevBuf d_items, d_slot, d_lists, d_cnt, d_bound;
+  DevBuf d_items, d_slot, d_lists, d_cnt, d_bound, d_rowthr;
+  MB_CHECK(d_rowthr.alloc(ctx, (size_t)num_m * BM * sizeof(uint32_t)));
+  MB_CUDA(ctx, cudaMemsetAsync(d_rowthr.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
   MB_CHECK(d_items.alloc(ctx, items.size() * sizeof(int2)));
   MB_CHECK(d_slot.alloc(ctx, slot_of.size() * sizeof(int32_t)));
   const size_t nlists = (size_t)num_items * 2 * BM;
@@ -1102,10 +1162,18 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
   p.lists = (uint2*)d_lists.p;
   p.list_cnt = (int32_t*)d_cnt.p;
   p.list_bound = (float*)d_bound.p;
+  p.row_thr = (uint32_t*)d_rowthr.p;
   p.dense_out = a->dense_out;
   p.dense_ld = a->dense_ld;
   p.inv_scale2 = 1.0f / scale2;
   p.idesc = umma_idesc_f16(a->dtype == MB200_DTYPE_BF16 ? 1 : 0, BM, BN);
+  p.policy_a = L2_EVICT_LAST;   // an A block is re-read for every B tile of the sweep
+  p.policy_b = L2_EVICT_FIRST;  // a B tile is shared only by the CTAs sweeping it right now
+  if (const char* ev = getenv("MB200_COS_HINTS")) {
+    const int h = atoi(ev);
+    p.policy_a = h == 0 ? L2_EVICT_NORMAL : (h == 2 ? L2_EVICT_NORMAL : L2_EVICT_LAST);
+    p.policy_b = h == 0 ? L2_EVICT_NORMAL : L2_EVICT_FIRST;
+  }
   const int grid = std::min(num_items, P);
   {
     ProfScope prof(ctx, MB200_K_COSINE);

@@ -43,7 +43,10 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None) is not None:
-            N.lib().mb200_destroy(self._h)
+            try:
+                N.lib().mb200_destroy(self._h)
+            except Exception:   # interpreter shutdown: module globals are already gone
+                pass
             self._h = None
 
     __del__ = close
@@ -230,7 +233,10 @@ class SketchBank:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self.ctx._h is not None:
-            N.lib().mb200_bank_destroy(self._h)
+            try:
+                N.lib().mb200_bank_destroy(self._h)
+            except Exception:   # interpreter shutdown
+                pass
         self._h = None
 
     __del__ = close
