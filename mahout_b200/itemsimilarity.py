@@ -1,0 +1,89 @@
+"""`mahout itemsimilarity` with the GPU sketch-cosine measure -- the job-level drop-in.
+
+    python -m mahout_b200.itemsimilarity --input prefs.csv --output out.tsv \
+        --similarityClassname SIMILARITY_SKETCH_COSINE --maxSimilaritiesPerItem 100 \
+        [--minPrefsPerUser 1] [--booleanData true] [--threshold 0.1] \
+        [--sketchWidth 4096] [--sketchDepth 4] [--sketchSeed 42] [--precision rescored|tensor]
+
+Same flags, input format (`userID,itemID[,pref]`, split on tab or comma) and output format
+(`itemA<TAB>itemB<TAB>similarity`, itemA < itemB, ordered by (itemA, itemB)) as the reference's
+ItemSimilarityJob (cf/taste/hadoop/similarity/item/ItemSimilarityJob.java:97-232); phase 1
+(RowSimilarityJob) is replaced by the native call sequence.  Returns 0 on success, -1 on bad
+arguments or failure, like AbstractJob.  `--maxPrefs` is accepted for compatibility: the sketch
+bounds the work per item by its width, so no down-sampling takes place.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+
+from . import similarity as sim
+
+MEASURES = ("SIMILARITY_SKETCH_COSINE", "SIMILARITY_COSINE",
+            "org.apache.mahout.math.hadoop.similarity.cooccurrence.measures.CosineSimilarity",
+            "org.apache.mahout.math.hadoop.similarity.cooccurrence.measures.NativeSketchCosineSimilarity")
+
+
+def _bool(s: str) -> bool:
+    return str(s).strip().lower() == "true"        # Boolean.valueOf
+
+
+def build_parser() -> argparse.ArgumentParser:
+    ap = argparse.ArgumentParser(prog="itemsimilarity", add_help=True)
+    ap.add_argument("--input", "-i", required=True)
+    ap.add_argument("--output", "-o", required=True)
+    ap.add_argument("--similarityClassname", "-s", required=True)
+    ap.add_argument("--maxSimilaritiesPerItem", "-m", type=int, default=sim.DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM)
+    ap.add_argument("--maxPrefs", "-mppu", type=int, default=500)
+    ap.add_argument("--minPrefsPerUser", "-mp", type=int, default=sim.DEFAULT_MIN_PREFS_PER_USER)
+    ap.add_argument("--booleanData", "-b", default="false")
+    ap.add_argument("--threshold", "-tr", type=float, default=None)
+    ap.add_argument("--randomSeed", type=int, default=None)
+    ap.add_argument("--tempDir", default=None)
+    ap.add_argument("--startPhase", type=int, default=0)
+    ap.add_argument("--endPhase", type=int, default=2 ** 31 - 1)
+    ap.add_argument("--sketchWidth", type=int, default=4096)
+    ap.add_argument("--sketchDepth", type=int, default=4)
+    ap.add_argument("--sketchSeed", type=int, default=42)
+    ap.add_argument("--fracBits", type=int, default=1)
+    ap.add_argument("--precision", default="rescored", choices=["rescored", "tensor"])
+    return ap
+
+
+class ItemSimilarityJob:
+    def run(self, argv) -> int:
+        try:
+            args = build_parser().parse_args(argv)
+        except SystemExit:
+            return -1
+        if args.similarityClassname not in MEASURES:
+            print(f"itemsimilarity: the native path implements the cosine measure only "
+                  f"(got {args.similarityClassname})", file=sys.stderr)
+            return -1
+        if args.maxSimilaritiesPerItem <= 0:
+            print("maxSimilarItemsPerItem must be greater then 0!", file=sys.stderr)
+            return -1
+        try:
+            with open(args.input) as f:
+                user, item, pref = sim.parse_prefs(f, boolean_data=_bool(args.booleanData))
+            prep = sim.PreferenceMatrix(user, item, pref, args.minPrefsPerUser)
+            idx, s, cnt = sim.item_similarity(
+                prep.row, prep.user, prep.pref, prep.num_items, k=args.maxSimilaritiesPerItem,
+                threshold=args.threshold, width=args.sketchWidth, depth=args.sketchDepth,
+                seed=args.sketchSeed, frac_bits=args.fracBits, precision=args.precision)
+            pairs = sim.most_similar_item_pairs(idx, s, cnt, prep.item_id)
+            with open(args.output, "w") as out:
+                for a, b, v in pairs:
+                    out.write(f"{a}\t{b}\t{v!r}\n")
+        except Exception as e:   # AbstractJob: failures surface as a non-zero exit code
+            print(f"itemsimilarity failed: {e}", file=sys.stderr)
+            return -1
+        return 0
+
+
+def main(argv=None) -> int:
+    return ItemSimilarityJob().run(sys.argv[1:] if argv is None else argv)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

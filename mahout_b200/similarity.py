@@ -1,0 +1,254 @@
+"""Host side of the item-similarity path over the C ABI: what ItemSimilarityJob / RowSimilarityJob
+do around the hot loop, with the hot loop (sketch build + all-pairs cosine + top-k) on the GPU.
+
+Reference call stack being mirrored:
+  ItemSimilarityJob.run                       cf/taste/hadoop/similarity/item/ItemSimilarityJob.java:97-179
+    PreparePreferenceMatrixJob                cf/taste/hadoop/preparation/PreparePreferenceMatrixJob.java:54-114
+      ToEntityPrefsMapper  (text -> long,long,float)     cf/taste/hadoop/ToEntityPrefsMapper.java:56-76
+      ItemIDIndexMapper / Reducer (idToIndex, min ID)     cf/taste/hadoop/item/ItemIDIndex*.java
+      ToUserVectorsReducer (set(index, pref): last wins; minPrefsPerUser)
+    RowSimilarityJob (cosine)                 math/hadoop/similarity/cooccurrence/RowSimilarityJob.java
+    MostSimilarItemPairsMapper / Reducer      ItemSimilarityJob.java:181-232  ((minID,maxID) keys, dedup)
+
+Single GPU: `item_similarity`.  One process per GPU (torch.distributed): `sharded_item_similarity`
+-- items are sharded by index % G, every rank builds the sketches of its own items, the
+normalised 16-bit rows are all-gathered (NCCL over NVLink) and each rank computes its block row of
+the similarity matrix; no merge across GPUs is needed because a row's candidates all live on its
+owner.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import sketch as sk
+
+NO_THRESHOLD = 4.9e-324          # RowSimilarityJob.NO_THRESHOLD = Double.MIN_VALUE (RowSimilarityJob.java:56)
+DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM = 100   # ItemSimilarityJob.java:88
+DEFAULT_MIN_PREFS_PER_USER = 1
+
+
+# ------------------------------------------------------------------------------------------------
+# ingest (host): the steps of PreparePreferenceMatrixJob
+# ------------------------------------------------------------------------------------------------
+def id_to_index(ids) -> np.ndarray:
+    """TasteHadoopUtils.idToIndex (TasteHadoopUtils.java:56-58):
+    0x7FFFFFFF & Longs.hashCode(id) % 0x7FFFFFFE, with Java's precedence and truncating '%'."""
+    v = np.asarray(ids, dtype=np.int64).view(np.uint64)
+    h = (v ^ (v >> np.uint64(32))).astype(np.uint32).view(np.int32).astype(np.int64)
+    m = np.sign(h) * (np.abs(h) % 0x7FFFFFFE)      # Java remainder truncates toward zero
+    return (m.astype(np.int32).view(np.uint32) & np.uint32(0x7FFFFFFF)).astype(np.int64)
+
+
+def parse_prefs(lines, boolean_data: bool = False, rating_shift: float = 0.0):
+    """ToEntityPrefsMapper.map: split on [\\t,]; user, item as long; pref as float (1.0 if absent or
+    booleanData).  Returns (user int64, item int64, pref float32) in input order."""
+    users, items, prefs = [], [], []
+    for line in lines:
+        line = line.strip()
+        if not line:
+            continue
+        tok = line.replace("\t", ",").split(",")
+        users.append(int(tok[0]))
+        items.append(int(tok[1]))
+        if boolean_data or len(tok) < 3:
+            prefs.append(1.0)
+        else:
+            prefs.append(float(np.float32(tok[2])) + rating_shift)
+    return (np.array(users, np.int64), np.array(items, np.int64), np.array(prefs, np.float32))
+
+
+class PreferenceMatrix:
+    """Output of the preparation phase: de-duplicated events over dense row numbers + the
+    index <-> itemID tables (ItemIDIndexReducer keeps the minimum itemID per index)."""
+
+    def __init__(self, user, item, pref, min_prefs_per_user: int = DEFAULT_MIN_PREFS_PER_USER):
+        user = np.asarray(user, np.int64)
+        item = np.asarray(item, np.int64)
+        pref = np.asarray(pref, np.float32)
+        idx = id_to_index(item)
+        # userVector.set(index, pref): the last preference of a (user, index) pair wins
+        order = np.lexsort((np.arange(user.shape[0]), idx, user))
+        u, i, p, it = user[order], idx[order], pref[order], item[order]
+        last = np.ones(u.shape[0], bool)
+        last[:-1] = (u[1:] != u[:-1]) | (i[1:] != i[:-1])
+        # ItemIDIndexReducer: min itemID per index (over ALL input lines, before user filtering)
+        uniq_idx, inv = np.unique(idx, return_inverse=True)
+        min_id = np.full(uniq_idx.shape[0], np.iinfo(np.int64).max, np.int64)
+        np.minimum.at(min_id, inv, item)
+        u, i, p = u[last], i[last], p[last]
+        # ToUserVectorsReducer: users with fewer than minPrefsPerUser preferences are dropped
+        uu, cnt = np.unique(u, return_counts=True)
+        keep_users = uu[cnt >= min_prefs_per_user]
+        keep = np.isin(u, keep_users)
+        self.user, self.index, self.pref = u[keep], i[keep], p[keep]
+        self.num_users = int(keep_users.shape[0])
+        self.index_values = uniq_idx                 # row r of the matrix <-> index_values[r]
+        self.item_id = min_id                        # row r -> itemID written to the output
+        self.row = np.searchsorted(uniq_idx, self.index)   # dense row number of every event
+        self.num_items = int(uniq_idx.shape[0])
+
+
+def most_similar_item_pairs(idx, sim, cnt, item_id=None):
+    """MostSimilarItemPairsMapper / Reducer: per-row top-k entries -> (minID, maxID) keys, the
+    duplicate of a symmetric pair collapses to one value; ordered by (a, b)
+    (EntityEntityWritable.java:64-71)."""
+    pairs = {}
+    for r in range(idx.shape[0]):
+        rid = int(item_id[r]) if item_id is not None else r
+        for t in range(int(cnt[r])):
+            c = int(idx[r, t])
+            cid = int(item_id[c]) if item_id is not None else c
+            key = (rid, cid) if rid < cid else (cid, rid)
+            pairs.setdefault(key, float(sim[r, t]))
+    return sorted((a, b, s) for (a, b), s in pairs.items())
+
+
+# ------------------------------------------------------------------------------------------------
+# single GPU
+# ------------------------------------------------------------------------------------------------
+def item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM,
+                    threshold: float | None = None, width: int = 4096, depth: int = 4, seed: int = 42,
+                    frac_bits: int = 1, dtype: str = "f16", precision: str = "rescored", ctx=None):
+    """Sketch build + all-pairs cosine + per-item top-k on one GPU.
+    entity = item row, key = userID, increment = pref (SURVEY.md 8a5, item-similarity mode)."""
+    ctx = ctx or sk.default_context()
+    bank = sk.SketchBank(num_items, width, depth, seed, frac_bits, ctx)
+    try:
+        bank.update(row, user, pref)
+        bank.check()
+        return bank.cosine_topk(k, threshold, True, dtype, precision)
+    finally:
+        bank.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# item-hash sharding (one process per GPU)
+# ------------------------------------------------------------------------------------------------
+class ShardPlan:
+    """owner(index) = index % G; local row = index // G; every shard is padded to the same size."""
+
+    def __init__(self, num_items: int, world: int, rank: int):
+        self.N, self.G, self.rank = int(num_items), int(world), int(rank)
+        self.rows_per_shard = (self.N + self.G - 1) // self.G
+
+    def owner(self, row):
+        return np.asarray(row) % self.G
+
+    def local_row(self, row):
+        return np.asarray(row) // self.G
+
+    def global_row(self, local, shard=None):
+        shard = self.rank if shard is None else shard
+        return np.asarray(local) * self.G + shard
+
+    def my_events(self, row, *cols):
+        """the events whose item this rank owns, with rows renumbered locally"""
+        m = self.owner(row) == self.rank
+        return (self.local_row(row[m]),) + tuple(c[m] for c in cols)
+
+    def local_count(self, shard=None):
+        shard = self.rank if shard is None else shard
+        return max(0, (self.N - shard + self.G - 1) // self.G)
+
+    def assemble(self, parts):
+        """per-shard [rows_per_shard, ...] results (shard order) -> global row order [N, ...]"""
+        first = np.asarray(parts[0])
+        out = np.zeros((self.N,) + first.shape[1:], first.dtype)
+        for g, part in enumerate(parts):
+            n = self.local_count(g)
+            out[g::self.G] = np.asarray(part)[:n]
+        return out
+
+
+class GpuShardBackend:
+    """The product backend: every step is a C-ABI call on this rank's GPU."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or sk.default_context()
+
+    def build(self, plan, local_row, key, inc, width, depth, seed, frac_bits):
+        self.bank = sk.SketchBank(plan.rows_per_shard, width, depth, seed, frac_bits, self.ctx)
+        self.bank.update(local_row, key, inc)
+        self.bank.check()
+
+    def normalized(self, dtype):
+        return self.bank.normalize(dtype)            # rows [d, E_loc, ld], valid [d, vw] (torch, device)
+
+    def counters(self):
+        return self.bank.counters_tensor()
+
+    def cosine(self, plan, a_rows, a_valid, b_rows, b_valid, k, threshold, dtype, precision,
+               a_counters=None, b_counters=None):
+        idx, sim, cnt = sk.cosine_topk_blocks(
+            self.ctx, a_rows, a_valid, b_rows, b_valid, self.bank.d, self.bank.w, k,
+            a_id=(plan.G, plan.rank), b_id=(plan.G, 1) if plan.G > 1 else (1, plan.rows_per_shard),
+            threshold=threshold, exclude_self=True, dtype=dtype, precision=precision,
+            a_counters=a_counters, b_counters=b_counters)
+        return idx, sim, cnt
+
+    def close(self):
+        self.bank.close()
+
+
+def _all_gather(t, world, group):
+    """all_gather_into_tensor of equally shaped shards -> [world, *t.shape] (NCCL and gloo)."""
+    import torch
+    import torch.distributed as dist
+    t = t.contiguous()
+    flat = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(flat, t, group=group)
+    return flat.view((world,) + tuple(t.shape))
+
+
+def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM,
+                            threshold: float | None = None, width: int = 4096, depth: int = 4, seed: int = 42,
+                            frac_bits: int = 1, dtype: str = "f16", precision: str = "tensor",
+                            group=None, backend=None, gather_result: bool = True):
+    """One call per rank (torch.distributed initialised; NCCL on GPUs).  `row, user, pref` are the
+    events this rank holds (any subset of the stream: they are first routed to their owners).
+    Returns (idx, sim, cnt) for all N items on every rank when gather_result, else this rank's
+    shard in local row order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    plan = ShardPlan(num_items, world, rank)
+    backend = backend or GpuShardBackend()
+    row, user, pref = np.asarray(row, np.int64), np.asarray(user, np.int64), np.asarray(pref, np.float32)
+    if world > 1:
+        # route events to the owner of their item: an all-gather of the (20 B) events followed by a
+        # local filter (a dedicated all-to-all only pays off once ingest, not compute, is the limit)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (row, user, pref), group=group)
+        row = np.concatenate([g[0] for g in gathered])
+        user = np.concatenate([g[1] for g in gathered])
+        pref = np.concatenate([g[2] for g in gathered])
+    lrow, luser, lpref = plan.my_events(row, user, pref)
+    backend.build(plan, lrow, luser, lpref, width, depth, seed, frac_bits)
+    a_rows, a_valid = backend.normalized(dtype)
+    if world > 1:
+        b_rows = _all_gather(a_rows, world, group)          # C1
+        b_valid = _all_gather(a_valid, world, group)
+    else:
+        b_rows, b_valid = a_rows.unsqueeze(0), a_valid.unsqueeze(0)
+    a_cnt = b_cnt = None
+    if precision == "rescored":
+        a_cnt = backend.counters()
+        if world > 1:
+            b_cnt = _all_gather(a_cnt, world, group)
+        else:
+            b_cnt = a_cnt
+    idx, sim, cnt = backend.cosine(plan, a_rows, a_valid, b_rows, b_valid, k, threshold, dtype, precision,
+                                   a_cnt, b_cnt)
+    if not gather_result:
+        backend.close()
+        return idx, sim, cnt
+    if world > 1:
+        parts = []
+        for t in (idx, sim, cnt):
+            parts.append(_all_gather(t, world, group).cpu().numpy())      # C3
+        out = tuple(plan.assemble(list(p)) for p in parts)
+    else:
+        out = tuple(np.asarray(t.cpu().numpy())[:num_items] for t in (idx, sim, cnt))
+    backend.close()
+    return out

@@ -1,0 +1,152 @@
+"""Job-level parity on the GPU: the ItemSimilarityJob mirror against the reference's own
+end-to-end golden (ItemSimilarityJobTest.testCompleteJob) and against the oracle on the
+MovieLens-100K-shaped configuration (BASELINE.json configs[0])."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_job(tmp_path, lines, *extra):
+    from mahout_b200.itemsimilarity import ItemSimilarityJob
+    inp = tmp_path / "prefs.csv"
+    inp.write_text("\n".join(lines) + "\n")
+    out = tmp_path / "out.tsv"
+    rc = ItemSimilarityJob().run(["--input", str(inp), "--output", str(out), "--similarityClassname",
+                                  "SIMILARITY_COSINE", *extra])
+    assert rc == 0
+    rows = []
+    for ln in out.read_text().splitlines():
+        a, b, s = ln.split("\t")
+        rows.append((int(a), int(b), float(s)))
+    return rows
+
+
+def test_complete_job_reference_golden(tmp_path):
+    """ItemSimilarityJobTest.testCompleteJob (:113-173): exactly two lines, 1-3 ~0.45, 2-3 ~0.89.
+    With a sketch far wider than the 3 users no two keys collide, so sketch cosine == cosine."""
+    rows = _run_job(tmp_path, ["2,1,1", "1,2,1", "3,4,1", "1,3,2", "2,3,1"], "--sketchWidth", "65536")
+    assert len(rows) == 2
+    assert rows[0][:2] == (1, 3) and abs(rows[0][2] - 0.45) < 0.01
+    assert rows[1][:2] == (2, 3) and abs(rows[1][2] - 0.89) < 0.01
+    assert abs(rows[0][2] - 1 / np.sqrt(5)) < 1e-12 and abs(rows[1][2] - 2 / np.sqrt(5)) < 1e-12
+
+
+def test_max_similarities_per_item_and_threshold(tmp_path):
+    lines = [f"{u},{i},{1 + (u * i) % 5}" for u in range(1, 12) for i in range(1, 9) if (u + i) % 3]
+    all_rows = _run_job(tmp_path, lines, "--sketchWidth", "65536")
+    capped = _run_job(tmp_path, lines, "--sketchWidth", "65536", "-m", "1")
+    assert set(capped) <= set(all_rows) and len(capped) < len(all_rows)
+    per_item = {}
+    for a, b, s in all_rows:
+        per_item.setdefault(a, []).append(s)
+        per_item.setdefault(b, []).append(s)
+    # with m = 1 every item still appears with its best partner
+    best = {i: max(v) for i, v in per_item.items()}
+    seen = {}
+    for a, b, s in capped:
+        seen[a] = max(seen.get(a, 0), s)
+        seen[b] = max(seen.get(b, 0), s)
+    assert all(abs(seen[i] - best[i]) < 1e-15 for i in best)
+    thr = _run_job(tmp_path, lines, "--sketchWidth", "65536", "--threshold", "0.8")
+    assert thr == [r for r in all_rows if r[2] >= 0.8]
+
+
+def test_movielens_100k_shaped_config(tmp_path):
+    """configs[0]: 943 users x 1682 items, 100K unique prefs.  GPU sketch path == oracle sketch path
+    (exactly); the exact MapReduce-path oracle gives the recall of the sketch measure."""
+    import mahout_b200 as mb
+    from mahout_b200 import similarity as sim
+    rng = np.random.Generator(np.random.PCG64(20240001))
+    U, I, n, k, d, w = 943, 1682, 100000, 100, 4, 4096
+    pairs = set()
+    cdf = np.cumsum(1.0 / np.arange(1, I + 1))
+    cdf /= cdf[-1]
+    perm = rng.permutation(I)
+    while len(pairs) < n:
+        u = rng.integers(1, U + 1, n)
+        it = perm[np.minimum(np.searchsorted(cdf, rng.random(n)), I - 1)] + 1
+        pairs.update(zip(u.tolist(), it.tolist()))
+    pairs = sorted(pairs)[:n]
+    user = np.array([p[0] for p in pairs], np.int64)
+    item = np.array([p[1] for p in pairs], np.int64)
+    pref = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
+    prep = sim.PreferenceMatrix(user, item, pref)
+    idx, s, cnt = sim.item_similarity(prep.row, prep.user, prep.pref, prep.num_items, k=k, width=w, depth=d)
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((prep.num_items, d, w))
+    orc.bank_update(ref, d, w, a, b, prep.row, prep.user, prep.pref)
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    assert (cnt == ocnt).all() and (idx == oidx).all() and s.tobytes() == osim.tobytes()
+    # exact path (RowSimilarityJob semantics) for the recall of the sketch measure
+    order = np.lexsort((prep.user, prep.row))
+    rowptr = np.zeros(prep.num_items + 1, np.int64)
+    np.add.at(rowptr, prep.row + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    ucol = np.searchsorted(np.unique(prep.user), prep.user[order]).astype(np.int32)
+    eidx, esim, ecnt = orc.rowsim_cosine_topk(prep.num_items, U, rowptr, ucol, prep.pref[order], k)
+    hit = tot = 0
+    for r in range(prep.num_items):
+        e = set(eidx[r, :ecnt[r]].tolist())
+        hit += len(e & set(idx[r, :cnt[r]].tolist()))
+        tot += len(e)
+    assert hit / tot > 0.5, hit / tot
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from mahout_b200 import similarity as sim
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    rng = np.random.Generator(np.random.PCG64(12))
+    N, n = 777, 60000
+    row = ((np.minimum(rng.zipf(1.2, n), N) - 1) * 13 % N).astype(np.int64)
+    user = rng.integers(1, 3000, n).astype(np.int64)
+    pref = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
+    res = {}
+    for precision in ("rescored", "tensor"):
+        res[precision] = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N,
+                                                     k=20, width=1024, depth=4, precision=precision)
+    if rank == 0:
+        q.put((row, user, pref, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_two_gpus_nccl():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = sck.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    row, user, pref, res = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    a, b = orc.hash_params(42, 4)
+    ref = np.zeros((777, 4, 1024))
+    orc.bank_update(ref, 4, 1024, a, b, row, user, pref)
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, 20)
+    idx, s, cnt = res["rescored"]
+    assert (cnt == ocnt).all() and (idx == oidx).all() and s.tobytes() == osim.tobytes()
+    idx, s, cnt = res["tensor"]
+    assert (cnt == ocnt).all()
+    dense = orc.bank_cosine_dense(ref)
+    for r in range(777):
+        for t in range(cnt[r]):
+            assert abs(s[r, t] - dense[r, idx[r, t]]) <= 1e-3 * abs(dense[r, idx[r, t]])
