@@ -630,9 +630,13 @@ __device__ __forceinline__ void b_locate(const RescoreParams& p, uint32_t id, lo
 #define TWO53 9007199254740992.0
 #define JAVA_MAX_DOUBLE 1.7976931348623157e308
 
+#define RESCORE_SEG 4096  /* counters of one A row segment staged in shared memory */
+
 __global__ void __launch_bounds__(256) k_rescore(const RescoreParams p) {
-  extern __shared__ long long s_a[];          // one depth row of A: W counters
+  __shared__ long long s_a[RESCORE_SEG];       // one segment of one depth row of A
   __shared__ double s_min[CAP];                // running min of cos_i per candidate
+  __shared__ long long s_ab[CAP], s_bb[CAP];   // exact integer dot products of the current depth
+  __shared__ double s_mag[CAP];
   __shared__ double s_red[8];
   __shared__ long long s_redi[8];
   __shared__ int s_bad;
@@ -644,16 +648,54 @@ __global__ void __launch_bounds__(256) k_rescore(const RescoreParams p) {
   __syncthreads();
   const long long* arow = p.a_counters + (size_t)r * p.d * p.W;
   for (int i = 0; i < p.d && n > 0; i++) {
-    // A row of this depth -> smem, AA exactly
+    for (int c = tid; c < CAP; c += blockDim.x) {
+      s_ab[c] = 0;
+      s_bb[c] = 0;
+      s_mag[c] = 0.0;
+    }
     long long aa = 0;
     double amag = 0.0;
     int bad = 0;
-    for (int j = tid; j < p.W; j += blockDim.x) {
-      const long long x = arow[(size_t)i * p.W + j];
-      s_a[j] = x;
-      if (x >= (1LL << 31) || x <= -(1LL << 31)) bad = 1;
-      aa += x * x;
-      amag += (double)x * (double)x;
+    for (int j0 = 0; j0 < p.W; j0 += RESCORE_SEG) {
+      const int seg = min(RESCORE_SEG, p.W - j0);
+      __syncthreads();  // previous segment fully consumed
+      for (int j = tid; j < seg; j += blockDim.x) {
+        const long long x = arow[(size_t)i * p.W + j0 + j];
+        s_a[j] = x;
+        if (x >= (1LL << 31) || x <= -(1LL << 31)) bad = 1;
+        aa += x * x;
+        amag += (double)x * (double)x;
+      }
+      __syncthreads();
+      for (int c = warp; c < n; c += 8) {
+        const uint32_t id = p.cand_id[(size_t)r * CAP + c];
+        long long g, l;
+        b_locate(p, id, g, l);
+        const long long* brow = p.b_counters + (((size_t)g * p.b_count + l) * p.d + i) * p.W + j0;
+        long long bb = 0, ab = 0;
+        double mag = 0.0;
+        int badb = 0;
+        for (int j = lane; j < seg; j += 32) {
+          const long long y = __ldg(brow + j);
+          const long long x = s_a[j];
+          if (y >= (1LL << 31) || y <= -(1LL << 31)) badb = 1;
+          bb += y * y;
+          ab += x * y;
+          mag += fabs((double)y * (double)y) + fabs((double)x * (double)y);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          bb += __shfl_xor_sync(0xffffffffu, bb, o);
+          ab += __shfl_xor_sync(0xffffffffu, ab, o);
+          mag += __shfl_xor_sync(0xffffffffu, mag, o);
+          badb |= __shfl_xor_sync(0xffffffffu, badb, o);
+        }
+        if (lane == 0) {  // candidate c belongs to this warp for every segment: no race
+          s_bb[c] += bb;
+          s_ab[c] += ab;
+          s_mag[c] += mag;
+          if (badb) s_bad = 1;
+        }
+      }
     }
     for (int o = 16; o > 0; o >>= 1) {
       aa += __shfl_xor_sync(0xffffffffu, aa, o);
@@ -673,35 +715,12 @@ __global__ void __launch_bounds__(256) k_rescore(const RescoreParams p) {
     }
     if (AAm >= TWO53 * 0.5 && tid == 0) s_bad = 1;
     const double sqa = sqrt((double)AA);
-    for (int c = warp; c < n; c += 8) {
-      const uint32_t id = p.cand_id[(size_t)r * CAP + c];
-      long long g, l;
-      b_locate(p, id, g, l);
-      const long long* brow = p.b_counters + (((size_t)g * p.b_count + l) * p.d + i) * p.W;
-      long long bb = 0, ab = 0;
-      double mag = 0.0;
-      int badb = 0;
-      for (int j = lane; j < p.W; j += 32) {
-        const long long y = __ldg(brow + j);
-        const long long x = s_a[j];
-        if (y >= (1LL << 31) || y <= -(1LL << 31)) badb = 1;
-        bb += y * y;
-        ab += x * y;
-        mag += fabs((double)y * (double)y) + fabs((double)x * (double)y);
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        bb += __shfl_xor_sync(0xffffffffu, bb, o);
-        ab += __shfl_xor_sync(0xffffffffu, ab, o);
-        mag += __shfl_xor_sync(0xffffffffu, mag, o);
-        badb |= __shfl_xor_sync(0xffffffffu, badb, o);
-      }
-      if (lane == 0) {
-        if (badb || mag >= TWO53 * 0.5) s_bad = 1;
-        const double den = __dmul_rn(sqa, sqrt((double)bb));
-        if (den != 0.0) {
-          const double cs = __ddiv_rn((double)ab, den);
-          s_min[c] = cs < s_min[c] ? cs : s_min[c];  // Math.min, no NaN possible here
-        }
+    for (int c = tid; c < n; c += blockDim.x) {
+      if (s_mag[c] >= TWO53 * 0.5) s_bad = 1;
+      const double den = __dmul_rn(sqa, sqrt((double)s_bb[c]));
+      if (den != 0.0) {
+        const double cs = __ddiv_rn((double)s_ab[c], den);
+        s_min[c] = cs < s_min[c] ? cs : s_min[c];  // Math.min, no NaN possible here
       }
     }
     __syncthreads();
@@ -1248,11 +1267,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
       rp.out_cnt = a->out_cnt;
       rp.row_flag = (int32_t*)d_flag.p;
       rp.flag_count = (int32_t*)d_fcount.p;
-      const size_t smem = (size_t)a->width * sizeof(long long);
-      if (smem > ctx->smem_optin - 8192)
-        return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_cosine_topk: width %d too large for the re-score kernel", a->width);
-      MB_CUDA(ctx, cudaFuncSetAttribute(k_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_rescore<<<(unsigned)a->a_count, 256, smem, ctx->stream>>>(rp);
+      k_rescore<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp);
       ctx->launches++;
       MB_CUDA(ctx, cudaGetLastError());
       int32_t nflag = 0;
