@@ -51,7 +51,7 @@ def _peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU during the timed region (NVML)."""
 
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -295,6 +295,15 @@ def run_ours(args):
                "sample": f"first {sample} events of rank 0's stream, {cpu_dt:.1f} s; oracle/ C port "
                          "(the Java reference cannot run: no JVM in the image)"}
 
+    # free the sketch-stage buffers before the cosine stage
+    bank.close()
+    ebank.close()
+    del item, pref, hk, hp, counters
+    torch.cuda.empty_cache()
+    cosine = None
+    if not args.no_cosine:
+        cosine = run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, args.steps, args.warmup)
+
     if rank == 0:
         kern_s = (k_ms / max(k_n, 1)) * 1e-3
         achieved = ALGO_BYTES_PER_EVENT * n / kern_s / 1e9
@@ -310,17 +319,184 @@ def run_ours(args):
                     "sample": f"{e2e_n} events/step from pinned host memory through mb200_bank_update(MEM_HOST) "
                               "+ mb200_bank_read of the whole sketch"},
             "roofline": {"bound": "hbm", "kernel": "k_update_single", "achieved": achieved, "peak": peaks["hbm"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peaks["hbm"],
+                         # ncu --set full (profiles/r1_k_update_single_ncu.txt): 3.056 GB of DRAM traffic per
+                         # 2.5e8-event launch = 12.2 B/event; the counters (32 MiB) stay in L2
+                         "traffic": 12.2 * n,
                          "peak_source": peaks["source"], "algorithmic_bytes_per_event": ALGO_BYTES_PER_EVENT,
                          "kernel_ms_per_launch": kern_s * 1e3, "launches_timed": int(k_n),
                          "physical_event_read_GBps": physical,
                          "atomic_updates_per_s": DEPTH * n / kern_s},
-            "cpu_baseline": cpu, "parity": parity,
+            "cpu_baseline": cpu, "parity": parity, "cosine": cosine,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------------
+# cosine stage (BASELINE.json configs[2]): MovieLens-20M-shaped sketch build + all-pairs cosine top-50
+# ------------------------------------------------------------------------------------------------
+C3_USERS, C3_ITEMS, C3_EVENTS, C3_WIDTH, C3_DEPTH, C3_K = 138_493, 26_744, 20_000_000, 4096, 4, 50
+C3_SEED = 20240003
+
+
+def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup):
+    """One step = K2 normalise + all-gather of the 16-bit rows (N > 1) + K3 + K5 for this rank's block
+    row of the N x N similarity matrix.  Returns the `cosine` object of the JSON line (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    import mahout_b200 as mb
+    from mahout_b200 import _native as N
+    from mahout_b200 import similarity as sim
+    from mahout_b200 import synth
+    from mahout_b200.sketch import cosine_topk_blocks, last_fallback_rows
+
+    plan = sim.ShardPlan(C3_ITEMS, world, rank)
+    cdf = torch.from_numpy(synth.zipf_cdf(C3_ITEMS, ZIPF_S)).to(dev)
+    perm = torch.from_numpy(synth.rank_permutation(C3_ITEMS, 3) - 1).to(dev)     # item rows 0..N-1
+    user, item, pref = synth.events_device(ctx, C3_SEED, 0, C3_EVENTS, C3_USERS, cdf, perm)
+    mine = (item % world) == rank
+    lrow, luser, lpref = (item[mine] // world).contiguous(), user[mine].contiguous(), pref[mine].contiguous()
+    bank = mb.SketchBank(plan.rows_per_shard, C3_WIDTH, C3_DEPTH, SKETCH_SEED, 1, ctx)
+    ctx.set_profiling(True)
+    ctx.reset_profile()
+    bank.update(lrow, luser, lpref)
+    bank.check()
+    upd_ms, _ = ctx.kernel_time(N.K_UPDATE)
+    n_local = int(lrow.numel())
+
+    ld = int(N.lib().mb200_row_ld(C3_WIDTH))
+    vw = int(N.lib().mb200_valid_words(plan.rows_per_shard))
+    a_rows = torch.empty((C3_DEPTH, plan.rows_per_shard, ld), dtype=torch.float16, device=dev)
+    a_valid = torch.empty((C3_DEPTH, vw), dtype=torch.int32, device=dev)
+    b_rows = torch.empty((world,) + tuple(a_rows.shape), dtype=torch.float16, device=dev) if world > 1 else None
+    b_valid = torch.empty((world,) + tuple(a_valid.shape), dtype=torch.int32, device=dev) if world > 1 else None
+    a_cnt = bank.counters_tensor()
+    b_id = (world, 1) if world > 1 else (1, plan.rows_per_shard)
+    out = {}
+
+    def step(precision, b_cnt=None):
+        N.check(N.lib().mb200_bank_normalize(bank.handle, N.DTYPE_F16, C.c_void_p(a_rows.data_ptr()),
+                                             C.c_void_p(a_valid.data_ptr())), ctx.handle)
+        if world > 1:
+            dist.all_gather_into_tensor(b_rows.view(-1, plan.rows_per_shard, ld), a_rows)
+            dist.all_gather_into_tensor(b_valid.view(-1, vw), a_valid)
+            br, bv = b_rows, b_valid
+        else:
+            br, bv = a_rows.unsqueeze(0), a_valid.unsqueeze(0)
+        return cosine_topk_blocks(ctx, a_rows, a_valid, br, bv, C3_DEPTH, C3_WIDTH, C3_K, a_id=(world, rank),
+                                  b_id=b_id, dtype="f16", precision=precision,
+                                  a_counters=a_cnt if precision == "rescored" else None, b_counters=b_cnt)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        step("tensor")
+    barrier()
+    ctx.reset_profile()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        idx, s, cnt = step("tensor")
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    k2_ms, k2_n = ctx.kernel_time(N.K_NORMALIZE)
+    k3_ms, k3_n = ctx.kernel_time(N.K_COSINE)
+    k5_ms, k5_n = ctx.kernel_time(N.K_RESCORE)
+    launches = ctx.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # exact (re-scored) variant, timed once
+    b_cnt = a_cnt
+    if world > 1:
+        b_cnt = torch.empty((world,) + tuple(a_cnt.shape), dtype=a_cnt.dtype, device=dev)
+        dist.all_gather_into_tensor(b_cnt.view(-1, C3_DEPTH, C3_WIDTH), a_cnt)
+    barrier()
+    ctx.reset_profile()
+    t0 = time.perf_counter()
+    ridx, rs, rcnt = step("rescored", b_cnt)
+    barrier()
+    rescored_ms = (time.perf_counter() - t0) * 1e3
+    r5_ms, _ = ctx.kernel_time(N.K_RESCORE)
+    fallback = last_fallback_rows(ctx)
+    ctx.set_profiling(False)
+
+    if rank == 0:
+        import oracle as orc
+        pairs = float(C3_ITEMS) ** 2
+        flops_rank = 2.0 * C3_DEPTH * plan.rows_per_shard * (plan.rows_per_shard * world) * ld
+        k3_s = k3_ms / max(k3_n, 1) * 1e-3
+        achieved = flops_rank / k3_s / 1e12
+        # parity + CPU baseline on sampled rows of shard 0 (the oracle needs the whole bank)
+        if world > 1:
+            full = b_cnt.cpu().numpy()                                           # [G, E_loc, d, w] quanta
+            bank_host = np.zeros((plan.rows_per_shard * world, C3_DEPTH, C3_WIDTH))
+            for g in range(world):
+                bank_host[g::world] = full[g] * 0.5
+        else:
+            bank_host = bank.read()
+        rows_chk = 32
+        threads = orc.max_threads()
+        t0 = time.perf_counter()
+        oi, osim, oc = [], [], []
+        for l in range(rows_chk):
+            r = l * world
+            i1, s1, c1 = orc.bank_cosine_topk(bank_host, C3_K, r0=r, r1=r + 1, nthreads=threads)
+            oi.append(i1[0]); osim.append(s1[0]); oc.append(c1[0])
+        cpu_s = time.perf_counter() - t0
+        oi, osim, oc = np.array(oi), np.array(osim), np.array(oc)
+        gi, gs, gc = ridx[:rows_chk].cpu().numpy(), rs[:rows_chk].cpu().numpy(), rcnt[:rows_chk].cpu().numpy()
+        ti, ts, tc = idx[:rows_chk].cpu().numpy(), s[:rows_chk].cpu().numpy(), cnt[:rows_chk].cpu().numpy()
+        exact_equal = bool((gi == oi).all() and (gc == oc).all() and gs.tobytes() == osim.tobytes())
+        # tensor precision: value of every returned pair vs the oracle's FP64 cosine of that pair
+        max_rel, overlap, tot = 0.0, 0, 0
+        for l in range(rows_chk):
+            o = dict(zip(oi[l, :oc[l]].tolist(), osim[l, :oc[l]].tolist()))
+            for c, v in zip(ti[l, :tc[l]].tolist(), ts[l, :tc[l]].tolist()):
+                if c in o:
+                    overlap += 1
+                    max_rel = max(max_rel, abs(v - o[c]) / abs(o[c]))
+            tot += int(oc[l])
+        out = {
+            "metric": "item_pair_cosine_sims_per_sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
+            "ms_per_step": ms, "steps": steps, "warmup": warmup, "n_gpus": world, "scaling": "strong",
+            "dtype": "f16 rows (x/||x|| * 2^12), f32 accumulate in TMEM; re-score in exact int64/f64",
+            "config": {"workload": "configs[2]: MovieLens-20M-shaped synthetic (138493 users x 26744 items, 2e7 "
+                                   "Zipf(1.1) events), sketch d=4 x W=4096, cosine top-50 per item",
+                       "precision_timed": "tensor", "items": C3_ITEMS, "depth": C3_DEPTH, "width": C3_WIDTH,
+                       "k": C3_K, "parallelism": f"item-hash sharded x{world} + all-gather of f16 rows"
+                       if world > 1 else "single GPU"},
+            "kernels_ms_per_step": {"K2_normalize": k2_ms / max(k2_n, 1), "K3_cosine_topk": k3_ms / max(k3_n, 1),
+                                    "K5_merge": k5_ms / max(k5_n, 1)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "k_cosine<256,1,true>", "achieved": achieved,
+                         "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
+                         "frac_of_burst_peak": achieved / peaks["bf16_burst"], "peak_source": peaks["source"],
+                         "flops_per_launch": flops_rank, "kernel_ms_per_launch": k3_s * 1e3, "traffic": None},
+            "rescored": {"ms_per_step": rescored_ms, "K5_merge_rescore_ms": r5_ms, "fallback_rows": int(fallback),
+                         "pairs_per_s": pairs / (rescored_ms * 1e-3)},
+            "sketch_build": {"events_per_s": n_local / (upd_ms * 1e-3) if upd_ms > 0 else None,
+                             "kernel": "k_update_bank", "events": n_local, "ms": upd_ms,
+                             "hbm_frac": (ALGO_BYTES_PER_EVENT * n_local / (upd_ms * 1e-3) / 1e9 / peaks["hbm"])
+                             if upd_ms > 0 else None},
+            "parity": {"rows_checked": rows_chk, "rescored_topk_and_sims_equal_oracle": exact_equal,
+                       "tensor_max_rel_err": max_rel, "tensor_topk_overlap": overlap / max(tot, 1)},
+            "cpu_baseline": {"value": rows_chk * C3_ITEMS / cpu_s, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": f"{rows_chk} rows x all {C3_ITEMS} columns, {cpu_s:.1f} s; oracle/ C port of "
+                                       "DoubleCountMinSketch.cosine + top-k"},
+        }
+    bank.close()
+    return out
 
 
 def main():
@@ -331,6 +507,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=float, default=1e9, help="events per step per GPU")
     ap.add_argument("--e2e-events", type=float, default=float(1 << 27))
+    ap.add_argument("--no-cosine", action="store_true", help="skip the secondary cosine-stage measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -60,6 +60,9 @@ const char* mb200_last_error(mb200_ctx* ctx); /* ctx may be NULL: error of the f
  * context's own stream).  Lets the caller bracket calls with its own CUDA events. */
 int mb200_set_stream(mb200_ctx* ctx, void* cuda_stream);
 int mb200_sync(mb200_ctx* ctx);
+/* the cosine stage keeps its device workspaces (candidate lists, gathered rows of the single-GPU
+ * convenience call) on the context between calls; this frees them */
+int mb200_release_workspace(mb200_ctx* ctx);
 
 /* kernel ids for mb200_kernel_time */
 #define MB200_K_UPDATE 0     /* K1 sketch update                 */

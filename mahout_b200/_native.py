@@ -60,6 +60,7 @@ _PROTOS = {
     "mb200_last_error": (C.c_char_p, [vp]),
     "mb200_set_stream": (C.c_int, [vp, vp]),
     "mb200_sync": (C.c_int, [vp]),
+    "mb200_release_workspace": (C.c_int, [vp]),
     "mb200_set_profiling": (C.c_int, [vp, C.c_int]),
     "mb200_kernel_time": (C.c_int, [vp, C.c_int, C.POINTER(f64), C.POINTER(i64)]),
     "mb200_reset_profile": (C.c_int, [vp]),

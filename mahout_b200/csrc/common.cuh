@@ -47,6 +47,18 @@ struct mb200_ctx {
   size_t stage_bytes = 0;
   cudaEvent_t stage_free[2] = {nullptr, nullptr};
   cudaEvent_t stage_full[2] = {nullptr, nullptr};
+  // grow-only device workspaces of the cosine stage (slot i = i-th request of a call); cudaMalloc /
+  // cudaFree of a few hundred MB per call would otherwise cost more than the kernels
+  std::vector<std::pair<void*, size_t>> ws;
+  int64_t last_fallback_rows = 0;
+};
+
+// borrows workspace slots from the context in request order; nothing is freed on return
+struct Workspace {
+  mb200_ctx* ctx;
+  size_t next = 0;
+  explicit Workspace(mb200_ctx* c) : ctx(c) {}
+  int get(size_t bytes, void** out);
 };
 
 struct mb200_bank {

@@ -959,20 +959,10 @@ static int make_tmap(mb200_ctx* ctx, CUtensorMap* tm, int dtype, const void* bas
   return MB200_OK;
 }
 
+// a workspace slot borrowed from the context (see Workspace in common.cuh)
 struct DevBuf {
   void* p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
-  }
-  int alloc(mb200_ctx* ctx, size_t bytes) {
-    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-    if (e != cudaSuccess) {
-      p = nullptr;
-      return mb200_fail(ctx, MB200_ERR_OOM, "cosine: cannot allocate %zu bytes of workspace: %s", bytes,
-                        cudaGetErrorString(e));
-    }
-    return MB200_OK;
-  }
+  int alloc(Workspace& ws, size_t bytes) { return ws.get(bytes, &p); }
 };
 
 template <int BN, int ACC, bool HM>
@@ -990,7 +980,6 @@ static int launch_cosine(mb200_ctx* ctx, const CUtensorMap& tmA, const CUtensorM
   return MB200_OK;
 }
 
-static int64_t g_last_fallback_rows = 0;
 
 extern "C" {
 
@@ -999,7 +988,7 @@ int64_t mb200_valid_words(int64_t rows) { return (rows + 255) / 256 * 8; }
 
 int mb200_cosine_last_fallback_rows(mb200_ctx* ctx, int64_t* rows) {
   if (!ctx || !rows) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_last_fallback_rows: NULL argument");
-  *rows = g_last_fallback_rows;
+  *rows = ctx->last_fallback_rows;
   return MB200_OK;
 }
 
@@ -1033,7 +1022,22 @@ int mb200_bank_normalize(mb200_bank* bk, int dtype, void* rows16, uint32_t* vali
   return normalize_locked(bk, dtype, rows16, valid);
 }
 
-static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
+#include <chrono>
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#define TRACE(label)                                                              \
+  do {                                                                            \
+    if (trace) {                                                                  \
+      double t_ = now_ms();                                                       \
+      fprintf(stderr, "[mb200 trace] %-18s +%.3f ms\n", label, t_ - t_last);      \
+      t_last = t_;                                                                \
+    }                                                                             \
+  } while (0)
+
+static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Workspace& ws) {
+  const bool trace = getenv("MB200_TRACE") != nullptr;
+  double t_last = now_ms();
   if (!a) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: args is NULL");
   if (!a->a_rows || !a->a_valid || !a->b_rows || !a->b_valid || !a->out_idx || !a->out_sim || !a->out_cnt)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: NULL pointer argument");
@@ -1122,16 +1126,17 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
     }
   }
   DevBuf d_items, d_slot, d_lists, d_cnt, d_bound, d_rowthr;
-  MB_CHECK(d_rowthr.alloc(ctx, (size_t)num_m * BM * sizeof(uint32_t)));
+  MB_CHECK(d_rowthr.alloc(ws, (size_t)num_m * BM * sizeof(uint32_t)));
   MB_CUDA(ctx, cudaMemsetAsync(d_rowthr.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
-  MB_CHECK(d_items.alloc(ctx, items.size() * sizeof(int2)));
-  MB_CHECK(d_slot.alloc(ctx, slot_of.size() * sizeof(int32_t)));
+  MB_CHECK(d_items.alloc(ws, items.size() * sizeof(int2)));
+  MB_CHECK(d_slot.alloc(ws, slot_of.size() * sizeof(int32_t)));
   const size_t nlists = (size_t)num_items * 2 * BM;
-  MB_CHECK(d_lists.alloc(ctx, nlists * CAP * sizeof(uint2)));
-  MB_CHECK(d_cnt.alloc(ctx, nlists * sizeof(int32_t)));
-  MB_CHECK(d_bound.alloc(ctx, nlists * sizeof(float)));
+  MB_CHECK(d_lists.alloc(ws, nlists * CAP * sizeof(uint2)));
+  MB_CHECK(d_cnt.alloc(ws, nlists * sizeof(int32_t)));
+  MB_CHECK(d_bound.alloc(ws, nlists * sizeof(float)));
   MB_CUDA(ctx, cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
   MB_CUDA(ctx, cudaMemcpyAsync(d_slot.p, slot_of.data(), slot_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  TRACE("alloc+items");
 
   // tensor maps
   alignas(64) CUtensorMap tmA, tmB;
@@ -1186,12 +1191,14 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
   p.dense_ld = a->dense_ld;
   p.inv_scale2 = 1.0f / scale2;
   p.idesc = umma_idesc_f16(a->dtype == MB200_DTYPE_BF16 ? 1 : 0, BM, BN);
-  p.policy_a = L2_EVICT_LAST;   // an A block is re-read for every B tile of the sweep
-  p.policy_b = L2_EVICT_FIRST;  // a B tile is shared only by the CTAs sweeping it right now
+  // L2 eviction priorities: measured on config 3, evict_last(A)/evict_first(B) loses ~25 % against
+  // the default policy (profiles/r1_cosine_tuning.md), so both operands use evict_normal
+  p.policy_a = L2_EVICT_NORMAL;
+  p.policy_b = L2_EVICT_NORMAL;
   if (const char* ev = getenv("MB200_COS_HINTS")) {
     const int h = atoi(ev);
-    p.policy_a = h == 0 ? L2_EVICT_NORMAL : (h == 2 ? L2_EVICT_NORMAL : L2_EVICT_LAST);
-    p.policy_b = h == 0 ? L2_EVICT_NORMAL : L2_EVICT_FIRST;
+    if (h == 1) p.policy_a = L2_EVICT_LAST;
+    if (h >= 1) p.policy_b = L2_EVICT_FIRST;
   }
   const int grid = std::min(num_items, P);
   {
@@ -1205,6 +1212,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
     }
   }
   ctx->launches++;
+  TRACE("launch K3");
 
   // merge (+ re-score)
   DevBuf d_cand, d_ccnt, d_cbound, d_flag, d_fcount;
@@ -1225,17 +1233,17 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
   mp.out_sim = a->out_sim;
   mp.out_cnt = a->out_cnt;
   if (rescored) {
-    MB_CHECK(d_cand.alloc(ctx, (size_t)a->a_count * CAP * sizeof(uint32_t)));
-    MB_CHECK(d_ccnt.alloc(ctx, (size_t)a->a_count * sizeof(int32_t)));
-    MB_CHECK(d_cbound.alloc(ctx, (size_t)a->a_count * sizeof(float)));
-    MB_CHECK(d_flag.alloc(ctx, (size_t)a->a_count * sizeof(int32_t)));
-    MB_CHECK(d_fcount.alloc(ctx, 2 * sizeof(int32_t)));
+    MB_CHECK(d_cand.alloc(ws, (size_t)a->a_count * CAP * sizeof(uint32_t)));
+    MB_CHECK(d_ccnt.alloc(ws, (size_t)a->a_count * sizeof(int32_t)));
+    MB_CHECK(d_cbound.alloc(ws, (size_t)a->a_count * sizeof(float)));
+    MB_CHECK(d_flag.alloc(ws, (size_t)a->a_count * sizeof(int32_t)));
+    MB_CHECK(d_fcount.alloc(ws, 2 * sizeof(int32_t)));
     MB_CUDA(ctx, cudaMemsetAsync(d_fcount.p, 0, 2 * sizeof(int32_t), ctx->stream));
     mp.cand_id = (uint32_t*)d_cand.p;
     mp.cand_cnt = (int32_t*)d_ccnt.p;
     mp.cand_bound = (float*)d_cbound.p;
   }
-  g_last_fallback_rows = 0;
+  ctx->last_fallback_rows = 0;
   {
     ProfScope prof(ctx, MB200_K_RESCORE);
     k_merge<<<(unsigned)((a->a_count + 7) / 8), 256, 0, ctx->stream>>>(mp);
@@ -1273,17 +1281,17 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
       int32_t nflag = 0;
       MB_CUDA(ctx, cudaMemcpyAsync(&nflag, d_fcount.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      g_last_fallback_rows = nflag;
+      ctx->last_fallback_rows = nflag;
       if (nflag > 0) {
         // exact full-row path, in batches bounded by scratch memory
         rp.b_id_add = p.b_id_add;  // forward mapping for k_exact_*
         DevBuf d_rows, d_scratch;
-        MB_CHECK(d_rows.alloc(ctx, (size_t)nflag * sizeof(int32_t)));
+        MB_CHECK(d_rows.alloc(ws, (size_t)nflag * sizeof(int32_t)));
         k_collect_flagged<<<(unsigned)((a->a_count + 255) / 256), 256, 0, ctx->stream>>>(
             rp.row_flag, a->a_count, (int32_t*)d_rows.p, rp.flag_count + 1);
         ctx->launches++;
         const int batch = (int)std::max<int64_t>(1, std::min<int64_t>(nflag, (1LL << 30) / (total_b * 8)));
-        MB_CHECK(d_scratch.alloc(ctx, (size_t)batch * total_b * sizeof(double)));
+        MB_CHECK(d_scratch.alloc(ws, (size_t)batch * total_b * sizeof(double)));
         for (int off = 0; off < nflag; off += batch) {
           const int m = std::min(batch, nflag - off);
           k_exact_rows<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, 1.0, 1.0, (double*)d_scratch.p, total_b);
@@ -1295,7 +1303,9 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a) {
       }
     }
   }
-  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // workspaces are freed on return
+  TRACE("launch K5");
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // results are complete on return
+  TRACE("sync");
   return MB200_OK;
 }
 
@@ -1311,8 +1321,9 @@ int mb200_bank_cosine_topk(mb200_bank* bk, int32_t k, double threshold, int excl
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t ld = mb200_row_ld(bk->W), vw = mb200_valid_words(bk->E);
   DevBuf rows, valid, o_idx, o_sim, o_cnt;
-  MB_CHECK(rows.alloc(ctx, (size_t)bk->d * bk->E * ld * 2));
-  MB_CHECK(valid.alloc(ctx, (size_t)bk->d * vw * sizeof(uint32_t)));
+  Workspace ws(ctx);
+  MB_CHECK(rows.alloc(ws, (size_t)bk->d * bk->E * ld * 2));
+  MB_CHECK(valid.alloc(ws, (size_t)bk->d * vw * sizeof(uint32_t)));
   MB_CHECK(normalize_locked(bk, dtype, rows.p, (uint32_t*)valid.p));
   mb200_cosine_args a;
   memset(&a, 0, sizeof(a));
@@ -1333,9 +1344,9 @@ int mb200_bank_cosine_topk(mb200_bank* bk, int32_t k, double threshold, int excl
   a.exclude_self = exclude_self;
   a.a_counters = a.b_counters = (const int64_t*)bk->counters;
   if (mem == MB200_MEM_HOST) {
-    MB_CHECK(o_idx.alloc(ctx, (size_t)bk->E * k * 8));
-    MB_CHECK(o_sim.alloc(ctx, (size_t)bk->E * k * 8));
-    MB_CHECK(o_cnt.alloc(ctx, (size_t)bk->E * 4));
+    MB_CHECK(o_idx.alloc(ws, (size_t)bk->E * k * 8));
+    MB_CHECK(o_sim.alloc(ws, (size_t)bk->E * k * 8));
+    MB_CHECK(o_cnt.alloc(ws, (size_t)bk->E * 4));
     a.out_idx = (int64_t*)o_idx.p;
     a.out_sim = (double*)o_sim.p;
     a.out_cnt = (int32_t*)o_cnt.p;
@@ -1344,7 +1355,7 @@ int mb200_bank_cosine_topk(mb200_bank* bk, int32_t k, double threshold, int excl
     a.out_sim = out_sim;
     a.out_cnt = out_cnt;
   }
-  MB_CHECK(cosine_topk_locked(ctx, &a));
+  MB_CHECK(cosine_topk_locked(ctx, &a, ws));
   if (mem == MB200_MEM_HOST) {
     MB_CUDA(ctx, cudaMemcpyAsync(out_idx, o_idx.p, (size_t)bk->E * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(ctx, cudaMemcpyAsync(out_sim, o_sim.p, (size_t)bk->E * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1357,7 +1368,8 @@ int mb200_bank_cosine_topk(mb200_bank* bk, int32_t k, double threshold, int excl
 int mb200_cosine_topk(mb200_ctx* ctx, const mb200_cosine_args* args) {
   if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_cosine_topk: ctx is NULL");
   std::lock_guard<std::mutex> g(ctx->mu);
-  return cosine_topk_locked(ctx, args);
+  Workspace ws(ctx);
+  return cosine_topk_locked(ctx, args, ws);
 }
 
 }  // extern "C"

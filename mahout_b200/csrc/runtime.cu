@@ -20,6 +20,25 @@ int mb200_fail(mb200_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
+int Workspace::get(size_t bytes, void** out) {
+  if (next >= ctx->ws.size()) ctx->ws.emplace_back(nullptr, 0);
+  auto& slot = ctx->ws[next++];
+  if (slot.second < bytes || !slot.first) {
+    if (slot.first) cudaFree(slot.first);
+    slot.first = nullptr;
+    slot.second = 0;
+    const size_t want = bytes ? bytes : 1;
+    cudaError_t e = cudaMalloc(&slot.first, want);
+    if (e != cudaSuccess) {
+      slot.first = nullptr;
+      return mb200_fail(ctx, MB200_ERR_OOM, "cannot allocate %zu bytes of workspace: %s", want, cudaGetErrorString(e));
+    }
+    slot.second = want;
+  }
+  *out = slot.first;
+  return MB200_OK;
+}
+
 ProfScope::ProfScope(mb200_ctx* c, int kernel_id) : ctx(c) {
   if (!ctx->profiling) return;
   ProfSpan s;
@@ -103,6 +122,8 @@ int mb200_destroy(mb200_ctx* ctx) {
     cudaEventDestroy(s.end);
   }
   for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
+  for (auto& w : ctx->ws)
+    if (w.first) cudaFree(w.first);
   for (int i = 0; i < 2; i++) {
     if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     cudaEventDestroy(ctx->stage_free[i]);
@@ -117,6 +138,17 @@ int mb200_destroy(mb200_ctx* ctx) {
 const char* mb200_last_error(mb200_ctx* ctx) {
   if (ctx && !ctx->err.empty()) return ctx->err.c_str();
   return g_last_error.c_str();
+}
+
+int mb200_release_workspace(mb200_ctx* ctx) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_release_workspace: ctx is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& w : ctx->ws)
+    if (w.first) cudaFree(w.first);
+  ctx->ws.clear();
+  return MB200_OK;
 }
 
 int mb200_set_stream(mb200_ctx* ctx, void* cuda_stream) {
