@@ -1,0 +1,115 @@
+/*
+ * JNI glue: Java_org_apache_mahout_cf_taste_impl_common_NativeSketch_* -> include/mahout_b200.h.
+ * 1:1, no logic.  Status codes map to exceptions the reference throws at the same places:
+ *   MB200_ERR_BAD_ARG            -> IllegalArgumentException (Guava Preconditions, DoubleCountMinSketch.java:117)
+ *   MB200_ERR_CM_DELTA/_EPSILON  -> IllegalArgumentException carrying the CMException text
+ *   everything else              -> org.apache.mahout.cf.taste.common.TasteException
+ *
+ * NOT BUILT IN THIS REPOSITORY: the image has no jni.h.  Build where a JDK exists with
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude \
+ *       jni/mahout_b200_jni.c -Lmahout_b200 -lmahout_b200 -o libmahout_b200_jni.so
+ */
+#include <jni.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "mahout_b200.h"
+
+#define JNI_FN(name) Java_org_apache_mahout_cf_taste_impl_common_NativeSketch_##name
+
+static void throw_status(JNIEnv* env, int rc, mb200_ctx* ctx) {
+  const char* cls = (rc == MB200_ERR_BAD_ARG || rc == MB200_ERR_CM_DELTA || rc == MB200_ERR_CM_EPSILON)
+                        ? "java/lang/IllegalArgumentException"
+                        : "org/apache/mahout/cf/taste/common/TasteException";
+  (*env)->ThrowNew(env, (*env)->FindClass(env, cls), mb200_last_error(ctx));
+}
+#define CHECK(rc, ctx) do { int rc_ = (rc); if (rc_ != MB200_OK) { throw_status(env, rc_, (ctx)); } } while (0)
+
+JNIEXPORT jlong JNICALL JNI_FN(createContext)(JNIEnv* env, jclass c, jint device) {
+  mb200_ctx* ctx = NULL;
+  CHECK(mb200_create(device, &ctx), NULL);
+  return (jlong)(intptr_t)ctx;
+}
+
+JNIEXPORT void JNICALL JNI_FN(destroyContext)(JNIEnv* env, jclass c, jlong ctx) {
+  mb200_destroy((mb200_ctx*)(intptr_t)ctx);
+}
+
+JNIEXPORT void JNICALL JNI_FN(hashParams)(JNIEnv* env, jclass c, jlong seed, jint depth, jlongArray a, jlongArray b) {
+  jlong* pa = (*env)->GetLongArrayElements(env, a, NULL);
+  jlong* pb = (*env)->GetLongArrayElements(env, b, NULL);
+  int rc = mb200_hash_params(seed, depth, (int64_t*)pa, (int64_t*)pb);
+  (*env)->ReleaseLongArrayElements(env, a, pa, 0);
+  (*env)->ReleaseLongArrayElements(env, b, pb, 0);
+  CHECK(rc, NULL);
+}
+
+JNIEXPORT jlong JNICALL JNI_FN(createBank)(JNIEnv* env, jclass c, jlong ctx, jlong entities, jint depth, jint width,
+                                           jlongArray a, jlongArray b, jint fracBits) {
+  mb200_bank* bank = NULL;
+  jlong* pa = (*env)->GetLongArrayElements(env, a, NULL);
+  jlong* pb = (*env)->GetLongArrayElements(env, b, NULL);
+  int rc = mb200_bank_create_params((mb200_ctx*)(intptr_t)ctx, entities, depth, width, (int64_t*)pa, (int64_t*)pb,
+                                    fracBits, &bank);
+  (*env)->ReleaseLongArrayElements(env, a, pa, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, b, pb, JNI_ABORT);
+  CHECK(rc, (mb200_ctx*)(intptr_t)ctx);
+  return (jlong)(intptr_t)bank;
+}
+
+JNIEXPORT void JNICALL JNI_FN(destroyBank)(JNIEnv* env, jclass c, jlong bank) {
+  mb200_bank_destroy((mb200_bank*)(intptr_t)bank);
+}
+
+JNIEXPORT void JNICALL JNI_FN(update)(JNIEnv* env, jclass c, jlong bank, jobject entity, jobject key, jobject inc, jlong n) {
+  const int64_t* e = entity ? (const int64_t*)(*env)->GetDirectBufferAddress(env, entity) : NULL;
+  const int64_t* k = (const int64_t*)(*env)->GetDirectBufferAddress(env, key);
+  const float* v = (const float*)(*env)->GetDirectBufferAddress(env, inc);
+  CHECK(mb200_bank_update((mb200_bank*)(intptr_t)bank, e, k, v, n, MB200_MEM_HOST), NULL);
+}
+
+JNIEXPORT void JNICALL JNI_FN(updateOne)(JNIEnv* env, jclass c, jlong bank, jlong entity, jlong key, jdouble inc) {
+  int64_t e = entity, k = key;
+  double v = inc;
+  CHECK(mb200_bank_update_f64((mb200_bank*)(intptr_t)bank, &e, &k, &v, 1, MB200_MEM_HOST), NULL);
+}
+
+JNIEXPORT jdouble JNICALL JNI_FN(query)(JNIEnv* env, jclass c, jlong bank, jlong entity, jlong key) {
+  int64_t e = entity, k = key;
+  double out = 0.0;
+  CHECK(mb200_bank_query((mb200_bank*)(intptr_t)bank, &e, &k, 1, &out, MB200_MEM_HOST), NULL);
+  return out;
+}
+
+JNIEXPORT jdouble JNICALL JNI_FN(cosine)(JNIEnv* env, jclass c, jlong bankA, jlong ea, jlong bankB, jlong eb) {
+  int64_t a = ea, b = eb;
+  double out = 0.0;
+  CHECK(mb200_bank_cross_cosine((mb200_bank*)(intptr_t)bankA, &a, (mb200_bank*)(intptr_t)bankB, &b, 1, &out,
+                                MB200_MEM_HOST), NULL);
+  return out;
+}
+
+JNIEXPORT void JNICALL JNI_FN(cosineTopK)(JNIEnv* env, jclass c, jlong bank, jint k, jdouble threshold,
+                                          jboolean excludeSelf, jint dtype, jint precision, jlongArray outIdx,
+                                          jdoubleArray outSim, jintArray outCnt) {
+  jlong* pi = (*env)->GetLongArrayElements(env, outIdx, NULL);
+  jdouble* ps = (*env)->GetDoubleArrayElements(env, outSim, NULL);
+  jint* pc = (*env)->GetIntArrayElements(env, outCnt, NULL);
+  int rc = mb200_bank_cosine_topk((mb200_bank*)(intptr_t)bank, k, threshold, excludeSelf, dtype, precision,
+                                  (int64_t*)pi, ps, (int32_t*)pc, MB200_MEM_HOST);
+  (*env)->ReleaseLongArrayElements(env, outIdx, pi, 0);
+  (*env)->ReleaseDoubleArrayElements(env, outSim, ps, 0);
+  (*env)->ReleaseIntArrayElements(env, outCnt, pc, 0);
+  CHECK(rc, NULL);
+}
+
+JNIEXPORT jobject JNICALL JNI_FN(allocPinned)(JNIEnv* env, jclass c, jlong bytes) {
+  void* p = NULL;
+  CHECK(mb200_host_alloc(bytes, &p), NULL);
+  return p ? (*env)->NewDirectByteBuffer(env, p, bytes) : NULL;
+}
+
+JNIEXPORT void JNICALL JNI_FN(freePinned)(JNIEnv* env, jclass c, jobject buffer) {
+  mb200_host_free((*env)->GetDirectBufferAddress(env, buffer));
+}
+/* clearBank, check, queryMany, read, cmDims follow the same pattern (one C call each). */

@@ -125,3 +125,12 @@ int main(int argc, char** argv) {
         out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
     want = [((a * k + b) % P) % w for a, b, k, w in cases]
     assert [int(x) for x in out] == want
+
+
+def test_jni_glue_type_checks():
+    """jni/mahout_b200_jni.c cannot be built without a JDK; it must at least type-check against
+    include/mahout_b200.h (a stub jni.h supplies the JNI declarations it uses)."""
+    import subprocess
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-parameter",
+                           "-I", os.path.join(ROOT, "tests", "jni_stub"), "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "jni", "mahout_b200_jni.c")])

@@ -220,3 +220,36 @@ def test_synth_stream_device_equals_numpy(mb, ctx):
     # Zipf head really is heavy
     top = perm[0]
     assert (hi == top).mean() > 0.05
+
+
+def test_cosine_cm_user_similarity(mb, ctx):
+    """CosineCM.userSimilarity / exported profiles / the point query of doEstimatePreference."""
+    from mahout_b200.cosinecm import CosineCM
+    rng = np.random.Generator(np.random.PCG64(21))
+    n, users, items, w, d = 3000, 40, 300, 256, 3
+    user = rng.integers(100, 100 + users, n).astype(np.int64) * 7       # arbitrary (non-dense) user IDs
+    item = rng.integers(1, items, n).astype(np.int64)
+    pref = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
+    cm = CosineCM(user, item, pref, w, d, mb.HashFunctionBuilder(42), ctx=ctx)
+    a, b = orc.hash_params(42, d)
+    ids = np.unique(user)
+    ref = {}
+    for u in ids:
+        c = np.zeros((d, w))
+        m = user == u
+        orc.cm_update(c, w, d, a, b, item[m], pref[m].astype(np.float64))
+        ref[int(u)] = c
+    for u1, u2 in [(ids[0], ids[1]), (ids[3], ids[3]), (ids[5], ids[17])]:
+        want = orc.clamp_similarity(orc.cm_cosine(ref[int(u1)], ref[int(u2)], w, d))
+        assert abs(cm.userSimilarity(int(u1), int(u2)) - want) < 1e-12
+    assert cm.getExportedCMProfile(int(ids[2])).tobytes() == ref[int(ids[2])].tobytes()
+    u = int(ids[4])
+    it = int(item[user == u][0])
+    assert cm.estimatePreference(u, it) == float(np.float32(orc.cm_get(ref[u], w, d, a, b, it)))
+    with pytest.raises(KeyError):
+        cm.userSimilarity(1, 2)
+    with pytest.raises(RuntimeError, match="CountMinSketch error"):
+        CosineCM(user, item, pref, 0.9, 0.01, 42, ctx=ctx)
+    near, sims = cm.mostSimilarUserIDs(u, 5)
+    assert len(near) == 5 and u not in near.tolist() and (np.diff(sims) <= 0).all()
+    cm.close()
