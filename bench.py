@@ -98,6 +98,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def _host_threads() -> int:
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle's OpenMP
+    regions take an explicit thread count)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def _physical_gpu_index(local: int) -> int:
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -128,7 +137,7 @@ def run_reference(args):
         return
     import oracle as orc
     from mahout_b200 import synth
-    threads = orc.max_threads()
+    threads = _host_threads()
     cdf = synth.zipf_cdf(ITEMS, ZIPF_S)
     _, item, pref = synth.events_numpy(SEED, 0, 1 << 22, USERS, cdf)
     rate, _, _ = _cpu_update_rate(item, pref, threads)           # calibration
@@ -280,10 +289,10 @@ def run_ours(args):
     parity = None
     if rank == 0:
         import oracle as orc
-        threads = orc.max_threads()
+        threads = _host_threads()
         cal = 1 << 22
         rate, _, _ = _cpu_update_rate(item[:cal].cpu().numpy(), pref[:cal].cpu().numpy(), threads)
-        sample = int(min(max(rate * 12.0, 1 << 25), 1 << 28, n))
+        sample = int(min(max(rate * (12.0 if world == 1 else 2.0), 1 << 25), 1 << 28, n))
         cpu_rate, cpu_dt, cpu_bank = _cpu_update_rate(item[:sample].cpu().numpy(),
                                                       pref[:sample].cpu().numpy(), threads)
         pbank = mb.SketchBank(1, WIDTH, DEPTH, SKETCH_SEED, 1, ctx)
@@ -445,8 +454,8 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                 bank_host[g::world] = full[g] * 0.5
         else:
             bank_host = bank.read()
-        rows_chk = 32
-        threads = orc.max_threads()
+        rows_chk = 32 if world == 1 else 8
+        threads = _host_threads()
         t0 = time.perf_counter()
         oi, osim, oc = [], [], []
         for l in range(rows_chk):
@@ -482,7 +491,10 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
             "roofline": {"bound": "tensor", "kernel": "k_cosine<256,1,true>", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
                          "frac_of_burst_peak": achieved / peaks["bf16_burst"], "peak_source": peaks["source"],
-                         "flops_per_launch": flops_rank, "kernel_ms_per_launch": k3_s * 1e3, "traffic": None},
+                         "flops_per_launch": flops_rank, "kernel_ms_per_launch": k3_s * 1e3,
+                         # ncu --set full of this kernel on this workload at 1 GPU
+                         # (profiles/r1_k_cosine_final_ncu.txt): dram read 69.06 GB + write 0.79 GB
+                         "traffic": 69.85e9 if world == 1 else None},
             "rescored": {"ms_per_step": rescored_ms, "K5_merge_rescore_ms": r5_ms, "fallback_rows": int(fallback),
                          "pairs_per_s": pairs / (rescored_ms * 1e-3)},
             "sketch_build": {"events_per_s": n_local / (upd_ms * 1e-3) if upd_ms > 0 else None,

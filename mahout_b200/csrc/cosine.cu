@@ -630,6 +630,90 @@ __device__ __forceinline__ void b_locate(const RescoreParams& p, uint32_t id, lo
 #define TWO53 9007199254740992.0
 #define JAVA_MAX_DOUBLE 1.7976931348623157e308
 
+// Ordering, certification and output of one row's re-scored candidates; executed by one warp.
+__device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long r, int n, const double* s_min,
+                                               int bad_flag, int lane) {
+  // warp 0: order the candidates by (exact sim desc, index asc), certify, write the top-k
+  double sim[CAP / 32];
+  uint32_t idv[CAP / 32];
+#pragma unroll
+  for (int u = 0; u < CAP / 32; u++) {
+    const int c = u * 32 + lane;
+    sim[u] = -INFINITY;
+    idv[u] = 0xFFFFFFFFu;
+    if (c < n) {
+      const double s = s_min[c];
+      idv[u] = p.cand_id[(size_t)r * CAP + c];
+      // admitted iff not NaN (no comparable row), >= threshold and > Double.MIN_VALUE
+      if (s != JAVA_MAX_DOUBLE && s >= p.threshold && s > 4.9e-324) sim[u] = s;
+    }
+  }
+  // bitonic sort on (sim desc, id asc) with 96-bit keys
+#pragma unroll
+  for (int k = 2; k <= CAP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int js = j >> 5;
+#pragma unroll
+        for (int s = 0; s < CAP / 32; s++) {
+          if ((s & js) == 0) {
+            const bool desc = (((s * 32) & k) == 0);
+            const bool a_first = sim[s] > sim[s | js] || (sim[s] == sim[s | js] && idv[s] <= idv[s | js]);
+            if (a_first != desc) {
+              double ts = sim[s]; sim[s] = sim[s | js]; sim[s | js] = ts;
+              uint32_t ti = idv[s]; idv[s] = idv[s | js]; idv[s | js] = ti;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < CAP / 32; s++) {
+          const double os = __shfl_xor_sync(0xffffffffu, sim[s], j);
+          const uint32_t oi = __shfl_xor_sync(0xffffffffu, idv[s], j);
+          const int e = s * 32 + lane;
+          const bool lower = (lane & j) == 0;
+          const bool desc = ((e & k) == 0);
+          const bool mine_first = sim[s] > os || (sim[s] == os && idv[s] <= oi);
+          const bool keep_first = (lower == desc);
+          if (mine_first != keep_first) {
+            sim[s] = os;
+            idv[s] = oi;
+          }
+        }
+      }
+    }
+  }
+  int admitted = 0;
+  double kth = -INFINITY;  // exact value of the k-th result (or -inf if fewer than k)
+#pragma unroll
+  for (int u = 0; u < CAP / 32; u++) {
+    const int e = u * 32 + lane;
+    const bool ok = sim[u] > -INFINITY && e < p.k;
+    if (e < p.k) {
+      p.out_idx[(size_t)r * p.k + e] = ok ? (long long)idv[u] : -1LL;
+      p.out_sim[(size_t)r * p.k + e] = ok ? sim[u] : 0.0;
+    }
+    admitted += __popc(__ballot_sync(0xffffffffu, ok));
+    const double v = __shfl_sync(0xffffffffu, sim[u], (p.k - 1) & 31);
+    if (u == ((p.k - 1) >> 5)) kth = v;
+  }
+  if (lane == 0) {
+    p.out_cnt[r] = admitted;
+    // every candidate that is not in the merged list has tensor value <= bound, hence exact value
+    // <= bound * (1 + eps) (+ eps absolute for values near zero).  The top-k is certain iff the
+    // k-th exact value clears that.
+    const float b = p.cand_bound[r];
+    int flag = bad_flag;
+    if (b > -INFINITY) {
+      const double ub = (double)(b * p.inv_scale2) * (1.0 + (double)p.eps_rel) + (double)p.eps_rel * 1e-3;
+      if (!(kth > ub)) flag = 1;
+    }
+    p.row_flag[r] = flag;
+    if (flag) atomicAdd(p.flag_count, 1);
+  }
+}
+
 #define RESCORE_SEG 4096  /* counters of one A row segment staged in shared memory */
 
 __global__ void __launch_bounds__(256) k_rescore(const RescoreParams p) {
@@ -725,86 +809,132 @@ __global__ void __launch_bounds__(256) k_rescore(const RescoreParams p) {
     }
     __syncthreads();
   }
-  // warp 0: order the candidates by (exact sim desc, index asc), certify, write the top-k
-  if (warp != 0) return;
-  double sim[CAP / 32];
-  uint32_t idv[CAP / 32];
-#pragma unroll
-  for (int u = 0; u < CAP / 32; u++) {
-    const int c = u * 32 + lane;
-    sim[u] = -INFINITY;
-    idv[u] = 0xFFFFFFFFu;
-    if (c < n) {
-      const double s = s_min[c];
-      idv[u] = p.cand_id[(size_t)r * CAP + c];
-      // admitted iff not NaN (no comparable row), >= threshold and > Double.MIN_VALUE
-      if (s != JAVA_MAX_DOUBLE && s >= p.threshold && s > 4.9e-324) sim[u] = s;
-    }
+  if (warp == 0) rescore_finish(p, r, n, s_min, s_bad, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b, narrow form.  k_rowstats makes an int32 copy of the counters and, per sketch row, max|c| and
+// the exact sum of squares; k_rescore32 then needs only the cross products, reads half the bytes and
+// multiplies with one IMAD.WIDE per element.  Exactness precondition per (row, candidate, depth):
+// max|a| * max|b| * W < 2^52 (and the same for the squares) -- checked from the row maxima.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rowstats(const long long* __restrict__ counters, int W,
+                                                  int* __restrict__ narrow, unsigned long long* __restrict__ row_max,
+                                                  long long* __restrict__ row_ss,
+                                                  unsigned long long* __restrict__ global_max) {
+  __shared__ unsigned long long s_mx[8];
+  __shared__ long long s_ss[8];
+  const size_t rowi = blockIdx.x;
+  const long long* row = counters + rowi * W;
+  int* out = narrow + rowi * W;
+  unsigned long long mx = 0;
+  long long ss = 0;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    const long long x = row[j];
+    const unsigned long long ax = x < 0 ? (unsigned long long)(-x) : (unsigned long long)x;
+    mx = ax > mx ? ax : mx;
+    const long long c = x > 2147483647LL ? 2147483647LL : (x < -2147483647LL ? -2147483647LL : x);
+    out[j] = (int)c;
+    ss += c * c;  // exact whenever the row passes the magnitude test below
   }
-  // bitonic sort on (sim desc, id asc) with 96-bit keys
-#pragma unroll
-  for (int k = 2; k <= CAP; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {
-        const int js = j >> 5;
-#pragma unroll
-        for (int s = 0; s < CAP / 32; s++) {
-          if ((s & js) == 0) {
-            const bool desc = (((s * 32) & k) == 0);
-            const bool a_first = sim[s] > sim[s | js] || (sim[s] == sim[s | js] && idv[s] <= idv[s | js]);
-            if (a_first != desc) {
-              double ts = sim[s]; sim[s] = sim[s | js]; sim[s | js] = ts;
-              uint32_t ti = idv[s]; idv[s] = idv[s | js]; idv[s | js] = ti;
-            }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long om = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = om > mx ? om : mx;
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_mx[threadIdx.x >> 5] = mx;
+    s_ss[threadIdx.x >> 5] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) {
+      mx = s_mx[w] > mx ? s_mx[w] : mx;
+      ss += s_ss[w];
+    }
+    row_max[rowi] = mx;
+    row_ss[rowi] = ss;
+    atomicMax(global_max, mx);
+  }
+}
+
+struct Narrow {
+  const int* a;                       // [a_count][d][W]
+  const int* b;                       // [blocks][b_count][d][W]
+  const unsigned long long* a_max;    // [a_count][d]
+  const unsigned long long* b_max;
+  const long long* a_ss;
+  const long long* b_ss;
+};
+
+#define RESCORE32_SEG 8192
+
+__global__ void __launch_bounds__(256) k_rescore32(const RescoreParams p, const Narrow nw) {
+  __shared__ __align__(16) int s_a[RESCORE32_SEG];
+  __shared__ double s_min[CAP];
+  __shared__ long long s_ab[CAP];
+  __shared__ int s_bad;
+  const long long r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.cand_cnt[r];
+  for (int c = tid; c < CAP; c += blockDim.x) s_min[c] = JAVA_MAX_DOUBLE;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  const int* arow = nw.a + (size_t)r * p.d * p.W;
+  const bool vec = (p.W & 3) == 0;
+  for (int i = 0; i < p.d && n > 0; i++) {
+    for (int c = tid; c < CAP; c += blockDim.x) s_ab[c] = 0;
+    for (int j0 = 0; j0 < p.W; j0 += RESCORE32_SEG) {
+      const int seg = min(RESCORE32_SEG, p.W - j0);
+      __syncthreads();
+      for (int j = tid; j < seg; j += blockDim.x) s_a[j] = arow[(size_t)i * p.W + j0 + j];
+      __syncthreads();
+      for (int c = warp; c < n; c += 8) {
+        const uint32_t id = p.cand_id[(size_t)r * CAP + c];
+        long long g, l;
+        b_locate(p, id, g, l);
+        const int* brow = nw.b + (((size_t)g * p.b_count + l) * p.d + i) * p.W + j0;
+        long long ab = 0;
+        if (vec) {
+          const int4* b4 = reinterpret_cast<const int4*>(brow);
+          const int4* a4 = reinterpret_cast<const int4*>(s_a);
+#pragma unroll 4
+          for (int j = lane; j < (seg >> 2); j += 32) {
+            const int4 y = __ldg(b4 + j);
+            const int4 x = a4[j];
+            ab += (long long)x.x * y.x;
+            ab += (long long)x.y * y.y;
+            ab += (long long)x.z * y.z;
+            ab += (long long)x.w * y.w;
           }
+        } else {
+          for (int j = lane; j < seg; j += 32) ab += (long long)s_a[j] * __ldg(brow + j);
         }
-      } else {
-#pragma unroll
-        for (int s = 0; s < CAP / 32; s++) {
-          const double os = __shfl_xor_sync(0xffffffffu, sim[s], j);
-          const uint32_t oi = __shfl_xor_sync(0xffffffffu, idv[s], j);
-          const int e = s * 32 + lane;
-          const bool lower = (lane & j) == 0;
-          const bool desc = ((e & k) == 0);
-          const bool mine_first = sim[s] > os || (sim[s] == os && idv[s] <= oi);
-          const bool keep_first = (lower == desc);
-          if (mine_first != keep_first) {
-            sim[s] = os;
-            idv[s] = oi;
-          }
-        }
+        for (int o = 16; o > 0; o >>= 1) ab += __shfl_xor_sync(0xffffffffu, ab, o);
+        if (lane == 0) s_ab[c] += ab;
       }
     }
-  }
-  int admitted = 0;
-  double kth = -INFINITY;  // exact value of the k-th result (or -inf if fewer than k)
-#pragma unroll
-  for (int u = 0; u < CAP / 32; u++) {
-    const int e = u * 32 + lane;
-    const bool ok = sim[u] > -INFINITY && e < p.k;
-    if (e < p.k) {
-      p.out_idx[(size_t)r * p.k + e] = ok ? (long long)idv[u] : -1LL;
-      p.out_sim[(size_t)r * p.k + e] = ok ? sim[u] : 0.0;
+    __syncthreads();
+    const double amax = (double)nw.a_max[(size_t)r * p.d + i];
+    const long long AA = nw.a_ss[(size_t)r * p.d + i];
+    const double sqa = sqrt((double)AA);
+    for (int c = tid; c < n; c += blockDim.x) {
+      const uint32_t id = p.cand_id[(size_t)r * CAP + c];
+      long long g, l;
+      b_locate(p, id, g, l);
+      const size_t bi = ((size_t)g * p.b_count + l) * p.d + i;
+      const double bmax = (double)nw.b_max[bi];
+      const double big = fmax(amax, bmax);
+      if (big * big * (double)p.W >= TWO53 * 0.5) s_bad = 1;   // sums might round in FP64: not this path
+      const double den = __dmul_rn(sqa, sqrt((double)nw.b_ss[bi]));
+      if (den != 0.0) {
+        const double cs = __ddiv_rn((double)s_ab[c], den);
+        s_min[c] = cs < s_min[c] ? cs : s_min[c];
+      }
     }
-    admitted += __popc(__ballot_sync(0xffffffffu, ok));
-    const double v = __shfl_sync(0xffffffffu, sim[u], (p.k - 1) & 31);
-    if (u == ((p.k - 1) >> 5)) kth = v;
+    __syncthreads();
   }
-  if (lane == 0) {
-    p.out_cnt[r] = admitted;
-    // every candidate that is not in the merged list has tensor value <= bound, hence exact value
-    // <= bound * (1 + eps) (+ eps absolute for values near zero).  The top-k is certain iff the
-    // k-th exact value clears that.
-    const float b = p.cand_bound[r];
-    int flag = s_bad;
-    if (b > -INFINITY) {
-      const double ub = (double)(b * p.inv_scale2) * (1.0 + (double)p.eps_rel) + (double)p.eps_rel * 1e-3;
-      if (!(kth > ub)) flag = 1;
-    }
-    p.row_flag[r] = flag;
-    if (flag) atomicAdd(p.flag_count, 1);
-  }
+  if (warp == 0) rescore_finish(p, r, n, s_min, s_bad, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1275,9 +1405,47 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
       rp.out_cnt = a->out_cnt;
       rp.row_flag = (int32_t*)d_flag.p;
       rp.flag_count = (int32_t*)d_fcount.p;
-      k_rescore<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp);
+      // narrow (int32) copies + per-row statistics; the generic int64 kernel is kept for banks whose
+      // counters do not fit 31 bits
+      const bool same = a->a_counters == a->b_counters && a->b_blocks == 1 && a->a_count == a->b_count;
+      const size_t rows_b = (size_t)total_b * a->depth, rows_a = (size_t)a->a_count * a->depth;
+      DevBuf d_nb, d_bmax, d_bss, d_na, d_amax, d_ass, d_gmax;
+      MB_CHECK(d_nb.alloc(ws, rows_b * a->width * sizeof(int)));
+      MB_CHECK(d_bmax.alloc(ws, rows_b * 8));
+      MB_CHECK(d_bss.alloc(ws, rows_b * 8));
+      MB_CHECK(d_gmax.alloc(ws, 8));
+      MB_CUDA(ctx, cudaMemsetAsync(d_gmax.p, 0, 8, ctx->stream));
+      k_rowstats<<<(unsigned)rows_b, 256, 0, ctx->stream>>>((const long long*)a->b_counters, a->width, (int*)d_nb.p,
+                                                             (unsigned long long*)d_bmax.p, (long long*)d_bss.p,
+                                                             (unsigned long long*)d_gmax.p);
       ctx->launches++;
-      MB_CUDA(ctx, cudaGetLastError());
+      Narrow nw;
+      nw.b = (const int*)d_nb.p;
+      nw.b_max = (const unsigned long long*)d_bmax.p;
+      nw.b_ss = (const long long*)d_bss.p;
+      if (same) {
+        nw.a = nw.b;
+        nw.a_max = nw.b_max;
+        nw.a_ss = nw.b_ss;
+      } else {
+        MB_CHECK(d_na.alloc(ws, rows_a * a->width * sizeof(int)));
+        MB_CHECK(d_amax.alloc(ws, rows_a * 8));
+        MB_CHECK(d_ass.alloc(ws, rows_a * 8));
+        k_rowstats<<<(unsigned)rows_a, 256, 0, ctx->stream>>>((const long long*)a->a_counters, a->width, (int*)d_na.p,
+                                                               (unsigned long long*)d_amax.p, (long long*)d_ass.p,
+                                                               (unsigned long long*)d_gmax.p);
+        ctx->launches++;
+        nw.a = (const int*)d_na.p;
+        nw.a_max = (const unsigned long long*)d_amax.p;
+        nw.a_ss = (const long long*)d_ass.p;
+      }
+      unsigned long long gmax = 0;
+      MB_CUDA(ctx, cudaMemcpyAsync(&gmax, d_gmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (gmax < (1ull << 31) && getenv("MB200_RESCORE64") == nullptr)
+        k_rescore32<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp, nw);
+      else
+        k_rescore<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp);
       int32_t nflag = 0;
       MB_CUDA(ctx, cudaMemcpyAsync(&nflag, d_fcount.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -253,3 +253,41 @@ def test_cosine_cm_user_similarity(mb, ctx):
     near, sims = cm.mostSimilarUserIDs(u, 5)
     assert len(near) == 5 and u not in near.tolist() and (np.diff(sims) <= 0).all()
     cm.close()
+
+
+def test_full_size_properties_config2(mb, ctx):
+    """Size-independent properties at BASELINE config-2 scale (2^28 device-generated Zipf events,
+    d=4 x W=2^20): every sketch row holds exactly the total mass, the update is linear (two halves
+    into one sketch == sum of two sketches), and a prefix agrees bit for bit with the oracle."""
+    import torch
+    from mahout_b200 import synth
+    n, d, w = 1 << 28, 4, 1 << 20
+    cdf = synth.zipf_cdf(10_000_000, 1.1)
+    cd = torch.from_numpy(cdf).cuda()
+    _, item, pref = synth.events_device(ctx, 20240002, 0, n, 1_000_000, cd, None, want_user=False)
+    whole = mb.SketchBank(1, w, d, 42, 1, ctx)
+    whole.update(None, item, pref)
+    whole.check()
+    c = whole.counters_tensor()                                   # int64 quanta [1, d, w]
+    total = int((pref.double() * 2).sum().item())
+    assert c.sum(dim=2).flatten().tolist() == [total] * d         # mass conservation per row
+    h1 = mb.SketchBank(1, w, d, 42, 1, ctx)
+    h2 = mb.SketchBank(1, w, d, 42, 1, ctx)
+    h1.update(None, item[: n // 2], pref[: n // 2])
+    h2.update(None, item[n // 2:], pref[n // 2:])
+    assert torch.equal(h1.counters_tensor() + h2.counters_tensor(), c)   # linearity
+    # point queries never under-estimate (count-min property) on the hottest keys
+    keys = torch.arange(1, 1001, device="cuda")
+    est = torch.from_numpy(whole.query(None, keys.cpu().numpy()))
+    true = torch.zeros(1001, dtype=torch.float64, device="cuda").index_add_(
+        0, item.clamp(max=1000), torch.where(item <= 1000, pref.double(), torch.zeros_like(pref).double()))[1:]
+    assert (est >= true.cpu() - 1e-9).all()
+    m = 1 << 22
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((1, d, w))
+    orc.bank_update(ref, d, w, a, b, None, item[:m].cpu().numpy(), pref[:m].cpu().numpy(), nthreads=orc.max_threads())
+    pre = mb.SketchBank(1, w, d, 42, 1, ctx)
+    pre.update(None, item[:m], pref[:m])
+    assert pre.read().tobytes() == ref.tobytes()
+    for bk in (whole, h1, h2, pre):
+        bk.close()
