@@ -1327,8 +1327,8 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
   p.policy_b = L2_EVICT_NORMAL;
   if (const char* ev = getenv("MB200_COS_HINTS")) {
     const int h = atoi(ev);
-    if (h == 1) p.policy_a = L2_EVICT_LAST;
-    if (h >= 1) p.policy_b = L2_EVICT_FIRST;
+    if (h == 1 || h == 3) p.policy_a = L2_EVICT_LAST;
+    if (h == 1 || h == 2) p.policy_b = L2_EVICT_FIRST;
   }
   const int grid = std::min(num_items, P);
   {
