@@ -35,6 +35,8 @@ SKETCH_SEED = 42
 DEPTH, WIDTH = 4, 1 << 20
 ITEMS, USERS, ZIPF_S = 10_000_000, 1_000_000, 1.1
 ALGO_BYTES_PER_EVENT = 20 + DEPTH * 16   # 20 B event + d x (8 B read + 8 B write)
+C3_USERS, C3_ITEMS, C3_EVENTS, C3_WIDTH, C3_DEPTH, C3_K = 138_493, 26_744, 20_000_000, 4096, 4, 50
+C3_SEED = 20240003
 METRIC = "sketch_updates_per_sec"
 UNIT = "events/s"
 
@@ -164,7 +166,34 @@ def run_reference(args):
         "note": "reference Java cannot run (no JVM in image): oracle/ C port of HashFunction.hash + "
                 "DoubleCountMinSketch.update, OpenMP over event slices with private sketches",
     }
+    if not args.no_cosine:
+        line["cosine"] = _reference_cosine(threads)
     print(json.dumps(line), flush=True)
+
+
+def _reference_cosine(threads: int):
+    """configs[2] on the host cores: oracle sketch build (all 2e7 events) + DoubleCountMinSketch.cosine
+    + top-k for a bounded sample of rows, all threads."""
+    import oracle as orc
+    from mahout_b200 import synth
+    cdf = synth.zipf_cdf(C3_ITEMS, ZIPF_S)
+    perm = synth.rank_permutation(C3_ITEMS, 3) - 1
+    user, item, pref = synth.events_numpy(C3_SEED, 0, C3_EVENTS, C3_USERS, cdf, perm)
+    a, b = orc.hash_params(SKETCH_SEED, C3_DEPTH)
+    bank = np.zeros((C3_ITEMS, C3_DEPTH, C3_WIDTH))
+    t0 = time.perf_counter()
+    orc.bank_update(bank, C3_DEPTH, C3_WIDTH, a, b, item, user, pref, nthreads=1)
+    build_s = time.perf_counter() - t0
+    rows = threads * 16
+    _, _, _, cpu_s = _cpu_cosine_rows(bank, list(range(rows)), C3_K, threads)
+    value = rows * C3_ITEMS / cpu_s
+    return {"metric": "item_pair_cosine_sims_per_sec", "value": value, "unit": "pairs/s",
+            "config": {"workload": "configs[2]: MovieLens-20M-shaped synthetic, sketch d=4 x W=4096, cosine top-50",
+                       "items": C3_ITEMS, "depth": C3_DEPTH, "width": C3_WIDTH, "k": C3_K},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": f"{rows} rows x all {C3_ITEMS} columns, {cpu_s:.1f} s"},
+            "sketch_build": {"events_per_s": C3_EVENTS / build_s, "events": C3_EVENTS, "s": build_s, "cores": 1},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 def _config(n_gpus: int, events_per_step: int):
@@ -271,17 +300,30 @@ def run_ours(args):
 
     for _ in range(2):
         e2e_step()
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_reps = []
+    for _ in range(3):                      # the host side of a shared box is noisy: best of 3 repetitions
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e_reps.append(e2e_s)
+    e2e_s = min(e2e_reps)
+    # what the link itself delivers for the same bytes (explains the e2e number; not part of it)
+    dkey = torch.empty(e2e_n, dtype=torch.int64, device=dev)
+    dkey.copy_(hk, non_blocking=True)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    dkey.copy_(hk, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    h2d_gbps = 8 * e2e_n / (time.perf_counter() - t0) / 1e9
+    del dkey
     e2e_value = world * e2e_n * e2e_steps / e2e_s
 
     # ---- parity + cpu_baseline on rank 0 ---------------------------------------------------------
@@ -326,7 +368,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * e2e_n,
                     "d2h_bytes_per_step": 8 * DEPTH * WIDTH,
                     "sample": f"{e2e_n} events/step from pinned host memory through mb200_bank_update(MEM_HOST) "
-                              "+ mb200_bank_read of the whole sketch"},
+                              "+ mb200_bank_read of the whole sketch; best of 3 repetitions of "
+                              f"{e2e_steps} steps",
+                    "repetitions_s": e2e_reps, "pinned_h2d_GBps": h2d_gbps,
+                    "bound": "PCIe: 12 B/event over the host link"},
             "roofline": {"bound": "hbm", "kernel": "k_update_single", "achieved": achieved, "peak": peaks["hbm"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm"],
                          # ncu --set full (profiles/r1_k_update_single_ncu.txt): 3.056 GB of DRAM traffic per
@@ -348,8 +393,25 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------
 # cosine stage (BASELINE.json configs[2]): MovieLens-20M-shaped sketch build + all-pairs cosine top-50
 # ------------------------------------------------------------------------------------------------
-C3_USERS, C3_ITEMS, C3_EVENTS, C3_WIDTH, C3_DEPTH, C3_K = 138_493, 26_744, 20_000_000, 4096, 4, 50
-C3_SEED = 20240003
+
+
+def _cpu_cosine_rows(bank_host, rows, k, threads):
+    """oracle top-k of the given global rows, one oracle call per row spread over `threads` host threads
+    (the oracle's own OpenMP loop runs over rows, so single-row calls are dealt out here)."""
+    import oracle as orc
+    from concurrent.futures import ThreadPoolExecutor
+    orc.lib()
+
+    def one(r):
+        i1, s1, c1 = orc.bank_cosine_topk(bank_host, k, r0=r, r1=r + 1, nthreads=1)
+        return i1[0], s1[0], c1[0]
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(one, rows))
+    dt = time.perf_counter() - t0
+    return (np.array([r[0] for r in res]), np.array([r[1] for r in res]), np.array([r[2] for r in res]), dt)
+
 
 
 def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup):
@@ -440,6 +502,48 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
     fallback = last_fallback_rows(ctx)
     ctx.set_profiling(False)
 
+    # ---- end to end: this rank's events start in pinned HOST memory, its rows' top-k ends in host memory;
+    # bank allocation + zero fill, H2D staging, K1, K2, (all-gathers), K3, K5 and the D2H are all inside
+    h_row, h_user, h_pref = (t.cpu().pin_memory() for t in (lrow, luser, lpref))
+
+    def e2e_step(precision):
+        eb = mb.SketchBank(plan.rows_per_shard, C3_WIDTH, C3_DEPTH, SKETCH_SEED, 1, ctx)
+        try:
+            eb.update(h_row.numpy(), h_user.numpy(), h_pref.numpy())
+            if world == 1:
+                return eb.cosine_topk(C3_K, None, True, "f16", precision)          # numpy (host) outputs
+            N.check(N.lib().mb200_bank_normalize(eb.handle, N.DTYPE_F16, C.c_void_p(a_rows.data_ptr()),
+                                                 C.c_void_p(a_valid.data_ptr())), ctx.handle)
+            dist.all_gather_into_tensor(b_rows.view(-1, plan.rows_per_shard, ld), a_rows)
+            dist.all_gather_into_tensor(b_valid.view(-1, vw), a_valid)
+            ec = eb.counters_tensor()
+            if precision == "rescored":
+                dist.all_gather_into_tensor(b_cnt.view(-1, C3_DEPTH, C3_WIDTH), ec)
+            r = cosine_topk_blocks(ctx, a_rows, a_valid, b_rows, b_valid, C3_DEPTH, C3_WIDTH, C3_K,
+                                   a_id=(world, rank), b_id=b_id, dtype="f16", precision=precision,
+                                   a_counters=ec if precision == "rescored" else None,
+                                   b_counters=b_cnt if precision == "rescored" else None)
+            return tuple(t.cpu() for t in r)
+        finally:
+            eb.close()
+
+    e2e = {}
+    for precision in ("rescored", "tensor"):
+        e2e_step(precision)
+        best = None
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            e2e_step(precision)
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            best = dt if best is None else min(best, dt)
+        e2e[precision] = best
+
     if rank == 0:
         import oracle as orc
         pairs = float(C3_ITEMS) ** 2
@@ -454,16 +558,9 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                 bank_host[g::world] = full[g] * 0.5
         else:
             bank_host = bank.read()
-        rows_chk = 32 if world == 1 else 8
         threads = _host_threads()
-        t0 = time.perf_counter()
-        oi, osim, oc = [], [], []
-        for l in range(rows_chk):
-            r = l * world
-            i1, s1, c1 = orc.bank_cosine_topk(bank_host, C3_K, r0=r, r1=r + 1, nthreads=threads)
-            oi.append(i1[0]); osim.append(s1[0]); oc.append(c1[0])
-        cpu_s = time.perf_counter() - t0
-        oi, osim, oc = np.array(oi), np.array(osim), np.array(oc)
+        rows_chk = int(min(plan.rows_per_shard, threads * (24 if world == 1 else 4)))   # ~0.5 s per row and thread
+        oi, osim, oc, cpu_s = _cpu_cosine_rows(bank_host, [l * world for l in range(rows_chk)], C3_K, threads)
         gi, gs, gc = ridx[:rows_chk].cpu().numpy(), rs[:rows_chk].cpu().numpy(), rcnt[:rows_chk].cpu().numpy()
         ti, ts, tc = idx[:rows_chk].cpu().numpy(), s[:rows_chk].cpu().numpy(), cnt[:rows_chk].cpu().numpy()
         exact_equal = bool((gi == oi).all() and (gc == oc).all() and gs.tobytes() == osim.tobytes())
@@ -495,6 +592,11 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                          # ncu --set full of this kernel on this workload at 1 GPU
                          # (profiles/r1_k_cosine_final_ncu.txt): dram read 69.06 GB + write 0.79 GB
                          "traffic": 69.85e9 if world == 1 else None},
+            "e2e": {"value": pairs / e2e["rescored"], "unit": "pairs/s", "ms_per_job": e2e["rescored"] * 1e3,
+                    "h2d_bytes_per_step": 20 * n_local, "d2h_bytes_per_step": plan.rows_per_shard * (C3_K * 16 + 4),
+                    "tensor_precision": {"value": pairs / e2e["tensor"], "ms_per_job": e2e["tensor"] * 1e3},
+                    "sample": "whole job per rank: SketchBank(...) + update(host events, pinned) + cosine_topk -> host "
+                              "arrays (API default precision = rescored, bit-equal to the reference); best of 3"},
             "rescored": {"ms_per_step": rescored_ms, "K5_merge_rescore_ms": r5_ms, "fallback_rows": int(fallback),
                          "pairs_per_s": pairs / (rescored_ms * 1e-3)},
             "sketch_build": {"events_per_s": n_local / (upd_ms * 1e-3) if upd_ms > 0 else None,

@@ -41,9 +41,9 @@ static constexpr int COS_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 
 static constexpr float F16_SCALE = 4096.0f;  // rows are stored as x/||x|| * 2^12 in FP16
 
 struct CosParams {
-  const int2* items;        // work items (m block, column chunk)
+  const int4* items;        // work items (m block, first tile, end tile, -)
   int32_t num_items;
-  int32_t chunk_tiles, total_tiles, tiles_per_block;
+  int32_t total_tiles, tiles_per_block;
   int32_t depth, kblocks, stages;
   int64_t a_count;
   const uint32_t* a_valid;
@@ -283,9 +283,8 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
-        const int2 it = p.items[w];
-        const int t0 = it.y * p.chunk_tiles;
-        const int t1 = min(p.total_tiles, t0 + p.chunk_tiles);
+        const int4 it = p.items[w];
+        const int t0 = it.y, t1 = it.z;
         for (int t = t0; t < t1; t++) {
           const int g = t / p.tiles_per_block;
           const int l0 = (t - g * p.tiles_per_block) * BN;
@@ -312,9 +311,8 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     uint32_t phase = 0;
     uint32_t q = 0;  // accumulation steps issued by this CTA
     for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
-      const int2 it = p.items[w];
-      const int t0 = it.y * p.chunk_tiles;
-      const int t1 = min(p.total_tiles, t0 + p.chunk_tiles);
+      const int4 it = p.items[w];
+      const int t0 = it.y, t1 = it.z;
       for (int t = t0; t < t1; t++) {
         for (int dep = 0; dep < p.depth; dep++, q++) {
           const uint32_t as = q % ACC_STAGES;
@@ -356,9 +354,8 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     uint32_t q = 0;
     for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
-      const int2 it = p.items[w];
-      const int t0 = it.y * p.chunk_tiles;
-      const int t1 = min(p.total_tiles, t0 + p.chunk_tiles);
+      const int4 it = p.items[w];
+      const int t0 = it.y, t1 = it.z;
       const long long grow = (long long)it.x * BM + row;
       const bool row_ok = grow < p.a_count;
       const uint32_t my_id = (row_ok && p.exclude_self) ? (uint32_t)grow * p.a_id_mul + p.a_id_off : 0xFFFFFFFFu;
@@ -396,6 +393,64 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           fence_after_sync();
           const uint32_t acc_addr = tmem_base + lane_addr + as * BN + half * HALF;
           const uint32_t min_addr = tmem_base + lane_addr + ACC_STAGES * BN + half * HALF;
+          // Candidate selection over one 32-column chunk of final values (executed per thread = per row).
+          auto select_chunk = [&](int c, uint32_t (&v)[32]) {
+            if (p.dense_out != nullptr && row_ok) {
+              float* dst = p.dense_out + (size_t)grow * p.dense_ld + (size_t)t * BN + half * HALF + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j++) dst[j] = __uint_as_float(v[j]) * p.inv_scale2;
+            }
+            const uint32_t id0 = (uint32_t)(l0 + c * 32) * p.b_id_mul + (uint32_t)g * p.b_id_add;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const float x = __uint_as_float(v[j]);
+              if (x > thr) {  // NaN never passes
+                const uint32_t id = id0 + (uint32_t)j * p.b_id_mul;
+                if (id != my_id) {
+                  __stcg(list + cnt, make_uint2(v[j], id));
+                  cnt++;
+                }
+              }
+            }
+            // keep 32 free slots for the next chunk; raise the threshold early once so that the
+            // other lists of the row can use it.  Threshold raises are warp-cooperative.
+            unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - 32 || (!published && cnt >= 2 * p.ksel));
+            while (need) {
+              const int src = __ffs(need) - 1;
+              need &= need - 1;
+              __syncwarp();
+              uint2* l2 = (uint2*)__shfl_sync(0xffffffffu, (unsigned long long)list, src);
+              const int n2 = __shfl_sync(0xffffffffu, cnt, src);
+              int n3 = 0;
+              const uint32_t T = warp_select_list(l2, n2, p.ksel, lane, &n3);
+              uint32_t kth = 0xFFFFFFFFu;
+              if (n3 > p.ksel + 32) {  // a large group of equal values: cut it by index (exact sort)
+                __syncwarp();
+                kth = warp_compact_list(l2, n3, p.ksel, lane);
+              }
+              if (lane == src) {
+                published = true;
+                if (kth != 0xFFFFFFFFu) {
+                  cnt = min(n3, p.ksel);
+                  const float kv = __uint_as_float(kth);
+                  bound = fmaxf(bound, kv);
+                  // ties at the k-th value may still win on the index unless the scan order is
+                  // index-monotone: admit them by stepping the threshold one ulp down
+                  const uint32_t ko = f2ord(kth);
+                  const uint32_t to = p.nonstrict && ko > 0 ? ko - 1 : ko;
+                  thr = fmaxf(thr, __uint_as_float(ord2f(to)));
+                  // other lists of the row scan other index ranges: they must keep admitting ties
+                  atomicMax(my_row_thr, ko > 0 ? ko - 1 : 0u);
+                } else if (T != 0u) {
+                  cnt = n3;
+                  bound = fmaxf(bound, __uint_as_float(ord2f(T)));
+                  thr = fmaxf(thr, __uint_as_float(ord2f(T - 1)));  // x > thr  <=>  x >= T
+                  atomicMax(my_row_thr, T - 1);
+                }
+              }
+              __syncwarp();
+            }
+          };
 #pragma unroll
           for (int c = 0; c < CHUNKS; c++) {
             uint32_t v[32];
@@ -411,70 +466,26 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
               if (HAS_MIN && dep > 0) x = fminf(__uint_as_float(m[j]), x);
               v[j] = __float_as_uint(x);
             }
-            if (!last) {
-              if (HAS_MIN) tmem_st32(min_addr + c * 32, v);
-            } else {
-              if (p.dense_out != nullptr && row_ok) {
-                float* dst = p.dense_out + (size_t)grow * p.dense_ld + (size_t)t * BN + half * HALF + c * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j++) dst[j] = __uint_as_float(v[j]) * p.inv_scale2;
-              }
-              const uint32_t id0 = (uint32_t)(l0 + c * 32) * p.b_id_mul + (uint32_t)g * p.b_id_add;
-#pragma unroll
-              for (int j = 0; j < 32; j++) {
-                const float x = __uint_as_float(v[j]);
-                if (x > thr) {  // NaN never passes
-                  const uint32_t id = id0 + (uint32_t)j * p.b_id_mul;
-                  if (id != my_id) {
-                    __stcg(list + cnt, make_uint2(v[j], id));
-                    cnt++;
-                  }
-                }
-              }
-              // keep 32 free slots for the next chunk; raise the threshold early once so that the
-              // other lists of the row can use it.  Threshold raises are warp-cooperative.
-              unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - 32 || (!published && cnt >= 2 * p.ksel));
-              while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                __syncwarp();
-                uint2* l2 = (uint2*)__shfl_sync(0xffffffffu, (unsigned long long)list, src);
-                const int n2 = __shfl_sync(0xffffffffu, cnt, src);
-                int n3 = 0;
-                const uint32_t T = warp_select_list(l2, n2, p.ksel, lane, &n3);
-                uint32_t kth = 0xFFFFFFFFu;
-                if (n3 > p.ksel + 32) {  // a large group of equal values: cut it by index (exact sort)
-                  __syncwarp();
-                  kth = warp_compact_list(l2, n3, p.ksel, lane);
-                }
-                if (lane == src) {
-                  published = true;
-                  if (kth != 0xFFFFFFFFu) {
-                    cnt = min(n3, p.ksel);
-                    const float kv = __uint_as_float(kth);
-                    bound = fmaxf(bound, kv);
-                    // ties at the k-th value may still win on the index unless the scan order is
-                    // index-monotone: admit them by stepping the threshold one ulp down
-                    const uint32_t ko = f2ord(kth);
-                    const uint32_t to = p.nonstrict && ko > 0 ? ko - 1 : ko;
-                    thr = fmaxf(thr, __uint_as_float(ord2f(to)));
-                    // other lists of the row scan other index ranges: they must keep admitting ties
-                    atomicMax(my_row_thr, ko > 0 ? ko - 1 : 0u);
-                  } else if (T != 0u) {
-                    cnt = n3;
-                    bound = fmaxf(bound, __uint_as_float(ord2f(T)));
-                    thr = fmaxf(thr, __uint_as_float(ord2f(T - 1)));  // x > thr  <=>  x >= T
-                    atomicMax(my_row_thr, T - 1);
-                  }
-                }
-                __syncwarp();
-              }
-            }
+            // With a min buffer the final values are parked there too, so that the accumulator goes
+            // back to the MMA warp before the (long, data-dependent) selection starts.
+            if (HAS_MIN) tmem_st32(min_addr + c * 32, v);
+            else select_chunk(c, v);
           }
-          if (HAS_MIN && !last) tmem_wait_st();
+          if (HAS_MIN) tmem_wait_st();
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+          if (HAS_MIN && last) {
+            // selection from the min buffer; this thread is its only reader and writer, and it will
+            // not touch it again before depth 0 of the next tile
+#pragma unroll
+            for (int c = 0; c < CHUNKS; c++) {
+              uint32_t v[32];
+              tmem_ld32(min_addr + c * 32, v);
+              tmem_wait_ld();
+              select_chunk(c, v);
+            }
+          }
         }
       }
       // the list stays unsorted (<= CAP entries); K5 merges and orders
@@ -499,8 +510,9 @@ struct MergeParams {
   const uint2* lists;
   const int32_t* list_cnt;
   const float* list_bound;
-  const int32_t* slot_of;  // [num_m][S] -> item slot
-  int32_t S;
+  const uint32_t* row_thr;  // [rows padded] (see CosParams)
+  const int32_t* slot_ptr;  // [num_m + 1]: the work items (= list slots) of row block m are
+  const int32_t* slot_of;   // slot_of[slot_ptr[m] .. slot_ptr[m+1])
   int64_t a_count;
   int32_t ksel, k;
   double threshold;        // admitted iff sim >= threshold && sim > 0
@@ -517,45 +529,73 @@ struct MergeParams {
 };
 
 __global__ void __launch_bounds__(256) k_merge(const MergeParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // survivors of the row-threshold filter wait here until CAP of them are pending; one 512-key sort
+  // then folds them into the running best (so the cost does not grow with the number of lists)
+  __shared__ unsigned long long s_pend[8][CAP];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
   if (r >= p.a_count) return;
   const int m = (int)(r / BM), rr = (int)(r % BM);
   unsigned long long key[2 * CAP / 32];
 #pragma unroll
   for (int s = 0; s < 2 * CAP / 32; s++) key[s] = 0ull;
   float bound = -INFINITY;
-  for (int s = 0; s < p.S; s++) {
-    const int w = p.slot_of[(size_t)m * p.S + s];
+  // Every value <= row_thr is below the row's ksel-th best (K3 proved it when it published the
+  // threshold, and the publishing list's bound covers everything dropped for that reason).
+  uint32_t rthr = p.row_thr[r];
+  unsigned long long* pend = s_pend[wib];
+  int npend = 0;
+  auto fold = [&]() {
+#pragma unroll
+    for (int u = 0; u < CAP / 32; u++) {
+      const int e = u * 32 + lane;
+      key[CAP / 32 + u] = e < npend ? pend[e] : 0ull;
+    }
+    __syncwarp();
+    npend = 0;
+    warp_sort_desc<2 * CAP / 32>(key, lane);
+    // truncate to ksel; the best value dropped here bounds everything dropped later as well
+    unsigned long long kfirst = 0ull;  // first key beyond the cut (ksel < CAP always)
+#pragma unroll
+    for (int u = 0; u < CAP / 32; u++) {
+      const unsigned long long kv = __shfl_sync(0xffffffffu, key[u], p.ksel & 31);
+      if (u == (p.ksel >> 5)) kfirst = kv;
+    }
+    if (kfirst != 0ull) {
+      const uint32_t ko = (uint32_t)(kfirst >> 32);
+      bound = fmaxf(bound, __uint_as_float(ord2f(ko)));
+      // from now on anything strictly below the dropped value cannot make the cut
+      if (ko > 0u && ko - 1u > rthr) rthr = ko - 1u;
+    }
+#pragma unroll
+    for (int u = 0; u < 2 * CAP / 32; u++)
+      if (u * 32 + lane >= p.ksel) key[u] = 0ull;
+  };
+  for (int s = p.slot_ptr[m]; s < p.slot_ptr[m + 1]; s++) {
+    const int w = p.slot_of[s];
     for (int h = 0; h < 2; h++) {
       const size_t slot = ((size_t)w * 2 + h) * BM + rr;
       const int n = p.list_cnt[slot];
       bound = fmaxf(bound, p.list_bound[slot]);
       const uint2* list = p.lists + slot * CAP;
-#pragma unroll
-      for (int u = 0; u < CAP / 32; u++) {
-        const int e = u * 32 + lane;
-        unsigned long long kk = 0ull;
+      for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        bool keep = false;
+        uint2 x = make_uint2(0u, 0u);
         if (e < n) {
-          const uint2 x = __ldcg(list + e);
-          kk = make_key(x.x, x.y);
+          x = __ldcg(list + e);
+          keep = f2ord(x.x) > rthr;
         }
-        key[CAP / 32 + u] = kk;
-      }
-      warp_sort_desc<2 * CAP / 32>(key, lane);
-      // truncate to ksel; remember the best value dropped here
-#pragma unroll
-      for (int u = 0; u < CAP / 32; u++) {
-        const int e = u * 32 + lane;
-        const uint32_t v = ord2f((uint32_t)(key[u] >> 32));
-        const unsigned long long kfirst = __shfl_sync(0xffffffffu, key[u], p.ksel & 31);
-        if (u == (p.ksel >> 5) && p.ksel < CAP && kfirst != 0ull)
-          bound = fmaxf(bound, __uint_as_float(ord2f((uint32_t)(kfirst >> 32))));
-        (void)v;
-        if (e >= p.ksel) key[u] = 0ull;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (b == 0u) continue;
+        if (npend + 32 > CAP) fold();
+        if (keep) pend[npend + __popc(b & ((1u << lane) - 1u))] = make_key(x.x, x.y);
+        npend += __popc(b);
+        __syncwarp();
       }
     }
   }
+  fold();
   // key[0 .. CAP/32) now holds the row's best <= ksel candidates, sorted (value desc, index asc)
   if (p.rescored) {
     int n = 0;
@@ -1212,59 +1252,90 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
   const int num_m = (int)((a->a_count + BM - 1) / BM);
   if (a->dense_out && a->dense_ld < (int64_t)T * BN)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: dense_ld must be >= %lld", (long long)T * BN);
-  // Column chunks per row block.  Work items (row block, chunk) are dealt round-robin to one CTA per
-  // SM; a CTA's time is (waves) x (tiles per chunk + ~1.5 tiles of list warm-up per item), and the
-  // merge kernel's work grows with the number of chunks: take the cheapest, fewest chunks on ties.
+  // Work items (row block m, tile range [t0, t1)) are dealt round-robin to one CTA per SM; the CTAs of
+  // one wave start their sweeps together, so items with the same tile range share their B tiles in L2.
+  // A wave of items with c tiles costs about c + 3 tile times (3 = candidate-list warm-up), and
+  // the merge kernel's work grows with the number of lists per row.  Two shapes are costed:
+  //   uniform: every row block is cut into S column chunks;
+  //   tail   : floor(num_m / P) full waves of whole-row sweeps, the remaining R < P row blocks cut
+  //            into S chunks (fixes the quantisation of the last wave without paying the warm-up
+  //            everywhere).
   const int P = ctx->num_sms;
-  int S = 1;
+  const int smax = std::min(T, 32);
+  auto wave_cost = [&](long long nblocks, int s) {
+    const long long waves = (nblocks * s + P - 1) / P;
+    const int ct = (T + s - 1) / s;
+    return (double)waves * ((double)ct + 3.0) * (1.0 + 0.01 * s);
+  };
+  int S_main = 1, S_tail = 1, main_blocks = 0;
   {
     double best = 1e300;
-    const int smax = std::min(T, 32);
     for (int s = 1; s <= smax; s++) {
-      const long long items = (long long)num_m * s;
-      const long long waves = (items + P - 1) / P;
-      const int ct = (T + s - 1) / s;
-      const double cost = (double)waves * ((double)ct + 1.5) * (1.0 + 0.004 * s);
+      const double cost = wave_cost(num_m, s);
       if (cost < best * 0.999) {
         best = cost;
-        S = s;
+        S_main = S_tail = s;
+        main_blocks = num_m;
+      }
+    }
+    const int full = num_m / P * P, R = num_m - full;
+    if (full > 0 && R > 0) {
+      for (int s = 1; s <= smax; s++) {
+        const double cost = wave_cost(full, 1) + wave_cost(R, s);
+        if (cost < best * 0.999) {
+          best = cost;
+          S_main = 1;
+          S_tail = s;
+          main_blocks = full;
+        }
       }
     }
   }
-  if (const char* ev = getenv("MB200_COS_CHUNKS")) {  // tuning override
+  if (const char* ev = getenv("MB200_COS_CHUNKS")) {  // tuning override: uniform chunks
     const int s = atoi(ev);
-    if (s >= 1 && s <= T) S = s;
-  }
-  const int chunk_tiles = (T + S - 1) / S;
-  S = (T + chunk_tiles - 1) / chunk_tiles;
-  const int num_items = num_m * S;
-  // item order: groups of Gm row blocks x all S chunks run together, so the CTAs of one wave share
-  // A blocks and sweep the same B tiles (L2 reuse)
-  const int Gm = std::max(1, P / S);
-  std::vector<int2> items((size_t)num_items);
-  std::vector<int32_t> slot_of((size_t)num_m * S);
-  {
-    int w = 0;
-    for (int m0 = 0; m0 < num_m; m0 += Gm) {
-      const int m1 = std::min(num_m, m0 + Gm);
-      for (int s = 0; s < S; s++)
-        for (int m = m0; m < m1; m++) {
-          items[w] = make_int2(m, s);
-          slot_of[(size_t)m * S + s] = w;
-          w++;
-        }
+    if (s >= 1 && s <= T) {
+      S_main = S_tail = s;
+      main_blocks = num_m;
     }
   }
-  DevBuf d_items, d_slot, d_lists, d_cnt, d_bound, d_rowthr;
+  std::vector<int4> items;
+  std::vector<int32_t> slot_ptr((size_t)num_m + 1, 0), slot_of;
+  {
+    // item order inside a group: groups of Gm row blocks x all S chunks run together, chunk-major
+    std::vector<std::vector<int32_t>> slots((size_t)num_m);
+    auto emit = [&](int mb, int me, int S) {
+      const int ct = (T + S - 1) / S;
+      const int Sr = (T + ct - 1) / ct;
+      const int Gm = std::max(1, P / Sr);
+      for (int m0 = mb; m0 < me; m0 += Gm) {
+        const int m1 = std::min(me, m0 + Gm);
+        for (int sI = 0; sI < Sr; sI++)
+          for (int m = m0; m < m1; m++) {
+            slots[m].push_back((int32_t)items.size());
+            items.push_back(make_int4(m, sI * ct, std::min(T, (sI + 1) * ct), 0));
+          }
+      }
+    };
+    emit(0, main_blocks, S_main);
+    emit(main_blocks, num_m, S_tail);
+    for (int m = 0; m < num_m; m++) {
+      slot_ptr[m + 1] = slot_ptr[m] + (int32_t)slots[m].size();
+      slot_of.insert(slot_of.end(), slots[m].begin(), slots[m].end());
+    }
+  }
+  const int num_items = (int)items.size();
+  DevBuf d_items, d_slot, d_sptr, d_lists, d_cnt, d_bound, d_rowthr;
   MB_CHECK(d_rowthr.alloc(ws, (size_t)num_m * BM * sizeof(uint32_t)));
   MB_CUDA(ctx, cudaMemsetAsync(d_rowthr.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
-  MB_CHECK(d_items.alloc(ws, items.size() * sizeof(int2)));
+  MB_CHECK(d_items.alloc(ws, items.size() * sizeof(int4)));
   MB_CHECK(d_slot.alloc(ws, slot_of.size() * sizeof(int32_t)));
+  MB_CHECK(d_sptr.alloc(ws, slot_ptr.size() * sizeof(int32_t)));
   const size_t nlists = (size_t)num_items * 2 * BM;
   MB_CHECK(d_lists.alloc(ws, nlists * CAP * sizeof(uint2)));
   MB_CHECK(d_cnt.alloc(ws, nlists * sizeof(int32_t)));
   MB_CHECK(d_bound.alloc(ws, nlists * sizeof(float)));
-  MB_CUDA(ctx, cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  MB_CUDA(ctx, cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+  MB_CUDA(ctx, cudaMemcpyAsync(d_sptr.p, slot_ptr.data(), slot_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   MB_CUDA(ctx, cudaMemcpyAsync(d_slot.p, slot_of.data(), slot_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   TRACE("alloc+items");
 
@@ -1288,9 +1359,8 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
   const float eps_rel = a->dtype == MB200_DTYPE_F16 ? 0x1.0p-10f : 0x1.0p-6f;
   CosParams p;
   memset(&p, 0, sizeof(p));
-  p.items = (const int2*)d_items.p;
+  p.items = (const int4*)d_items.p;
   p.num_items = num_items;
-  p.chunk_tiles = chunk_tiles;
   p.total_tiles = T;
   p.tiles_per_block = tpb;
   p.depth = a->depth;
@@ -1351,8 +1421,9 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
   mp.lists = p.lists;
   mp.list_cnt = p.list_cnt;
   mp.list_bound = p.list_bound;
+  mp.row_thr = p.row_thr;
+  mp.slot_ptr = (const int32_t*)d_sptr.p;
   mp.slot_of = (const int32_t*)d_slot.p;
-  mp.S = S;
   mp.a_count = a->a_count;
   mp.ksel = ksel;
   mp.k = a->k;
@@ -1442,6 +1513,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
       unsigned long long gmax = 0;
       MB_CUDA(ctx, cudaMemcpyAsync(&gmax, d_gmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
       MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      TRACE("K3+merge+rowstats");
       if (gmax < (1ull << 31) && getenv("MB200_RESCORE64") == nullptr)
         k_rescore32<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp, nw);
       else
@@ -1449,6 +1521,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
       int32_t nflag = 0;
       MB_CUDA(ctx, cudaMemcpyAsync(&nflag, d_fcount.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      TRACE("rescore");
       ctx->last_fallback_rows = nflag;
       if (nflag > 0) {
         // exact full-row path, in batches bounded by scratch memory
