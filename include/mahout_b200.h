@@ -207,6 +207,34 @@ typedef struct mb200_cosine_args {
 } mb200_cosine_args;
 
 int mb200_cosine_topk(mb200_ctx* ctx, const mb200_cosine_args* args);
+
+/* Incremental form of mb200_cosine_topk: the B side arrives in pieces -- row chunks of an
+ * all-gather that is still in flight (C1 overlapped with K3) or peer blocks streamed
+ * through a ring when the gathered rows do not fit in HBM (config 5).
+ *   begin  fixes the A side and the parameters (a_*, depth, width, dtype, precision, k, threshold,
+ *          exclude_self, block_n, dense_* of `args`; its b_*, *_counters and out_* are ignored).
+ *   push   queues K3 for one piece on the context's stream and returns; the piece's memory may be
+ *          reused once the work queued so far has completed (mb200_sync, or an event recorded by
+ *          the caller on the stream it set with mb200_set_stream).  Per-row candidates and
+ *          thresholds persist across pushes, so later pieces start with the bound of the earlier.
+ *   finish merges, (RESCORED) re-scores and writes out_idx / out_sim / out_cnt of `fin`, then
+ *          frees the job.  RESCORED needs fin->a_counters and fin->b_counters for the WHOLE B side
+ *          resident, with fin->b_count / b_blocks / b_id_mul / b_id_add describing its layout.
+ *   abort  frees a job without results.
+ * One job per context at a time. */
+typedef struct mb200_cosine_job mb200_cosine_job;
+typedef struct mb200_cosine_piece {
+  const void* b_rows;      /* [b_blocks][d][b_count][ld] */
+  const uint32_t* b_valid; /* [b_blocks][d][valid_words(b_count)] */
+  int64_t b_count;
+  int32_t b_blocks;
+  /* global index of row l of block g of this piece = l * b_id_mul + g * b_id_add + b_id_base */
+  int64_t b_id_mul, b_id_add, b_id_base;
+} mb200_cosine_piece;
+int mb200_cosine_begin(mb200_ctx* ctx, const mb200_cosine_args* args, mb200_cosine_job** job);
+int mb200_cosine_push(mb200_cosine_job* job, const mb200_cosine_piece* piece);
+int mb200_cosine_finish(mb200_cosine_job* job, const mb200_cosine_args* fin);
+int mb200_cosine_abort(mb200_cosine_job* job);
 /* rows whose top-k could not be certified from the tensor-core candidates and went through the
  * exact full-row path during the last mb200_cosine_topk / mb200_bank_cosine_topk on ctx */
 int mb200_cosine_last_fallback_rows(mb200_ctx* ctx, int64_t* rows);

@@ -54,6 +54,14 @@ class CosineArgs(C.Structure):
     ]
 
 
+class CosinePiece(C.Structure):
+    """struct mb200_cosine_piece (include/mahout_b200.h)."""
+    _fields_ = [
+        ("b_rows", C.c_void_p), ("b_valid", C.c_void_p), ("b_count", C.c_int64), ("b_blocks", C.c_int32),
+        ("b_id_mul", C.c_int64), ("b_id_add", C.c_int64), ("b_id_base", C.c_int64),
+    ]
+
+
 _PROTOS = {
     "mb200_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "mb200_destroy": (C.c_int, [vp]),
@@ -89,6 +97,10 @@ _PROTOS = {
     "mb200_valid_words": (i64, [i64]),
     "mb200_bank_normalize": (C.c_int, [vp, C.c_int, vp, vp]),
     "mb200_cosine_topk": (C.c_int, [vp, C.POINTER(CosineArgs)]),
+    "mb200_cosine_begin": (C.c_int, [vp, C.POINTER(CosineArgs), C.POINTER(vp)]),
+    "mb200_cosine_push": (C.c_int, [vp, C.POINTER(CosinePiece)]),
+    "mb200_cosine_finish": (C.c_int, [vp, C.POINTER(CosineArgs)]),
+    "mb200_cosine_abort": (C.c_int, [vp]),
     "mb200_cosine_last_fallback_rows": (C.c_int, [vp, C.POINTER(i64)]),
     # bench / test support (mahout_b200/csrc/synth.h)
     "mb200_synth_events": (C.c_int, [vp, C.c_uint64, i64, i64, i64, vp, i64, vp, vp, vp, vp]),

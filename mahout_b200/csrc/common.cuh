@@ -51,6 +51,7 @@ struct mb200_ctx {
   // cudaFree of a few hundred MB per call would otherwise cost more than the kernels
   std::vector<std::pair<void*, size_t>> ws;
   int64_t last_fallback_rows = 0;
+  struct mb200_cosine_job* active_job = nullptr;  // the cosine stage's workspaces serve one job at a time
 };
 
 // borrows workspace slots from the context in request order; nothing is freed on return

@@ -50,7 +50,7 @@ struct CosParams {
   int64_t a_vw;
   const uint32_t* b_valid;
   int64_t b_vw;
-  uint32_t a_id_mul, a_id_off, b_id_mul, b_id_add;
+  uint32_t a_id_mul, a_id_off, b_id_mul, b_id_add, b_id_base;
   int32_t exclude_self, nonstrict;
   float thr_init;
   int32_t ksel;
@@ -400,7 +400,7 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 #pragma unroll
               for (int j = 0; j < 32; j++) dst[j] = __uint_as_float(v[j]) * p.inv_scale2;
             }
-            const uint32_t id0 = (uint32_t)(l0 + c * 32) * p.b_id_mul + (uint32_t)g * p.b_id_add;
+            const uint32_t id0 = (uint32_t)(l0 + c * 32) * p.b_id_mul + (uint32_t)g * p.b_id_add + p.b_id_base;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
               const float x = __uint_as_float(v[j]);
@@ -518,6 +518,12 @@ struct MergeParams {
   double threshold;        // admitted iff sim >= threshold && sim > 0
   float inv_scale2;
   int32_t rescored;
+  // carry state of a multi-push job: [rows][CAP] sorted keys (0 = empty) + bound
+  const unsigned long long* carry_in;
+  const float* carry_bound_in;
+  unsigned long long* carry_out;
+  float* carry_bound_out;
+  int32_t emit;            // 0: only update the carry state
   // TENSOR outputs
   long long* out_idx;
   double* out_sim;
@@ -540,6 +546,11 @@ __global__ void __launch_bounds__(256) k_merge(const MergeParams p) {
 #pragma unroll
   for (int s = 0; s < 2 * CAP / 32; s++) key[s] = 0ull;
   float bound = -INFINITY;
+  if (p.carry_in != nullptr) {
+#pragma unroll
+    for (int u = 0; u < CAP / 32; u++) key[u] = p.carry_in[(size_t)r * CAP + u * 32 + lane];
+    bound = p.carry_bound_in[r];
+  }
   // Every value <= row_thr is below the row's ksel-th best (K3 proved it when it published the
   // threshold, and the publishing list's bound covers everything dropped for that reason).
   uint32_t rthr = p.row_thr[r];
@@ -596,6 +607,12 @@ __global__ void __launch_bounds__(256) k_merge(const MergeParams p) {
     }
   }
   fold();
+  if (p.carry_out != nullptr) {
+#pragma unroll
+    for (int u = 0; u < CAP / 32; u++) p.carry_out[(size_t)r * CAP + u * 32 + lane] = key[u];
+    if (lane == 0) p.carry_bound_out[r] = bound;
+  }
+  if (!p.emit) return;
   // key[0 .. CAP/32) now holds the row's best <= ksel candidates, sorted (value desc, index asc)
   if (p.rescored) {
     int n = 0;
@@ -1205,51 +1222,145 @@ static double now_ms() {
     }                                                                             \
   } while (0)
 
-static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Workspace& ws) {
-  const bool trace = getenv("MB200_TRACE") != nullptr;
-  double t_last = now_ms();
-  if (!a) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: args is NULL");
-  if (!a->a_rows || !a->a_valid || !a->b_rows || !a->b_valid || !a->out_idx || !a->out_sim || !a->out_cnt)
+// ------------------------------------------------------------------------------------------------
+// A cosine job: the A side and the top-k parameters are fixed at begin; every push runs K3 over one
+// piece of the B side; the candidate lists of a push are merged lazily -- into the job's carry
+// state when another push follows, straight into the outputs at finish (so the one-shot call
+// begin + push + finish launches exactly one merge).
+// ------------------------------------------------------------------------------------------------
+struct mb200_cosine_job {
+  mb200_ctx* ctx = nullptr;
+  mb200_cosine_args a;           // begin arguments (A side, shape, k, threshold, ...)
+  bool rescored = false;
+  int ksel = 0, BN = 256, num_m = 0, ld = 0;
+  float scale2 = 1.f, eps_rel = 0.f;
+  uint32_t* row_thr = nullptr;               // [num_m * BM], job-owned
+  unsigned long long* best = nullptr;        // [num_m * BM][CAP] carry state (allocated on the 2nd push)
+  float* best_bound = nullptr;               // [num_m * BM]
+  bool have_best = false;
+  bool pending = false;                      // lists of the last push not merged yet
+  MergeParams mp;                            // ... described here (context workspace memory)
+  int pushes = 0;
+  size_t ws_base = 0, ws_next = 0;           // workspace slots [ws_base, ws_next) belong to the pending push
+};
+
+static void job_free(mb200_cosine_job* j) {
+  if (!j) return;
+  if (j->ctx->active_job == j) j->ctx->active_job = nullptr;
+  cudaFree(j->row_thr);
+  cudaFree(j->best);
+  cudaFree(j->best_bound);
+  delete j;
+}
+
+static int job_begin_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t ws_base, mb200_cosine_job** out) {
+  if (!a || !out) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_begin: args/out is NULL");
+  *out = nullptr;
+  if (ctx->active_job)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_begin: another cosine job is active on this context");
+  if (!a->a_rows || !a->a_valid)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: NULL pointer argument");
-  if (a->a_count <= 0 || a->b_count <= 0 || a->b_blocks <= 0 || a->depth <= 0 || a->depth > MB200_MAX_DEPTH ||
-      a->width <= 0)
-    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad shape (a_count=%lld b_count=%lld blocks=%d d=%d w=%d)",
-                      (long long)a->a_count, (long long)a->b_count, a->b_blocks, a->depth, a->width);
+  if (a->a_count <= 0 || a->depth <= 0 || a->depth > MB200_MAX_DEPTH || a->width <= 0)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad shape (a_count=%lld d=%d w=%d)",
+                      (long long)a->a_count, a->depth, a->width);
   if (a->k <= 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: k must be positive (got %d)", a->k);
   if (a->dtype != MB200_DTYPE_F16 && a->dtype != MB200_DTYPE_BF16)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad dtype %d", a->dtype);
   if (a->precision != MB200_PRECISION_TENSOR && a->precision != MB200_PRECISION_RESCORED)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad precision %d", a->precision);
-  const bool rescored = a->precision == MB200_PRECISION_RESCORED;
-  if (rescored && (!a->a_counters || !a->b_counters))
-    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: MB200_PRECISION_RESCORED needs a_counters and b_counters");
-  const int64_t total_b = a->b_count * a->b_blocks;
-  const int64_t max_id = std::max((a->a_count - 1) * a->a_id_mul + a->a_id_off,
-                                  (a->b_count - 1) * a->b_id_mul + (a->b_blocks - 1) * a->b_id_add);
-  if (a->a_id_mul <= 0 || a->b_id_mul <= 0 || a->a_id_off < 0 || a->b_id_add < 0 || max_id >= 0xFFFFFFFFLL)
+  if (a->a_id_mul <= 0 || a->a_id_off < 0 || (a->a_count - 1) * a->a_id_mul + a->a_id_off >= 0xFFFFFFFFLL)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: index mapping out of the 32-bit range");
-  const bool contiguous = a->b_id_mul == 1 && (a->b_blocks == 1 || a->b_id_add == a->b_count);
-  const bool interleaved = a->b_id_add == 1 && a->b_id_mul == a->b_blocks && a->b_blocks > 1;
-  if (!contiguous && !interleaved)
-    return mb200_fail(ctx, MB200_ERR_BAD_ARG,
-                      "mb200_cosine_topk: B indices must be contiguous blocks (mul=1, add=b_count) or interleaved "
-                      "shards (mul=b_blocks, add=1)");
-  // candidates kept per row: k + margin, at most CAP - 32
-  int margin = rescored ? std::max(14, a->k / 4) : 0;
-  int ksel = a->k + margin;
-  ksel = (ksel + 31) / 32 * 32;
+  if (a->block_n != 0 && a->block_n != 128 && a->block_n != 256)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: block_n must be 0, 128 or 256");
+  const bool rescored = a->precision == MB200_PRECISION_RESCORED;
+  // candidates kept per row: k + margin, at most CAP - 64
+  const int margin = rescored ? std::max(14, a->k / 4) : 0;
+  int ksel = (a->k + margin + 31) / 32 * 32;
   if (ksel > CAP - 64) ksel = CAP - 64;
   if (a->k > ksel)
     return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_cosine_topk: k = %d exceeds the fused top-k capacity %d", a->k, CAP - 64);
-  const int BN = a->block_n == 128 ? 128 : 256;
-  if (a->block_n != 0 && a->block_n != 128 && a->block_n != 256)
-    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: block_n must be 0, 128 or 256");
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  mb200_cosine_job* j = new mb200_cosine_job();
+  j->ctx = ctx;
+  j->a = *a;
+  j->rescored = rescored;
+  j->ksel = ksel;
+  j->BN = a->block_n == 128 ? 128 : 256;
+  j->num_m = (int)((a->a_count + BM - 1) / BM);
+  j->ld = (int)mb200_row_ld(a->width);
+  const float scale = a->dtype == MB200_DTYPE_F16 ? F16_SCALE : 1.0f;
+  j->scale2 = scale * scale;
+  j->eps_rel = a->dtype == MB200_DTYPE_F16 ? 0x1.0p-10f : 0x1.0p-6f;
+  j->ws_base = j->ws_next = ws_base;
+  const size_t rows_pad = (size_t)j->num_m * BM;
+  cudaError_t e = cudaMalloc(&j->row_thr, rows_pad * sizeof(uint32_t));
+  if (e != cudaSuccess) {
+    delete j;
+    return mb200_fail(ctx, MB200_ERR_OOM, "mb200_cosine_begin: cannot allocate row thresholds: %s", cudaGetErrorString(e));
+  }
+  e = cudaMemsetAsync(j->row_thr, 0, rows_pad * sizeof(uint32_t), ctx->stream);
+  if (e != cudaSuccess) {
+    job_free(j);
+    return mb200_fail(ctx, MB200_ERR_CUDA, "mb200_cosine_begin: %s", cudaGetErrorString(e));
+  }
+  ctx->active_job = j;
+  ctx->last_fallback_rows = 0;
+  *out = j;
+  return MB200_OK;
+}
 
-  const int ld = (int)mb200_row_ld(a->width);
-  const int tpb = (int)((a->b_count + BN - 1) / BN);
-  const int T = tpb * a->b_blocks;
-  const int num_m = (int)((a->a_count + BM - 1) / BM);
+// merge the pending lists: into the carry state (to_carry) or, at finish, into the outputs
+static int job_merge_pending(mb200_cosine_job* j, bool to_carry, const mb200_cosine_args* outs, MergeParams* used) {
+  mb200_ctx* ctx = j->ctx;
+  MergeParams mp = j->mp;
+  mp.carry_in = j->have_best ? j->best : nullptr;
+  mp.carry_bound_in = j->have_best ? j->best_bound : nullptr;
+  mp.carry_out = nullptr;
+  mp.carry_bound_out = nullptr;
+  mp.emit = to_carry ? 0 : 1;
+  if (to_carry) {
+    const size_t rows_pad = (size_t)j->num_m * BM;
+    if (!j->best) {
+      cudaError_t e = cudaMalloc(&j->best, rows_pad * CAP * sizeof(unsigned long long));
+      if (e == cudaSuccess) e = cudaMalloc(&j->best_bound, rows_pad * sizeof(float));
+      if (e != cudaSuccess)
+        return mb200_fail(ctx, MB200_ERR_OOM, "mb200_cosine_push: cannot allocate the carry state: %s", cudaGetErrorString(e));
+    }
+    mp.carry_out = j->best;
+    mp.carry_bound_out = j->best_bound;
+  } else {
+    mp.out_idx = (long long*)outs->out_idx;
+    mp.out_sim = outs->out_sim;
+    mp.out_cnt = outs->out_cnt;
+  }
+  k_merge<<<(unsigned)((j->a.a_count + 7) / 8), 256, 0, ctx->stream>>>(mp);
+  ctx->launches++;
+  MB_CUDA(ctx, cudaGetLastError());
+  if (to_carry) j->have_best = true;
+  j->pending = false;
+  if (used) *used = mp;
+  return MB200_OK;
+}
+
+static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
+  mb200_ctx* ctx = j->ctx;
+  const mb200_cosine_args* a = &j->a;
+  if (!pc || !pc->b_rows || !pc->b_valid)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: NULL pointer argument");
+  if (pc->b_count <= 0 || pc->b_blocks <= 0)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad shape (b_count=%lld blocks=%d)",
+                      (long long)pc->b_count, pc->b_blocks);
+  const int64_t max_id = (pc->b_count - 1) * pc->b_id_mul + (pc->b_blocks - 1) * pc->b_id_add + pc->b_id_base;
+  if (pc->b_id_mul <= 0 || pc->b_id_add < 0 || pc->b_id_base < 0 || max_id >= 0xFFFFFFFFLL)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: index mapping out of the 32-bit range");
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool trace = getenv("MB200_TRACE") != nullptr;
+  double t_last = now_ms();
+  if (j->pending) MB_CHECK(job_merge_pending(j, true, nullptr, nullptr));  // before the workspace is reused
+
+  const int BN = j->BN, ld = j->ld, num_m = j->num_m;
+  const int tpb = (int)((pc->b_count + BN - 1) / BN);
+  const int T = tpb * pc->b_blocks;
   if (a->dense_out && a->dense_ld < (int64_t)T * BN)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: dense_ld must be >= %lld", (long long)T * BN);
   // Work items (row block m, tile range [t0, t1)) are dealt round-robin to one CTA per SM; the CTAs of
@@ -1324,9 +1435,9 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
     }
   }
   const int num_items = (int)items.size();
-  DevBuf d_items, d_slot, d_sptr, d_lists, d_cnt, d_bound, d_rowthr;
-  MB_CHECK(d_rowthr.alloc(ws, (size_t)num_m * BM * sizeof(uint32_t)));
-  MB_CUDA(ctx, cudaMemsetAsync(d_rowthr.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
+  Workspace ws(ctx);
+  ws.next = j->ws_base;
+  DevBuf d_items, d_slot, d_sptr, d_lists, d_cnt, d_bound;
   MB_CHECK(d_items.alloc(ws, items.size() * sizeof(int4)));
   MB_CHECK(d_slot.alloc(ws, slot_of.size() * sizeof(int32_t)));
   MB_CHECK(d_sptr.alloc(ws, slot_ptr.size() * sizeof(int32_t)));
@@ -1334,6 +1445,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
   MB_CHECK(d_lists.alloc(ws, nlists * CAP * sizeof(uint2)));
   MB_CHECK(d_cnt.alloc(ws, nlists * sizeof(int32_t)));
   MB_CHECK(d_bound.alloc(ws, nlists * sizeof(float)));
+  j->ws_next = ws.next;
   MB_CUDA(ctx, cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
   MB_CUDA(ctx, cudaMemcpyAsync(d_sptr.p, slot_ptr.data(), slot_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   MB_CUDA(ctx, cudaMemcpyAsync(d_slot.p, slot_of.data(), slot_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1348,15 +1460,12 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
     MB_CHECK(make_tmap(ctx, &tmA, a->dtype, a->a_rows, 3, dims, str, box));
   }
   {
-    const uint64_t dims[4] = {(uint64_t)ld, (uint64_t)a->b_count, (uint64_t)a->depth, (uint64_t)a->b_blocks};
-    const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)a->b_count * ld * 2, (uint64_t)a->depth * a->b_count * ld * 2};
+    const uint64_t dims[4] = {(uint64_t)ld, (uint64_t)pc->b_count, (uint64_t)a->depth, (uint64_t)pc->b_blocks};
+    const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)pc->b_count * ld * 2, (uint64_t)a->depth * pc->b_count * ld * 2};
     const uint32_t box[4] = {BK, (uint32_t)BN, 1, 1};
-    MB_CHECK(make_tmap(ctx, &tmB, a->dtype, a->b_rows, 4, dims, str, box));
+    MB_CHECK(make_tmap(ctx, &tmB, a->dtype, pc->b_rows, 4, dims, str, box));
   }
 
-  const float scale = a->dtype == MB200_DTYPE_F16 ? F16_SCALE : 1.0f;
-  const float scale2 = scale * scale;
-  const float eps_rel = a->dtype == MB200_DTYPE_F16 ? 0x1.0p-10f : 0x1.0p-6f;
   CosParams p;
   memset(&p, 0, sizeof(p));
   p.items = (const int4*)d_items.p;
@@ -1368,31 +1477,33 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
   p.a_count = a->a_count;
   p.a_valid = a->a_valid;
   p.a_vw = mb200_valid_words(a->a_count);
-  p.b_valid = a->b_valid;
-  p.b_vw = mb200_valid_words(a->b_count);
+  p.b_valid = pc->b_valid;
+  p.b_vw = mb200_valid_words(pc->b_count);
   p.a_id_mul = (uint32_t)a->a_id_mul;
   p.a_id_off = (uint32_t)a->a_id_off;
-  p.b_id_mul = (uint32_t)a->b_id_mul;
-  p.b_id_add = (uint32_t)a->b_id_add;
+  p.b_id_mul = (uint32_t)pc->b_id_mul;
+  p.b_id_add = (uint32_t)pc->b_id_add;
+  p.b_id_base = (uint32_t)pc->b_id_base;
   p.exclude_self = a->exclude_self ? 1 : 0;
-  p.nonstrict = (a->b_blocks > 1 && interleaved) ? 1 : 0;
+  // a list scans its columns in index order iff the blocks do not interleave
+  p.nonstrict = (pc->b_blocks > 1 && pc->b_id_add < pc->b_count * pc->b_id_mul) ? 1 : 0;
   {
     const double thr = a->threshold > 0.0 ? a->threshold : 0.0;
-    const double slack = rescored ? (1.0 - (double)eps_rel) : (1.0 - 1e-6);
-    p.thr_init = (float)(thr * slack * (double)scale2);
+    const double slack = j->rescored ? (1.0 - (double)j->eps_rel) : (1.0 - 1e-6);
+    p.thr_init = (float)(thr * slack * (double)j->scale2);
     if (thr > 0.0) p.thr_init = nextafterf(p.thr_init, -INFINITY);
   }
-  p.ksel = ksel;
+  p.ksel = j->ksel;
   p.lists = (uint2*)d_lists.p;
   p.list_cnt = (int32_t*)d_cnt.p;
   p.list_bound = (float*)d_bound.p;
-  p.row_thr = (uint32_t*)d_rowthr.p;
+  p.row_thr = j->row_thr;
   p.dense_out = a->dense_out;
   p.dense_ld = a->dense_ld;
-  p.inv_scale2 = 1.0f / scale2;
+  p.inv_scale2 = 1.0f / j->scale2;
   p.idesc = umma_idesc_f16(a->dtype == MB200_DTYPE_BF16 ? 1 : 0, BM, BN);
-  // L2 eviction priorities: measured on config 3, evict_last(A)/evict_first(B) loses ~25 % against
-  // the default policy (profiles/r1_cosine_tuning.md), so both operands use evict_normal
+  // L2 eviction priorities: measured on config 3 and at 1e5 items, evict_last(A) / evict_first(B) lose
+  // against the default policy (profiles/r1_cosine_tuning.md), so both operands use evict_normal
   p.policy_a = L2_EVICT_NORMAL;
   p.policy_b = L2_EVICT_NORMAL;
   if (const char* ev = getenv("MB200_COS_HINTS")) {
@@ -1414,9 +1525,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
   ctx->launches++;
   TRACE("launch K3");
 
-  // merge (+ re-score)
-  DevBuf d_cand, d_ccnt, d_cbound, d_flag, d_fcount;
-  MergeParams mp;
+  MergeParams& mp = j->mp;
   memset(&mp, 0, sizeof(mp));
   mp.lists = p.lists;
   mp.list_cnt = p.list_cnt;
@@ -1425,14 +1534,48 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
   mp.slot_ptr = (const int32_t*)d_sptr.p;
   mp.slot_of = (const int32_t*)d_slot.p;
   mp.a_count = a->a_count;
-  mp.ksel = ksel;
+  mp.ksel = j->ksel;
   mp.k = a->k;
   mp.threshold = a->threshold > 0.0 ? a->threshold : 0.0;
   mp.inv_scale2 = p.inv_scale2;
-  mp.rescored = rescored ? 1 : 0;
-  mp.out_idx = (long long*)a->out_idx;
-  mp.out_sim = a->out_sim;
-  mp.out_cnt = a->out_cnt;
+  mp.rescored = j->rescored ? 1 : 0;
+  j->pending = true;
+  j->pushes++;
+  return MB200_OK;
+}
+
+// fin carries the outputs and, for MB200_PRECISION_RESCORED, the resident counters with the index
+// mapping of the whole B side (b_count, b_blocks, b_id_mul, b_id_add)
+static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) {
+  mb200_ctx* ctx = j->ctx;
+  const mb200_cosine_args* a = &j->a;
+  const bool trace = getenv("MB200_TRACE") != nullptr;
+  double t_last = now_ms();
+  if (!fin || !fin->out_idx || !fin->out_sim || !fin->out_cnt)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: NULL pointer argument");
+  if (!j->pending) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_finish: nothing was pushed");
+  const bool rescored = j->rescored;
+  if (rescored && (!fin->a_counters || !fin->b_counters))
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: MB200_PRECISION_RESCORED needs a_counters and b_counters");
+  bool contiguous = false;
+  if (rescored) {
+    if (fin->b_count <= 0 || fin->b_blocks <= 0)
+      return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad shape (b_count=%lld blocks=%d)",
+                        (long long)fin->b_count, fin->b_blocks);
+    contiguous = fin->b_id_mul == 1 && (fin->b_blocks == 1 || fin->b_id_add == fin->b_count);
+    const bool interleaved = fin->b_id_add == 1 && fin->b_id_mul == fin->b_blocks && fin->b_blocks > 1;
+    if (!contiguous && !interleaved)
+      return mb200_fail(ctx, MB200_ERR_BAD_ARG,
+                        "mb200_cosine_topk: B indices must be contiguous blocks (mul=1, add=b_count) or interleaved "
+                        "shards (mul=b_blocks, add=1)");
+  }
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  Workspace ws(ctx);
+  ws.next = j->ws_next;
+  const int64_t total_b = fin->b_count * fin->b_blocks;
+
+  // merge (+ re-score)
+  DevBuf d_cand, d_ccnt, d_cbound, d_flag, d_fcount;
   if (rescored) {
     MB_CHECK(d_cand.alloc(ws, (size_t)a->a_count * CAP * sizeof(uint32_t)));
     MB_CHECK(d_ccnt.alloc(ws, (size_t)a->a_count * sizeof(int32_t)));
@@ -1440,45 +1583,44 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
     MB_CHECK(d_flag.alloc(ws, (size_t)a->a_count * sizeof(int32_t)));
     MB_CHECK(d_fcount.alloc(ws, 2 * sizeof(int32_t)));
     MB_CUDA(ctx, cudaMemsetAsync(d_fcount.p, 0, 2 * sizeof(int32_t), ctx->stream));
-    mp.cand_id = (uint32_t*)d_cand.p;
-    mp.cand_cnt = (int32_t*)d_ccnt.p;
-    mp.cand_bound = (float*)d_cbound.p;
+    j->mp.cand_id = (uint32_t*)d_cand.p;
+    j->mp.cand_cnt = (int32_t*)d_ccnt.p;
+    j->mp.cand_bound = (float*)d_cbound.p;
   }
   ctx->last_fallback_rows = 0;
   {
     ProfScope prof(ctx, MB200_K_RESCORE);
-    k_merge<<<(unsigned)((a->a_count + 7) / 8), 256, 0, ctx->stream>>>(mp);
-    ctx->launches++;
-    MB_CUDA(ctx, cudaGetLastError());
+    MergeParams mp;
+    MB_CHECK(job_merge_pending(j, false, fin, &mp));
     if (rescored) {
       RescoreParams rp;
       memset(&rp, 0, sizeof(rp));
-      rp.a_counters = (const long long*)a->a_counters;
-      rp.b_counters = (const long long*)a->b_counters;
+      rp.a_counters = (const long long*)fin->a_counters;
+      rp.b_counters = (const long long*)fin->b_counters;
       rp.a_count = a->a_count;
-      rp.b_count = a->b_count;
+      rp.b_count = fin->b_count;
       rp.d = a->depth;
       rp.W = a->width;
-      rp.blocks = a->b_blocks;
-      rp.a_id_mul = p.a_id_mul;
-      rp.a_id_off = p.a_id_off;
-      rp.b_id_mul = p.b_id_mul;
-      rp.b_id_add = contiguous ? (uint32_t)a->b_count : 1u;
+      rp.blocks = fin->b_blocks;
+      rp.a_id_mul = (uint32_t)a->a_id_mul;
+      rp.a_id_off = (uint32_t)a->a_id_off;
+      rp.b_id_mul = (uint32_t)fin->b_id_mul;
+      rp.b_id_add = contiguous ? (uint32_t)fin->b_count : 1u;
       rp.cand_id = mp.cand_id;
       rp.cand_cnt = mp.cand_cnt;
       rp.cand_bound = mp.cand_bound;
-      rp.inv_scale2 = p.inv_scale2;
-      rp.eps_rel = eps_rel;
+      rp.inv_scale2 = mp.inv_scale2;
+      rp.eps_rel = j->eps_rel;
       rp.k = a->k;
       rp.threshold = mp.threshold;
-      rp.out_idx = (long long*)a->out_idx;
-      rp.out_sim = a->out_sim;
-      rp.out_cnt = a->out_cnt;
+      rp.out_idx = (long long*)fin->out_idx;
+      rp.out_sim = fin->out_sim;
+      rp.out_cnt = fin->out_cnt;
       rp.row_flag = (int32_t*)d_flag.p;
       rp.flag_count = (int32_t*)d_fcount.p;
       // narrow (int32) copies + per-row statistics; the generic int64 kernel is kept for banks whose
       // counters do not fit 31 bits
-      const bool same = a->a_counters == a->b_counters && a->b_blocks == 1 && a->a_count == a->b_count;
+      const bool same = fin->a_counters == fin->b_counters && fin->b_blocks == 1 && a->a_count == fin->b_count;
       const size_t rows_b = (size_t)total_b * a->depth, rows_a = (size_t)a->a_count * a->depth;
       DevBuf d_nb, d_bmax, d_bss, d_na, d_amax, d_ass, d_gmax;
       MB_CHECK(d_nb.alloc(ws, rows_b * a->width * sizeof(int)));
@@ -1486,7 +1628,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
       MB_CHECK(d_bss.alloc(ws, rows_b * 8));
       MB_CHECK(d_gmax.alloc(ws, 8));
       MB_CUDA(ctx, cudaMemsetAsync(d_gmax.p, 0, 8, ctx->stream));
-      k_rowstats<<<(unsigned)rows_b, 256, 0, ctx->stream>>>((const long long*)a->b_counters, a->width, (int*)d_nb.p,
+      k_rowstats<<<(unsigned)rows_b, 256, 0, ctx->stream>>>((const long long*)fin->b_counters, a->width, (int*)d_nb.p,
                                                              (unsigned long long*)d_bmax.p, (long long*)d_bss.p,
                                                              (unsigned long long*)d_gmax.p);
       ctx->launches++;
@@ -1502,7 +1644,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
         MB_CHECK(d_na.alloc(ws, rows_a * a->width * sizeof(int)));
         MB_CHECK(d_amax.alloc(ws, rows_a * 8));
         MB_CHECK(d_ass.alloc(ws, rows_a * 8));
-        k_rowstats<<<(unsigned)rows_a, 256, 0, ctx->stream>>>((const long long*)a->a_counters, a->width, (int*)d_na.p,
+        k_rowstats<<<(unsigned)rows_a, 256, 0, ctx->stream>>>((const long long*)fin->a_counters, a->width, (int*)d_na.p,
                                                                (unsigned long long*)d_amax.p, (long long*)d_ass.p,
                                                                (unsigned long long*)d_gmax.p);
         ctx->launches++;
@@ -1518,6 +1660,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
         k_rescore32<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp, nw);
       else
         k_rescore<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp);
+      ctx->launches++;
       int32_t nflag = 0;
       MB_CUDA(ctx, cudaMemcpyAsync(&nflag, d_fcount.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1525,7 +1668,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
       ctx->last_fallback_rows = nflag;
       if (nflag > 0) {
         // exact full-row path, in batches bounded by scratch memory
-        rp.b_id_add = p.b_id_add;  // forward mapping for k_exact_*
+        rp.b_id_add = (uint32_t)fin->b_id_add;  // forward mapping for k_exact_*
         DevBuf d_rows, d_scratch;
         MB_CHECK(d_rows.alloc(ws, (size_t)nflag * sizeof(int32_t)));
         k_collect_flagged<<<(unsigned)((a->a_count + 255) / 256), 256, 0, ctx->stream>>>(
@@ -1537,7 +1680,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
           const int m = std::min(batch, nflag - off);
           k_exact_rows<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, 1.0, 1.0, (double*)d_scratch.p, total_b);
           k_exact_topk<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (const double*)d_scratch.p, total_b,
-                                                   p.exclude_self);
+                                                   a->exclude_self ? 1 : 0);
           ctx->launches += 2;
           MB_CUDA(ctx, cudaGetLastError());
         }
@@ -1548,6 +1691,39 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, Worksp
   MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // results are complete on return
   TRACE("sync");
   return MB200_OK;
+}
+
+// the one-shot form: begin + one push of the whole B side + finish
+static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t ws_base) {
+  if (!a) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: args is NULL");
+  if (!a->b_rows || !a->b_valid || !a->out_idx || !a->out_sim || !a->out_cnt)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: NULL pointer argument");
+  if (a->b_count <= 0 || a->b_blocks <= 0)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad shape (a_count=%lld b_count=%lld blocks=%d d=%d w=%d)",
+                      (long long)a->a_count, (long long)a->b_count, a->b_blocks, a->depth, a->width);
+  const bool contiguous = a->b_id_mul == 1 && (a->b_blocks == 1 || a->b_id_add == a->b_count);
+  const bool interleaved = a->b_id_add == 1 && a->b_id_mul == a->b_blocks && a->b_blocks > 1;
+  if (a->b_id_mul > 0 && a->b_id_add >= 0 && !contiguous && !interleaved)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG,
+                      "mb200_cosine_topk: B indices must be contiguous blocks (mul=1, add=b_count) or interleaved "
+                      "shards (mul=b_blocks, add=1)");
+  if (a->precision == MB200_PRECISION_RESCORED && (!a->a_counters || !a->b_counters))
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: MB200_PRECISION_RESCORED needs a_counters and b_counters");
+  mb200_cosine_job* j = nullptr;
+  MB_CHECK(job_begin_locked(ctx, a, ws_base, &j));
+  mb200_cosine_piece pc;
+  pc.b_rows = a->b_rows;
+  pc.b_valid = a->b_valid;
+  pc.b_count = a->b_count;
+  pc.b_blocks = a->b_blocks;
+  pc.b_id_mul = a->b_id_mul;
+  pc.b_id_add = a->b_id_add;
+  pc.b_id_base = 0;
+  int rc = job_push_locked(j, &pc);
+  if (rc == MB200_OK) rc = job_finish_locked(j, a);
+  if (rc != MB200_OK) cudaStreamSynchronize(ctx->stream);
+  job_free(j);
+  return rc;
 }
 
 int mb200_bank_cosine_topk(mb200_bank* bk, int32_t k, double threshold, int exclude_self, int dtype,
@@ -1596,7 +1772,7 @@ int mb200_bank_cosine_topk(mb200_bank* bk, int32_t k, double threshold, int excl
     a.out_sim = out_sim;
     a.out_cnt = out_cnt;
   }
-  MB_CHECK(cosine_topk_locked(ctx, &a, ws));
+  MB_CHECK(cosine_topk_locked(ctx, &a, ws.next));
   if (mem == MB200_MEM_HOST) {
     MB_CUDA(ctx, cudaMemcpyAsync(out_idx, o_idx.p, (size_t)bk->E * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(ctx, cudaMemcpyAsync(out_sim, o_sim.p, (size_t)bk->E * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1609,8 +1785,39 @@ int mb200_bank_cosine_topk(mb200_bank* bk, int32_t k, double threshold, int excl
 int mb200_cosine_topk(mb200_ctx* ctx, const mb200_cosine_args* args) {
   if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_cosine_topk: ctx is NULL");
   std::lock_guard<std::mutex> g(ctx->mu);
-  Workspace ws(ctx);
-  return cosine_topk_locked(ctx, args, ws);
+  return cosine_topk_locked(ctx, args, 0);
+}
+
+int mb200_cosine_begin(mb200_ctx* ctx, const mb200_cosine_args* args, mb200_cosine_job** job) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_cosine_begin: ctx is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return job_begin_locked(ctx, args, 0, job);
+}
+
+int mb200_cosine_push(mb200_cosine_job* job, const mb200_cosine_piece* piece) {
+  if (!job) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_cosine_push: job is NULL");
+  std::lock_guard<std::mutex> g(job->ctx->mu);
+  return job_push_locked(job, piece);
+}
+
+int mb200_cosine_finish(mb200_cosine_job* job, const mb200_cosine_args* fin) {
+  if (!job) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_cosine_finish: job is NULL");
+  mb200_ctx* ctx = job->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  int rc = job_finish_locked(job, fin);
+  if (rc != MB200_OK) cudaStreamSynchronize(ctx->stream);
+  job_free(job);
+  return rc;
+}
+
+int mb200_cosine_abort(mb200_cosine_job* job) {
+  if (!job) return MB200_OK;
+  mb200_ctx* ctx = job->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  job_free(job);
+  return MB200_OK;
 }
 
 }  // extern "C"

@@ -186,6 +186,11 @@ class GpuShardBackend:
             a_counters=a_counters, b_counters=b_counters)
         return idx, sim, cnt
 
+    def begin(self, plan, a_rows, a_valid, k, threshold, dtype, precision):
+        """incremental form of `cosine` (mb200_cosine_begin / push / finish)"""
+        return sk.CosineJob(self.ctx, a_rows, a_valid, self.bank.d, self.bank.w, k, a_id=(plan.G, plan.rank),
+                            threshold=threshold, exclude_self=True, dtype=dtype, precision=precision)
+
     def close(self):
         self.bank.close()
 
@@ -200,12 +205,101 @@ def _all_gather(t, world, group):
     return flat.view((world,) + tuple(t.shape))
 
 
+def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precision, group=None,
+                     chunk_rows: int = 2048, a_counters=None):
+    """C1 overlapped with K3: the all-gather of the normalised rows runs in row chunks on
+    a communication stream, two chunks ahead of the compute stream, and every gathered chunk
+    [G, d, rows_c, ld] is pushed into one incremental cosine job as soon as it has landed.  Only two
+    chunk buffers are resident, so the gathered operand never exists as a whole (config 5).
+    Chunk c covers local rows [c0, c1) of every shard: global index of (shard g, row l) = (c0 + l) * G + g.
+    Returns this rank's (idx, sim, cnt)."""
+    import torch
+    import torch.distributed as dist
+    G, E_loc = plan.G, plan.rows_per_shard
+    d, ld = int(a_rows.shape[0]), int(a_rows.shape[2])
+    chunk_rows = max(256, (int(chunk_rows) + 255) // 256 * 256)
+    cuda = a_rows.is_cuda
+    nbuf = 2
+    rows_max = min(chunk_rows, (E_loc + 255) // 256 * 256)
+    vw_of = lambda n: (n + 255) // 256 * 8                                  # mb200_valid_words
+    bufs = [torch.empty(G * d * rows_max * ld, dtype=a_rows.dtype, device=a_rows.device) for _ in range(nbuf)]
+    vbufs = [torch.empty(G * d * vw_of(rows_max), dtype=a_valid.dtype, device=a_valid.device) for _ in range(nbuf)]
+    job = backend.begin(plan, a_rows, a_valid, k, threshold, dtype, precision)
+    if cuda:
+        ctx = backend.ctx
+        prev = ctx.stream_ptr
+        comp = torch.cuda.Stream(a_rows.device) if prev is None else torch.cuda.ExternalStream(prev, a_rows.device)
+        if prev is None:
+            ctx.set_stream(comp.cuda_stream)
+        comm = torch.cuda.Stream(a_rows.device)
+        comm.wait_stream(torch.cuda.current_stream(a_rows.device))
+        comm.wait_stream(comp)
+        free = [None] * nbuf
+    b_cnt = None
+    try:
+        for ci, c0 in enumerate(range(0, E_loc, chunk_rows)):
+            c1 = min(E_loc, c0 + chunk_rows)
+            n, vw = c1 - c0, vw_of(c1 - c0)
+            b = ci % nbuf
+            out = bufs[b][:G * d * n * ld].view(G, d, n, ld)
+            vout = vbufs[b][:G * d * vw].view(G, d, vw)
+
+            def gather():
+                src = a_rows[:, c0:c1].contiguous()
+                vsrc = torch.zeros((d, vw), dtype=a_valid.dtype, device=a_valid.device)
+                words = a_valid[:, c0 // 32:(c1 + 31) // 32]
+                vsrc[:, :words.shape[1]] = words
+                dist.all_gather_into_tensor(out.view(G * d, n, ld), src, group=group)
+                dist.all_gather_into_tensor(vout.view(G * d, vw), vsrc, group=group)
+
+            if cuda:
+                with torch.cuda.stream(comm):
+                    if free[b] is not None:
+                        comm.wait_event(free[b])                 # the push that read this buffer is done
+                    gather()
+                    landed = torch.cuda.Event()
+                    landed.record(comm)
+                comp.wait_event(landed)
+                job.push(out, vout, id_mul=G, id_add=1, id_base=c0 * G)
+                free[b] = torch.cuda.Event()
+                free[b].record(comp)
+            else:
+                gather()
+                job.push(out.clone(), vout.clone(), id_mul=G, id_add=1, id_base=c0 * G)
+        if precision == "rescored":
+            # the exact re-score reads the counters of arbitrary peers: gathered whole, behind the rows
+            if cuda:
+                with torch.cuda.stream(comm):
+                    b_cnt = _all_gather(a_counters, G, group)
+                    done = torch.cuda.Event()
+                    done.record(comm)
+                comp.wait_event(done)
+            else:
+                b_cnt = _all_gather(a_counters, G, group)
+            res = job.finish(a_counters=a_counters, b_counters=b_cnt, b_id=(G, 1))
+        else:
+            res = job.finish()
+        if cuda:
+            torch.cuda.current_stream(a_rows.device).wait_stream(comp)
+            torch.cuda.current_stream(a_rows.device).wait_stream(comm)
+        return res
+    except BaseException:
+        job.abort()
+        raise
+    finally:
+        if cuda and prev is None:
+            backend.ctx.sync()
+            backend.ctx.set_stream(None)
+
+
 def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM,
                             threshold: float | None = None, width: int = 4096, depth: int = 4, seed: int = 42,
                             frac_bits: int = 1, dtype: str = "f16", precision: str = "tensor",
-                            group=None, backend=None, gather_result: bool = True):
+                            group=None, backend=None, gather_result: bool = True, chunk_rows: int = 0):
     """One call per rank (torch.distributed initialised; NCCL on GPUs).  `row, user, pref` are the
     events this rank holds (any subset of the stream: they are first routed to their owners).
+    chunk_rows > 0 selects the pipelined form (`pipelined_cosine`): the all-gather runs in chunks of that
+    many rows per shard, overlapped with K3.
     Returns (idx, sim, cnt) for all N items on every rank when gather_result, else this rank's
     shard in local row order."""
     import torch
@@ -226,20 +320,22 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
     lrow, luser, lpref = plan.my_events(row, user, pref)
     backend.build(plan, lrow, luser, lpref, width, depth, seed, frac_bits)
     a_rows, a_valid = backend.normalized(dtype)
-    if world > 1:
-        b_rows = _all_gather(a_rows, world, group)          # C1
-        b_valid = _all_gather(a_valid, world, group)
+    a_cnt = backend.counters() if precision == "rescored" else None
+    if world > 1 and chunk_rows > 0:
+        # C1 in row chunks, overlapped with K3 through the incremental cosine job
+        idx, sim, cnt = pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precision, group,
+                                         chunk_rows, a_cnt)
     else:
-        b_rows, b_valid = a_rows.unsqueeze(0), a_valid.unsqueeze(0)
-    a_cnt = b_cnt = None
-    if precision == "rescored":
-        a_cnt = backend.counters()
         if world > 1:
-            b_cnt = _all_gather(a_cnt, world, group)
+            b_rows = _all_gather(a_rows, world, group)          # C1
+            b_valid = _all_gather(a_valid, world, group)
         else:
-            b_cnt = a_cnt
-    idx, sim, cnt = backend.cosine(plan, a_rows, a_valid, b_rows, b_valid, k, threshold, dtype, precision,
-                                   a_cnt, b_cnt)
+            b_rows, b_valid = a_rows.unsqueeze(0), a_valid.unsqueeze(0)
+        b_cnt = None
+        if precision == "rescored":
+            b_cnt = _all_gather(a_cnt, world, group) if world > 1 else a_cnt
+        idx, sim, cnt = backend.cosine(plan, a_rows, a_valid, b_rows, b_valid, k, threshold, dtype, precision,
+                                       a_cnt, b_cnt)
     if not gather_result:
         backend.close()
         return idx, sim, cnt

@@ -34,6 +34,7 @@ class Context:
             N.check(rc, None)
         self._h = h
         self.device = int(device)
+        self.stream_ptr = None       # the caller's stream when set_stream was used
 
     @property
     def handle(self):
@@ -62,6 +63,7 @@ class Context:
 
     def set_stream(self, cuda_stream: int | None):
         N.check(N.lib().mb200_set_stream(self.handle, C.c_void_p(cuda_stream or 0)), self.handle)
+        self.stream_ptr = cuda_stream or None
 
     def set_profiling(self, on: bool):
         N.check(N.lib().mb200_set_profiling(self.handle, int(on)), self.handle)
@@ -341,16 +343,19 @@ _PRECISIONS = {"tensor": N.PRECISION_TENSOR, "rescored": N.PRECISION_RESCORED}
 def cosine_topk_blocks(ctx: Context, a_rows, a_valid, b_rows, b_valid, depth: int, width: int, k: int,
                        a_id=(1, 0), b_id=(1, 0), threshold: float | None = None, exclude_self: bool = True,
                        dtype: str = "f16", precision: str = "tensor", a_counters=None, b_counters=None,
-                       block_n: int = 0, want_dense: bool = False):
+                       block_n: int = 0, want_dense: bool = False, out=None):
     """mb200_cosine_topk over device tensors: A rows [d, a_count, ld] against b_blocks gathered blocks
     B [blocks, d, b_count, ld].  Returns torch device tensors (idx, sim, cnt[, dense])."""
     import torch
     dev = f"cuda:{ctx.device}"
     a_count = a_rows.shape[1]
     blocks, b_count = b_rows.shape[0], b_rows.shape[2]
-    idx = torch.empty((a_count, k), dtype=torch.int64, device=dev)
-    sim = torch.empty((a_count, k), dtype=torch.float64, device=dev)
-    cnt = torch.empty((a_count,), dtype=torch.int32, device=dev)
+    if out is not None:
+        idx, sim, cnt = out
+    else:
+        idx = torch.empty((a_count, k), dtype=torch.int64, device=dev)
+        sim = torch.empty((a_count, k), dtype=torch.float64, device=dev)
+        cnt = torch.empty((a_count,), dtype=torch.int32, device=dev)
     args = N.CosineArgs()
     args.a_rows, args.a_valid, args.a_count = a_rows.data_ptr(), a_valid.data_ptr(), a_count
     args.a_id_mul, args.a_id_off = a_id
@@ -371,6 +376,66 @@ def cosine_topk_blocks(ctx: Context, a_rows, a_valid, b_rows, b_valid, depth: in
     N.check(N.lib().mb200_cosine_topk(ctx.handle, C.byref(args)), ctx.handle)
     ctx.sync()
     return (idx, sim, cnt, dense) if want_dense else (idx, sim, cnt)
+
+
+class CosineJob:
+    """mb200_cosine_begin / push / finish: the B side arrives in pieces (row chunks of an all-gather in
+    flight, or peer blocks streamed through a ring).  All tensors are torch CUDA tensors; push only
+    queues work on the context's stream."""
+
+    def __init__(self, ctx: Context, a_rows, a_valid, depth: int, width: int, k: int, a_id=(1, 0),
+                 threshold: float | None = None, exclude_self: bool = True, dtype: str = "f16",
+                 precision: str = "tensor", block_n: int = 0):
+        self.ctx, self.k, self.a_count = ctx, int(k), int(a_rows.shape[1])
+        self._keep = [a_rows, a_valid]              # the job borrows these until finish
+        args = N.CosineArgs()
+        args.a_rows, args.a_valid, args.a_count = a_rows.data_ptr(), a_valid.data_ptr(), self.a_count
+        args.a_id_mul, args.a_id_off = a_id
+        args.depth, args.width, args.dtype, args.precision = depth, width, _DTYPES[dtype], _PRECISIONS[precision]
+        args.k, args.threshold, args.exclude_self, args.block_n = k, (threshold or 0.0), int(exclude_self), block_n
+        self._args = args
+        h = C.c_void_p()
+        N.check(N.lib().mb200_cosine_begin(ctx.handle, C.byref(args), C.byref(h)), ctx.handle)
+        self._h = h
+
+    def push(self, b_rows, b_valid, id_mul: int = 1, id_add: int = 0, id_base: int = 0):
+        """b_rows [blocks, d, b_count, ld], b_valid [blocks, d, valid_words(b_count)];
+        global index of row l of block g = l * id_mul + g * id_add + id_base."""
+        pc = N.CosinePiece()
+        pc.b_rows, pc.b_valid = b_rows.data_ptr(), b_valid.data_ptr()
+        pc.b_blocks, pc.b_count = int(b_rows.shape[0]), int(b_rows.shape[2])
+        pc.b_id_mul, pc.b_id_add, pc.b_id_base = int(id_mul), int(id_add), int(id_base)
+        self._keep += [b_rows, b_valid]
+        N.check(N.lib().mb200_cosine_push(self._h, C.byref(pc)), self.ctx.handle)
+
+    def finish(self, a_counters=None, b_counters=None, b_id=(1, 0), out=None):
+        """Returns (idx, sim, cnt) device tensors.  precision="rescored" needs the resident counters:
+        a_counters [a_count, d, w], b_counters [blocks, b_count, d, w] with b_id = (id_mul, id_add)."""
+        import torch
+        dev = f"cuda:{self.ctx.device}"
+        if out is None:
+            out = (torch.empty((self.a_count, self.k), dtype=torch.int64, device=dev),
+                   torch.empty((self.a_count, self.k), dtype=torch.float64, device=dev),
+                   torch.empty((self.a_count,), dtype=torch.int32, device=dev))
+        idx, sim, cnt = out
+        fin = N.CosineArgs()
+        fin.out_idx, fin.out_sim, fin.out_cnt = idx.data_ptr(), sim.data_ptr(), cnt.data_ptr()
+        if a_counters is not None:
+            fin.a_counters, fin.b_counters = a_counters.data_ptr(), b_counters.data_ptr()
+            fin.b_blocks, fin.b_count = int(b_counters.shape[0]), int(b_counters.shape[1])
+            fin.b_id_mul, fin.b_id_add = b_id
+        h, self._h = self._h, None
+        N.check(N.lib().mb200_cosine_finish(h, C.byref(fin)), self.ctx.handle)
+        self._keep = []
+        return idx, sim, cnt
+
+    def abort(self):
+        if getattr(self, "_h", None) is not None:
+            N.lib().mb200_cosine_abort(self._h)
+            self._h = None
+            self._keep = []
+
+    __del__ = abort
 
 
 def last_fallback_rows(ctx: Context) -> int:

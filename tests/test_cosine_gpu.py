@@ -187,3 +187,80 @@ def test_bad_arguments(mb, ctx):
     with pytest.raises(mb.NativeError):
         bank.cosine_topk(1000)          # beyond the fused top-k capacity
     bank.close()
+
+
+def _shards(mb, ctx, full, G):
+    """shard banks (owner = index % G) of one bank -> rows [G,d,per,ld], valid [G,d,vw], counters [G,per,d,w]"""
+    import torch
+    E, d, w = full.E, full.d, full.w
+    counters = full.counters_tensor()
+    per = E // G
+    rows, valid, cnts = [], [], []
+    for g in range(G):
+        sh = mb.SketchBank(per, w, d, 42, 1, ctx)
+        sh.counters_tensor().copy_(counters[g::G])
+        torch.cuda.synchronize()
+        r, v = sh.normalize()
+        rows.append(r)
+        valid.append(v)
+        cnts.append(sh.counters_tensor().clone())
+        sh.close()
+    return torch.stack(rows), torch.stack(valid), torch.stack(cnts)
+
+
+@pytest.mark.parametrize("precision", ["tensor", "rescored"])
+def test_incremental_job_equals_one_shot_and_oracle(mb, ctx, precision):
+    """mb200_cosine_begin / push / finish: the B side pushed block by block (ring order), and as row
+    chunks of all blocks (a chunked all-gather), gives the one-shot result; re-scored == oracle."""
+    import torch
+    from mahout_b200.sketch import CosineJob, cosine_topk_blocks
+    E, d, w, k, G = 1536, 4, 512, 20, 3
+    full, ref = _make_bank(mb, ctx, E, d, w, 40 * E, seed=21, empty=(7, 100))
+    b_rows, b_valid, b_cnt = _shards(mb, ctx, full, G)
+    per = E // G
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    for g in range(G):
+        kw = dict(a_counters=b_cnt[g], b_counters=b_cnt) if precision == "rescored" else {}
+        one = cosine_topk_blocks(ctx, b_rows[g], b_valid[g], b_rows, b_valid, d, w, k, a_id=(G, g), b_id=(G, 1),
+                                 precision=precision, **kw)
+        # (1) one push per peer block, starting with the local one (ring order)
+        job = CosineJob(ctx, b_rows[g], b_valid[g], d, w, k, a_id=(G, g), precision=precision)
+        for s in range(G):
+            src = (g + s) % G
+            job.push(b_rows[src:src + 1], b_valid[src:src + 1], id_mul=G, id_add=0, id_base=src)
+        ring = job.finish(b_id=(G, 1), **kw)
+        # (2) row chunks of all blocks (what a chunked all-gather delivers); chunk rows % 256 == 0
+        job = CosineJob(ctx, b_rows[g], b_valid[g], d, w, k, a_id=(G, g), precision=precision)
+        for c0 in range(0, per, 256):
+            c1 = min(per, c0 + 256)
+            rows_c = b_rows[:, :, c0:c1].contiguous()
+            valid_c = b_valid[:, :, c0 // 32:(c1 + 31) // 32].contiguous()
+            vw = int(mb._native.lib().mb200_valid_words(c1 - c0))
+            vpad = torch.zeros((G, d, vw), dtype=torch.int32, device=valid_c.device)
+            vpad[:, :, :valid_c.shape[2]] = valid_c
+            job.push(rows_c, vpad, id_mul=G, id_add=1, id_base=c0 * G)
+        chunks = job.finish(b_id=(G, 1), **kw)
+        for got in (ring, chunks):
+            for x, y in zip(got, one):
+                assert torch.equal(x, y)
+        if precision == "rescored":
+            assert (one[2].cpu().numpy() == ocnt[g::G]).all()
+            assert (one[0].cpu().numpy() == oidx[g::G]).all()
+            assert one[1].cpu().numpy().tobytes() == osim[g::G].tobytes()
+    full.close()
+
+
+def test_job_misuse(mb, ctx):
+    from mahout_b200.sketch import CosineJob
+    bank = mb.SketchBank(256, 64, 2, 42, 1, ctx)
+    rows, valid = bank.normalize()
+    job = CosineJob(ctx, rows, valid, 2, 64, 4)
+    with pytest.raises(ValueError):
+        CosineJob(ctx, rows, valid, 2, 64, 4)          # one job per context
+    with pytest.raises(ValueError):
+        job.finish()                                   # nothing pushed
+    job = CosineJob(ctx, rows, valid, 2, 64, 4)         # the failed finish freed the job
+    job.push(rows.unsqueeze(0), valid.unsqueeze(0))
+    idx, sim, cnt = job.finish()
+    assert idx.shape == (256, 4)
+    bank.close()

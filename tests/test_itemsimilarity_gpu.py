@@ -115,6 +115,11 @@ def _nccl_worker(rank, world, port, q):
     for precision in ("rescored", "tensor"):
         res[precision] = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N,
                                                      k=20, width=1024, depth=4, precision=precision)
+        # chunked all-gather overlapped with K3 through the incremental job: must give the same answer
+        piped = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N,
+                                            k=20, width=1024, depth=4, precision=precision, chunk_rows=256)
+        for x, y in zip(piped, res[precision]):
+            assert x.tobytes() == y.tobytes(), f"pipelined {precision} result differs"
     if rank == 0:
         q.put((row, user, pref, res))
     dist.barrier()

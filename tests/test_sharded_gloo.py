@@ -49,7 +49,49 @@ class OracleShardBackend:
             idx[l], s[l], cnt[l] = i1[0], s1[0], c1[0]
         return torch.from_numpy(idx), torch.from_numpy(s), torch.from_numpy(cnt)
 
+    def begin(self, plan, a_rows, a_valid, k, threshold, dtype, precision):
+        return _OracleJob(plan, k, threshold)
+
     def close(self):
+        pass
+
+
+class _OracleJob:
+    """stand-in for sk.CosineJob: collects the pushed pieces, rebuilds the bank from the index mapping"""
+
+    def __init__(self, plan, k, threshold):
+        self.plan, self.k, self.threshold, self.pieces = plan, k, threshold, []
+
+    def push(self, b_rows, b_valid, id_mul=1, id_add=0, id_base=0):
+        self.pieces.append((b_rows.numpy().copy(), id_mul, id_add, id_base))
+
+    def finish(self, a_counters=None, b_counters=None, b_id=(1, 0), out=None):
+        plan, k = self.plan, self.k
+        d, w = self.pieces[0][0].shape[1], self.pieces[0][0].shape[3]
+        full = np.zeros((plan.rows_per_shard * plan.G, d, w))
+        seen = np.zeros(full.shape[0], bool)
+        for rows, mul, add, base in self.pieces:
+            for g in range(rows.shape[0]):
+                ids = np.arange(rows.shape[2]) * mul + g * add + base
+                assert not seen[ids].any()
+                seen[ids] = True
+                full[ids] = rows[g].transpose(1, 0, 2)
+        assert seen.all(), "some global rows were never pushed"
+        if b_counters is not None:      # the re-score operand must be the same bank, laid out [G, E_loc, d, w]
+            chk = np.zeros_like(full)
+            for g in range(plan.G):
+                chk[g::plan.G] = b_counters[g].numpy()
+            assert (chk == full).all()
+        E_loc = plan.rows_per_shard
+        idx, s, cnt = np.zeros((E_loc, k), np.int64), np.zeros((E_loc, k)), np.zeros(E_loc, np.int32)
+        for l in range(E_loc):
+            r = l * plan.G + plan.rank
+            i1, s1, c1 = orc.bank_cosine_topk(full, k, self.threshold if self.threshold else orc.NO_THRESHOLD,
+                                              True, r0=r, r1=r + 1, nthreads=1)
+            idx[l], s[l], cnt[l] = i1[0], s1[0], c1[0]
+        return torch.from_numpy(idx), torch.from_numpy(s), torch.from_numpy(cnt)
+
+    def abort(self):
         pass
 
 
@@ -60,29 +102,29 @@ def _events(seed, n, N, users):
     return row, rng.integers(1, users, n).astype(np.int64), (rng.integers(1, 11, n) * 0.5).astype(np.float32)
 
 
-def _worker(rank, world, port, N, k, d, w, out_q):
+def _worker(rank, world, port, N, k, d, w, out_q, chunk_rows=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     row, user, pref = _events(5, 4000, N, 200)
     mine = slice(rank, None, world)               # each rank holds an arbitrary slice of the stream
     idx, s, cnt = sim.sharded_item_similarity(row[mine], user[mine], pref[mine], N, k=k, width=w, depth=d,
-                                              precision="rescored", backend=OracleShardBackend())
+                                              precision="rescored", backend=OracleShardBackend(),
+                                              chunk_rows=chunk_rows)
     if rank == 0:
         out_q.put((idx, s, cnt))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(300)
-def test_sharded_driver_world2_gloo():
-    N, k, d, w, world = 45, 6, 3, 64, 2
+def _run_world2(N, k, d, w, chunk_rows):
+    world = 2
     with socket.socket() as sck:
         sck.bind(("127.0.0.1", 0))
         port = sck.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, N, k, d, w, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, k, d, w, q, chunk_rows)) for r in range(world)]
     for p in procs:
         p.start()
     idx, s, cnt = q.get(timeout=240)
@@ -96,3 +138,15 @@ def test_sharded_driver_world2_gloo():
     oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
     assert (cnt == ocnt).all() and (idx == oidx).all()
     assert s.tobytes() == osim.tobytes()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_driver_world2_gloo():
+    _run_world2(45, 6, 3, 64, 0)
+
+
+@pytest.mark.timeout(300)
+def test_pipelined_driver_world2_gloo():
+    """chunked all-gather + incremental job: two row chunks per shard ([0,256) and [256,301)), odd N so the
+    last shard is one row short"""
+    _run_world2(601, 6, 2, 32, 256)
