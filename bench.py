@@ -37,6 +37,7 @@ ITEMS, USERS, ZIPF_S = 10_000_000, 1_000_000, 1.1
 ALGO_BYTES_PER_EVENT = 20 + DEPTH * 16   # 20 B event + d x (8 B read + 8 B write)
 C3_USERS, C3_ITEMS, C3_EVENTS, C3_WIDTH, C3_DEPTH, C3_K = 138_493, 26_744, 20_000_000, 4096, 4, 50
 C3_SEED = 20240003
+C3_CHUNK_ROWS = 1024       # rows per shard and all-gather chunk of the pipelined multi-GPU cosine step
 METRIC = "sketch_updates_per_sec"
 UNIT = "events/s"
 
@@ -487,6 +488,31 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # pipelined variant (N > 1): chunked all-gather on a side stream overlapped with K3 pushes
+    piped_ms, piped_equal = None, None
+    if world > 1:
+        be = sim.GpuShardBackend(ctx)
+        be.bank = bank
+
+        def step_piped():
+            N.check(N.lib().mb200_bank_normalize(bank.handle, N.DTYPE_F16, C.c_void_p(a_rows.data_ptr()),
+                                                 C.c_void_p(a_valid.data_ptr())), ctx.handle)
+            return sim.pipelined_cosine(be, plan, a_rows, a_valid, C3_K, None, "f16", "tensor", None,
+                                        C3_CHUNK_ROWS, None)
+
+        for _ in range(warmup):
+            step_piped()
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            pidx, ps, pcnt = step_piped()
+        e1.record(stream)
+        barrier()
+        piped_ms = e0.elapsed_time(e1) / steps
+        t = torch.tensor([piped_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        piped_ms = float(t.item())
+        piped_equal = bool(torch.equal(pidx, idx) and torch.equal(ps, s) and torch.equal(pcnt, cnt))
     # exact (re-scored) variant, timed once
     b_cnt = a_cnt
     if world > 1:
@@ -574,8 +600,10 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                     max_rel = max(max_rel, abs(v - o[c]) / abs(o[c]))
             tot += int(oc[l])
         out = {
-            "metric": "item_pair_cosine_sims_per_sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
-            "ms_per_step": ms, "steps": steps, "warmup": warmup, "n_gpus": world, "scaling": "strong",
+            "metric": "item_pair_cosine_sims_per_sec", "value": pairs / (min(ms, piped_ms or ms) * 1e-3), "unit": "pairs/s",
+            "ms_per_step": min(ms, piped_ms or ms), "ms_per_step_allgather_then_k3": ms,
+            "ms_per_step_pipelined": piped_ms, "pipelined_equals_one_shot": piped_equal,
+            "pipelined_chunk_rows": C3_CHUNK_ROWS if world > 1 else None, "steps": steps, "warmup": warmup, "n_gpus": world, "scaling": "strong",
             "dtype": "f16 rows (x/||x|| * 2^12), f32 accumulate in TMEM; re-score in exact int64/f64",
             "config": {"workload": "configs[2]: MovieLens-20M-shaped synthetic (138493 users x 26744 items, 2e7 "
                                    "Zipf(1.1) events), sketch d=4 x W=4096, cosine top-50 per item",

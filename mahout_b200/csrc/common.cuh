@@ -50,6 +50,8 @@ struct mb200_ctx {
   // grow-only device workspaces of the cosine stage (slot i = i-th request of a call); cudaMalloc /
   // cudaFree of a few hundred MB per call would otherwise cost more than the kernels
   std::vector<std::pair<void*, size_t>> ws;
+  // grow-only device staging of host-memory arguments (see io_slot in sketch.cu)
+  std::pair<void*, size_t> io[3] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
   int64_t last_fallback_rows = 0;
   struct mb200_cosine_job* active_job = nullptr;  // the cosine stage's workspaces serve one job at a time
 };

@@ -124,6 +124,8 @@ int mb200_destroy(mb200_ctx* ctx) {
   for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
   for (auto& w : ctx->ws)
     if (w.first) cudaFree(w.first);
+  for (auto& w : ctx->io)
+    if (w.first) cudaFree(w.first);
   for (int i = 0; i < 2; i++) {
     if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     cudaEventDestroy(ctx->stage_free[i]);
@@ -145,9 +147,15 @@ int mb200_release_workspace(mb200_ctx* ctx) {
   std::lock_guard<std::mutex> g(ctx->mu);
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->active_job)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_release_workspace: a cosine job is active on this context");
   for (auto& w : ctx->ws)
     if (w.first) cudaFree(w.first);
   ctx->ws.clear();
+  for (auto& w : ctx->io) {
+    if (w.first) cudaFree(w.first);
+    w = {nullptr, 0};
+  }
   return MB200_OK;
 }
 

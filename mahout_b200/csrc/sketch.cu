@@ -505,32 +505,50 @@ static int bank_update_impl(mb200_bank* bk, const int64_t* entity, const int64_t
   return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_update: mem must be MB200_MEM_HOST or MB200_MEM_DEVICE");
 }
 
+// Device staging of host-memory arguments: grow-only slots on the context (slot = position of the
+// argument in the call).  cudaMalloc / cudaFree per call were measured at 1 ms .. 1 s each on a
+// process holding tens of GB (they synchronise the device), which dominated mb200_bank_read.
+static int io_slot(mb200_ctx* ctx, int slot, size_t bytes, void** out) {
+  auto& s = ctx->io[slot];
+  if (s.second < bytes || !s.first) {
+    if (s.first) MB_CUDA(ctx, cudaFree(s.first));
+    s.first = nullptr;
+    s.second = 0;
+    const size_t want = bytes ? bytes : 1;
+    cudaError_t e = cudaMalloc(&s.first, want);
+    if (e != cudaSuccess) {
+      s.first = nullptr;
+      return mb200_fail(ctx, MB200_ERR_OOM, "cannot allocate %zu bytes of staging memory: %s", want, cudaGetErrorString(e));
+    }
+    s.second = want;
+  }
+  *out = s.first;
+  return MB200_OK;
+}
+
 // copy `bytes` of results to the caller (host) or leave them where the kernel wrote them
 struct OutBuf {
   mb200_ctx* ctx;
   void* user;
   void* dev = nullptr;
   size_t bytes;
-  int mem;
-  bool owned = false;
-  OutBuf(mb200_ctx* c, void* u, size_t b, int m) : ctx(c), user(u), bytes(b), mem(m) {}
+  int mem, slot;
+  bool staged = false;
+  OutBuf(mb200_ctx* c, void* u, size_t b, int m, int s) : ctx(c), user(u), bytes(b), mem(m), slot(s) {}
   int acquire() {
     if (mem == MB200_MEM_DEVICE) {
       dev = user;
       return MB200_OK;
     }
-    MB_CUDA(ctx, cudaMalloc(&dev, bytes ? bytes : 1));
-    owned = true;
+    MB_CHECK(io_slot(ctx, slot, bytes, &dev));
+    staged = true;
     return MB200_OK;
   }
   int release() {
-    if (!owned) return MB200_OK;
+    if (!staged) return MB200_OK;
     MB_CUDA(ctx, cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MB200_OK;
-  }
-  ~OutBuf() {
-    if (owned && dev) cudaFree(dev);
   }
 };
 
@@ -539,25 +557,24 @@ struct InBuf {
   const void* user;
   void* dev = nullptr;
   size_t bytes;
-  int mem;
-  bool owned = false;
-  InBuf(mb200_ctx* c, const void* u, size_t b, int m) : ctx(c), user(u), bytes(b), mem(m) {}
+  int mem, slot;
+  bool staged = false;
+  InBuf(mb200_ctx* c, const void* u, size_t b, int m, int s) : ctx(c), user(u), bytes(b), mem(m), slot(s) {}
   int acquire() {
     if (!user) return MB200_OK;
     if (mem == MB200_MEM_DEVICE) {
       dev = const_cast<void*>(user);
       return MB200_OK;
     }
-    MB_CUDA(ctx, cudaMalloc(&dev, bytes ? bytes : 1));
-    owned = true;
+    MB_CHECK(io_slot(ctx, slot, bytes, &dev));
+    staged = true;
     MB_CUDA(ctx, cudaMemcpyAsync(dev, user, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return MB200_OK;
   }
   ~InBuf() {
-    if (owned && dev) {
-      cudaStreamSynchronize(ctx->stream);
-      cudaFree(dev);
-    }
+    // the caller's buffer is only borrowed for the call (pageable copies are already staged by the
+    // runtime when cudaMemcpyAsync returns; pinned ones are read asynchronously)
+    if (staged) cudaStreamSynchronize(ctx->stream);
   }
 };
 
@@ -571,8 +588,8 @@ int mb200_hash_keys(mb200_ctx* ctx, int64_t a, int64_t b, int32_t w, const int64
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_hash_keys: bad arguments (w=%d n=%lld)", w, (long long)n);
   if (n == 0) return MB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
-  InBuf in(ctx, keys, (size_t)n * 8, mem);
-  OutBuf ob(ctx, out, (size_t)n * 4, mem);
+  InBuf in(ctx, keys, (size_t)n * 8, mem, 0);
+  OutBuf ob(ctx, out, (size_t)n * 4, mem, 2);
   MB_CHECK(in.acquire());
   MB_CHECK(ob.acquire());
   uint32_t wmask = (w > 1 && (w & (w - 1)) == 0) ? (uint32_t)(w - 1) : 0u;
@@ -691,7 +708,7 @@ int mb200_bank_read(mb200_bank* bk, int64_t e0, int64_t e1, double* out, int mem
   for (int64_t e = e0; e < e1; e += step) {
     int64_t m = (e1 - e) < step ? (e1 - e) : step;
     int64_t cells = m * cells_per;
-    OutBuf ob(ctx, out + (e - e0) * cells_per, (size_t)cells * 8, mem);
+    OutBuf ob(ctx, out + (e - e0) * cells_per, (size_t)cells * 8, mem, 2);
     MB_CHECK(ob.acquire());
     long long want = ceil_div64(cells, 256);
     int grid = (int)(want < (long long)ctx->num_sms * 32 ? want : (long long)ctx->num_sms * 32);
@@ -712,8 +729,8 @@ int mb200_bank_query(mb200_bank* bk, const int64_t* entity, const int64_t* key, 
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_query: bad arguments");
   if (n == 0) return MB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
-  InBuf ie(ctx, entity, (size_t)n * 8, mem), ik(ctx, key, (size_t)n * 8, mem);
-  OutBuf ob(ctx, out, (size_t)n * 8, mem);
+  InBuf ie(ctx, entity, (size_t)n * 8, mem, 0), ik(ctx, key, (size_t)n * 8, mem, 1);
+  OutBuf ob(ctx, out, (size_t)n * 8, mem, 2);
   MB_CHECK(ie.acquire());
   MB_CHECK(ik.acquire());
   MB_CHECK(ob.acquire());
@@ -741,8 +758,8 @@ int mb200_bank_cross_cosine(mb200_bank* bka, const int64_t* ea, mb200_bank* bkb,
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_cross_cosine: bad arguments");
   if (n == 0) return MB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
-  InBuf ia(ctx, ea, (size_t)n * 8, mem), ib(ctx, eb, (size_t)n * 8, mem);
-  OutBuf ob(ctx, out, (size_t)n * 8, mem);
+  InBuf ia(ctx, ea, (size_t)n * 8, mem, 0), ib(ctx, eb, (size_t)n * 8, mem, 1);
+  OutBuf ob(ctx, out, (size_t)n * 8, mem, 2);
   MB_CHECK(ia.acquire());
   MB_CHECK(ib.acquire());
   MB_CHECK(ob.acquire());
