@@ -165,6 +165,7 @@ class GpuShardBackend:
 
     def __init__(self, ctx=None):
         self.ctx = ctx or sk.default_context()
+        self.device = f"cuda:{self.ctx.device}"
 
     def build(self, plan, local_row, key, inc, width, depth, seed, frac_bits):
         self.bank = sk.SketchBank(plan.rows_per_shard, width, depth, seed, frac_bits, self.ctx)
@@ -203,6 +204,34 @@ def _all_gather(t, world, group):
     flat = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(flat, t, group=group)
     return flat.view((world,) + tuple(t.shape))
+
+
+def route_events(plan, row, user, pref, group=None):
+    """The exchange step of a sharded ingest: every rank holds an arbitrary slice of the
+    event stream; events travel to the owner of their item (owner = row % G) with one all-to-all of the
+    20-byte events -- NCCL over NVLink for CUDA tensors, gloo for CPU tensors.  Returns this rank's
+    (local_row, user, pref) as torch tensors on the inputs' device; order within a source is kept."""
+    import torch
+    import torch.distributed as dist
+    G = plan.G
+    row = torch.as_tensor(row)
+    dev = row.device
+    user, pref = torch.as_tensor(user).to(dev), torch.as_tensor(pref).to(dev)
+    if G == 1:
+        return row // 1, user, pref
+    owner = row % G
+    order = torch.sort(owner, stable=True).indices
+    send_counts = torch.bincount(owner, minlength=G)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    out = []
+    for t in (row, user, pref):
+        src = t[order].contiguous()
+        dst = torch.empty(sum(rc), dtype=t.dtype, device=dev)
+        dist.all_to_all_single(dst, src, rc, sc, group=group)
+        out.append(dst)
+    return out[0] // G, out[1], out[2]
 
 
 def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precision, group=None,
@@ -308,16 +337,19 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     plan = ShardPlan(num_items, world, rank)
     backend = backend or GpuShardBackend()
-    row, user, pref = np.asarray(row, np.int64), np.asarray(user, np.int64), np.asarray(pref, np.float32)
     if world > 1:
-        # route events to the owner of their item: an all-gather of the (20 B) events followed by a
-        # local filter (a dedicated all-to-all only pays off once ingest, not compute, is the limit)
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (row, user, pref), group=group)
-        row = np.concatenate([g[0] for g in gathered])
-        user = np.concatenate([g[1] for g in gathered])
-        pref = np.concatenate([g[2] for g in gathered])
-    lrow, luser, lpref = plan.my_events(row, user, pref)
+        # route events to the owner of their item: one all-to-all of the 20-byte events, on the GPUs
+        # (NCCL) when the backend computes there
+        dev = getattr(backend, "device", None)
+        t = [torch.as_tensor(np.asarray(x, dt)) for x, dt in ((row, np.int64), (user, np.int64), (pref, np.float32))]
+        if dev is not None:
+            t = [x.to(dev) for x in t]
+        lrow, luser, lpref = route_events(plan, *t, group=group)
+        if dev is None:
+            lrow, luser, lpref = lrow.numpy(), luser.numpy(), lpref.numpy()
+    else:
+        row, user, pref = np.asarray(row, np.int64), np.asarray(user, np.int64), np.asarray(pref, np.float32)
+        lrow, luser, lpref = plan.my_events(row, user, pref)
     backend.build(plan, lrow, luser, lpref, width, depth, seed, frac_bits)
     a_rows, a_valid = backend.normalized(dtype)
     a_cnt = backend.counters() if precision == "rescored" else None
