@@ -145,6 +145,43 @@ int mb200_bank_pair_cosine(mb200_bank* bank, const int64_t* ea, const int64_t* e
 int mb200_bank_cross_cosine(mb200_bank* bank_a, const int64_t* ea, mb200_bank* bank_b,
                             const int64_t* eb, int64_t n, double* out, int mem);
 
+/* ---- ingest: text preference data -> device-resident events -> preference matrix ------------ */
+/* The step in front of the sketch path (PreparePreferenceMatrixJob.java:54-114), so that the events
+ * never leave the GPU between the input file and K1.
+ *
+ * mb200_events_parse = ToEntityPrefsMapper.map (ToEntityPrefsMapper.java:56-76) over a whole text
+ * buffer: lines `userID,itemID[,pref[,...]]` split on tab or comma; Long.parseLong / Float.parseFloat
+ * (+ rating_shift); pref = 1.0 when absent or boolean_data; transpose swaps the first two columns.
+ * Blank lines are skipped; a malformed line fails the call with MB200_ERR_BAD_ARG and a message
+ * naming the Java exception and the byte offset.  Events keep the order of the lines. */
+typedef struct mb200_events mb200_events;
+typedef struct mb200_prefs mb200_prefs;
+int mb200_events_parse(mb200_ctx* ctx, const char* text, int64_t bytes, int mem, int boolean_data,
+                       float rating_shift, int transpose, mb200_events** out);
+/* the same object from binary columns */
+int mb200_events_create(mb200_ctx* ctx, const int64_t* user, const int64_t* item, const float* pref,
+                        int64_t n, int mem, mb200_events** out);
+int mb200_events_count(mb200_events* ev, int64_t* n);
+/* DEVICE pointers of the columns, valid until mb200_events_destroy */
+int mb200_events_columns(mb200_events* ev, int64_t** user, int64_t** item, float** pref);
+/* copies to HOST arrays of mb200_events_count elements (NULL = skip the column) */
+int mb200_events_read(mb200_events* ev, int64_t* user, int64_t* item, float* pref);
+int mb200_events_destroy(mb200_events* ev);
+/* TasteHadoopUtils.idToIndex (TasteHadoopUtils.java:56-58) for n ids */
+int mb200_id_to_index(mb200_ctx* ctx, const int64_t* ids, int64_t n, int32_t* out, int mem);
+/* The bookkeeping of the preparation phase: item index = idToIndex(itemID); per index the minimum
+ * itemID over ALL lines (ItemIDIndexReducer.java:31-46); the last preference of a (user, index) pair
+ * wins (userVector.set, ToUserVectorsReducer.java:66-82); users with fewer than min_prefs_per_user
+ * distinct indexes are dropped.  The result holds the surviving events in input order with their
+ * dense row number (rank of the index among the distinct indexes, ascending) -- ready for
+ * mb200_bank_update(entity = row, key = user, inc = pref, MB200_MEM_DEVICE). */
+int mb200_events_prepare(mb200_events* ev, int32_t min_prefs_per_user, mb200_prefs** out);
+int mb200_prefs_info(mb200_prefs* p, int64_t* n, int64_t* num_items, int64_t* num_users);
+int mb200_prefs_columns(mb200_prefs* p, int64_t** row, int64_t** user, float** pref); /* DEVICE */
+/* HOST tables of num_items entries: row -> itemID written to the output, row -> index */
+int mb200_prefs_tables(mb200_prefs* p, int64_t* item_id, int32_t* index_values);
+int mb200_prefs_destroy(mb200_prefs* p);
+
 /* ---- all-pairs cosine + per-row top-k ----------------------------------------------------- */
 /* Single-GPU convenience: normalise the bank's rows (K2), compute every pair's sketch cosine
  * -- min over depth of the per-row cosines, DoubleCountMinSketch.cosine -- on the tensor cores

@@ -97,6 +97,18 @@ _PROTOS = {
     "mb200_valid_words": (i64, [i64]),
     "mb200_bank_normalize": (C.c_int, [vp, C.c_int, vp, vp]),
     "mb200_cosine_topk": (C.c_int, [vp, C.POINTER(CosineArgs)]),
+    "mb200_events_parse": (C.c_int, [vp, vp, i64, C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(vp)]),
+    "mb200_events_create": (C.c_int, [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp)]),
+    "mb200_events_count": (C.c_int, [vp, C.POINTER(i64)]),
+    "mb200_events_columns": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "mb200_events_read": (C.c_int, [vp, vp, vp, vp]),
+    "mb200_events_destroy": (C.c_int, [vp]),
+    "mb200_id_to_index": (C.c_int, [vp, vp, i64, vp, C.c_int]),
+    "mb200_events_prepare": (C.c_int, [vp, i32, C.POINTER(vp)]),
+    "mb200_prefs_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+    "mb200_prefs_columns": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "mb200_prefs_tables": (C.c_int, [vp, vp, vp]),
+    "mb200_prefs_destroy": (C.c_int, [vp]),
     "mb200_cosine_begin": (C.c_int, [vp, C.POINTER(CosineArgs), C.POINTER(vp)]),
     "mb200_cosine_push": (C.c_int, [vp, C.POINTER(CosinePiece)]),
     "mb200_cosine_finish": (C.c_int, [vp, C.POINTER(CosineArgs)]),

@@ -17,6 +17,7 @@ from __future__ import annotations
 import argparse
 import sys
 
+from . import ingest
 from . import similarity as sim
 
 MEASURES = ("SIMILARITY_SKETCH_COSINE", "SIMILARITY_COSINE",
@@ -64,14 +65,22 @@ class ItemSimilarityJob:
             print("maxSimilarItemsPerItem must be greater then 0!", file=sys.stderr)
             return -1
         try:
-            with open(args.input) as f:
-                user, item, pref = sim.parse_prefs(f, boolean_data=_bool(args.booleanData))
-            prep = sim.PreferenceMatrix(user, item, pref, args.minPrefsPerUser)
-            idx, s, cnt = sim.item_similarity(
-                prep.row, prep.user, prep.pref, prep.num_items, k=args.maxSimilaritiesPerItem,
-                threshold=args.threshold, width=args.sketchWidth, depth=args.sketchDepth,
-                seed=args.sketchSeed, frac_bits=args.fracBits, precision=args.precision)
-            pairs = sim.most_similar_item_pairs(idx, s, cnt, prep.item_id)
+            # PreparePreferenceMatrixJob on the GPU: the text goes to the device once, the events stay there
+            with open(args.input, "rb") as f:
+                text = f.read()
+            events = ingest.Events.parse(text, boolean_data=_bool(args.booleanData))
+            prep = events.prepare(args.minPrefsPerUser)
+            events.close()
+            if prep.num_items == 0:
+                idx = s = cnt = ()
+                pairs = []
+            else:
+                idx, s, cnt = sim.item_similarity(
+                    prep.row, prep.user, prep.pref, prep.num_items, k=args.maxSimilaritiesPerItem,
+                    threshold=args.threshold, width=args.sketchWidth, depth=args.sketchDepth,
+                    seed=args.sketchSeed, frac_bits=args.fracBits, precision=args.precision)
+                pairs = sim.most_similar_item_pairs(idx, s, cnt, prep.item_id)
+            prep.close()
             with open(args.output, "w") as out:
                 for a, b, v in pairs:
                     out.write(f"{a}\t{b}\t{v!r}\n")

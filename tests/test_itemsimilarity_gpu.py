@@ -76,7 +76,8 @@ def test_movielens_100k_shaped_config(tmp_path):
     user = np.array([p[0] for p in pairs], np.int64)
     item = np.array([p[1] for p in pairs], np.int64)
     pref = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
-    prep = sim.PreferenceMatrix(user, item, pref)
+    from oracle import prep as oprep
+    prep = oprep.PreferenceMatrix(user, item, pref)
     idx, s, cnt = sim.item_similarity(prep.row, prep.user, prep.pref, prep.num_items, k=k, width=w, depth=d)
     a, b = orc.hash_params(42, d)
     ref = np.zeros((prep.num_items, d, w))
