@@ -69,7 +69,9 @@ int mb200_release_workspace(mb200_ctx* ctx);
 #define MB200_K_NORMALIZE 1  /* K2 row norms + split conversion  */
 #define MB200_K_COSINE 2     /* K3 tcgen05 S.S^T + top-k epilogue */
 #define MB200_K_RESCORE 3    /* K5 merge + FP64 re-score + sort  */
-#define MB200_K_COUNT 4
+#define MB200_K_PARSE 4     /* ingest: line count + scan + parse    */
+#define MB200_K_PREPARE 5   /* ingest: hash-table preparation + compaction */
+#define MB200_K_COUNT 6
 /* when profiling is on every launch of the kernels above is bracketed with CUDA events on the
  * launching stream; mb200_kernel_time syncs and returns the accumulated ms and launch count
  * since the last reset. */

@@ -17,7 +17,7 @@ ERR_NO_DEVICE, ERR_CM_DELTA, ERR_CM_EPSILON, ERR_UNSUPPORTED = -6, -7, -8, -9
 MEM_HOST, MEM_DEVICE = 0, 1
 DTYPE_F16, DTYPE_BF16 = 0, 1
 PRECISION_TENSOR, PRECISION_RESCORED = 0, 1
-K_UPDATE, K_NORMALIZE, K_COSINE, K_RESCORE = 0, 1, 2, 3
+K_UPDATE, K_NORMALIZE, K_COSINE, K_RESCORE, K_PARSE, K_PREPARE = 0, 1, 2, 3, 4, 5
 MAX_DEPTH = 16
 
 

@@ -40,8 +40,8 @@ struct mb200_ctx {
   bool profiling = false;
   std::vector<ProfSpan> spans;
   std::vector<cudaEvent_t> event_pool;
-  double prof_ms[MB200_K_COUNT] = {0, 0, 0, 0};
-  int64_t prof_n[MB200_K_COUNT] = {0, 0, 0, 0};
+  double prof_ms[MB200_K_COUNT] = {};
+  int64_t prof_n[MB200_K_COUNT] = {};
   // host-path staging (device) buffers, grown on demand
   void* stage[2] = {nullptr, nullptr};
   size_t stage_bytes = 0;

@@ -672,8 +672,11 @@ int mb200_events_parse(mb200_ctx* ctx, const char* text, int64_t bytes, int mem,
   EV_TRY(sc.get(&d_fix_len, (size_t)FIX_CAP));
   EV_TRY(sc.get(&d_fix_count, 1));
   const int grid = grid_for(ctx, num_tiles, 8);
-  k_count_lines<<<grid, PT, 0, ctx->stream>>>(d_text, bytes, num_tiles, d_counts);
-  k_scan<<<1, 1024, 0, ctx->stream>>>(d_counts, num_tiles, d_off, d_total);
+  {
+    ProfScope prof(ctx, MB200_K_PARSE);
+    k_count_lines<<<grid, PT, 0, ctx->stream>>>(d_text, bytes, num_tiles, d_counts);
+    k_scan<<<1, 1024, 0, ctx->stream>>>(d_counts, num_tiles, d_off, d_total);
+  }
   ctx->launches += 2;
   long long total = 0;
   EV_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -704,7 +707,10 @@ int mb200_events_parse(mb200_ctx* ctx, const char* text, int64_t bytes, int mem,
     a.fix_len = d_fix_len;
     a.fix_count = d_fix_count;
     a.fix_cap = FIX_CAP;
-    k_parse_lines<<<grid, PT, 0, ctx->stream>>>(a);
+    {
+      ProfScope prof(ctx, MB200_K_PARSE);
+      k_parse_lines<<<grid, PT, 0, ctx->stream>>>(a);
+    }
     ctx->launches++;
     EV_TRY(cudaGetLastError());
     unsigned long long err_pos = 0;
@@ -875,10 +881,13 @@ int mb200_events_prepare(mb200_events* ev, int32_t min_prefs_per_user, mb200_pre
   PM_TRY(cudaMemsetAsync(d_nusers, 0, 8, ctx->stream));
   PM_TRY(cudaMemsetAsync(d_nidx, 0, 8, ctx->stream));
   const int grid = grid_for(ctx, ceil_div64(n, 256), 16);
-  k_prep_insert<<<grid, 256, 0, ctx->stream>>>(a);
-  k_prep_mark<<<grid, 256, 0, ctx->stream>>>(a);
-  k_prep_flags<<<grid, 256, 0, ctx->stream>>>(a);
-  k_count_users<<<grid_for(ctx, (long long)((slots + 1 + 255) / 256), 16), 256, 0, ctx->stream>>>(a.ucount, slots + 1, min_prefs_per_user, d_nusers);
+  {
+    ProfScope prof(ctx, MB200_K_PREPARE);
+    k_prep_insert<<<grid, 256, 0, ctx->stream>>>(a);
+    k_prep_mark<<<grid, 256, 0, ctx->stream>>>(a);
+    k_prep_flags<<<grid, 256, 0, ctx->stream>>>(a);
+    k_count_users<<<grid_for(ctx, (long long)((slots + 1 + 255) / 256), 16), 256, 0, ctx->stream>>>(a.ucount, slots + 1, min_prefs_per_user, d_nusers);
+  }
   ctx->launches += 4;
   PM_TRY(cudaGetLastError());
   // distinct indexes: collect, sort on the host (a few million 12-byte entries at most), send back
@@ -920,7 +929,10 @@ int mb200_events_prepare(mb200_events* ev, int32_t min_prefs_per_user, mb200_pre
     PM_TRY(cudaMalloc(&pm->row, (size_t)total * 8));
     PM_TRY(cudaMalloc(&pm->user, (size_t)total * 8));
     PM_TRY(cudaMalloc(&pm->pref, (size_t)total * 4));
-    k_compact<<<cgrid, CT, 0, ctx->stream>>>(a, num_tiles, d_off, ev->pref, d_sorted, (long long)nidx, pm->row, pm->user, pm->pref);
+    {
+      ProfScope prof(ctx, MB200_K_PREPARE);
+      k_compact<<<cgrid, CT, 0, ctx->stream>>>(a, num_tiles, d_off, ev->pref, d_sorted, (long long)nidx, pm->row, pm->user, pm->pref);
+    }
     ctx->launches++;
     PM_TRY(cudaGetLastError());
   }
