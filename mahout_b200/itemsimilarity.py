@@ -1,7 +1,7 @@
 """`mahout itemsimilarity` with the GPU sketch-cosine measure -- the job-level drop-in.
 
     python -m mahout_b200.itemsimilarity --input prefs.csv --output out.tsv \
-        --similarityClassname SIMILARITY_SKETCH_COSINE --maxSimilaritiesPerItem 100 \
+        --similarityClassname SIMILARITY_COSINE | SIMILARITY_SKETCH_COSINE --maxSimilaritiesPerItem 100 \
         [--minPrefsPerUser 1] [--booleanData true] [--threshold 0.1] \
         [--sketchWidth 4096] [--sketchDepth 4] [--sketchSeed 42] [--precision rescored|tensor]
 
@@ -9,8 +9,10 @@ Same flags, input format (`userID,itemID[,pref]`, split on tab or comma) and out
 (`itemA<TAB>itemB<TAB>similarity`, itemA < itemB, ordered by (itemA, itemB)) as the reference's
 ItemSimilarityJob (cf/taste/hadoop/similarity/item/ItemSimilarityJob.java:97-232); phase 1
 (RowSimilarityJob) is replaced by the native call sequence.  Returns 0 on success, -1 on bad
-arguments or failure, like AbstractJob.  `--maxPrefs` is accepted for compatibility: the sketch
-bounds the work per item by its width, so no down-sampling takes place.
+arguments or failure, like AbstractJob.  SIMILARITY_COSINE is the reference's exact cosine (every
+user owns a counter column); SIMILARITY_SKETCH_COSINE the count-min sketch measure of the fork.
+`--maxPrefs` is accepted for compatibility: no down-sampling takes place (the dense tensor-core
+contraction does not need it), i.e. the job behaves like the reference with --maxPrefs >= every count.
 """
 from __future__ import annotations
 
@@ -20,9 +22,13 @@ import sys
 from . import ingest
 from . import similarity as sim
 
-MEASURES = ("SIMILARITY_SKETCH_COSINE", "SIMILARITY_COSINE",
-            "org.apache.mahout.math.hadoop.similarity.cooccurrence.measures.CosineSimilarity",
-            "org.apache.mahout.math.hadoop.similarity.cooccurrence.measures.NativeSketchCosineSimilarity")
+# -s SIMILARITY_COSINE (or the measure's class name) is the reference's exact cosine; the sketch measure
+# of the fork is selected by its own names
+EXACT_MEASURES = ("SIMILARITY_COSINE",
+                  "org.apache.mahout.math.hadoop.similarity.cooccurrence.measures.CosineSimilarity")
+SKETCH_MEASURES = ("SIMILARITY_SKETCH_COSINE",
+                   "org.apache.mahout.math.hadoop.similarity.cooccurrence.measures.NativeSketchCosineSimilarity")
+MEASURES = EXACT_MEASURES + SKETCH_MEASURES
 
 
 def _bool(s: str) -> bool:
@@ -75,10 +81,15 @@ class ItemSimilarityJob:
                 idx = s = cnt = ()
                 pairs = []
             else:
-                idx, s, cnt = sim.item_similarity(
-                    prep.row, prep.user, prep.pref, prep.num_items, k=args.maxSimilaritiesPerItem,
-                    threshold=args.threshold, width=args.sketchWidth, depth=args.sketchDepth,
-                    seed=args.sketchSeed, frac_bits=args.fracBits, precision=args.precision)
+                if args.similarityClassname in EXACT_MEASURES:
+                    idx, s, cnt = sim.exact_item_similarity(
+                        prep.row, prep.user, prep.pref, prep.num_items, k=args.maxSimilaritiesPerItem,
+                        threshold=args.threshold, frac_bits=args.fracBits, precision=args.precision)
+                else:
+                    idx, s, cnt = sim.item_similarity(
+                        prep.row, prep.user, prep.pref, prep.num_items, k=args.maxSimilaritiesPerItem,
+                        threshold=args.threshold, width=args.sketchWidth, depth=args.sketchDepth,
+                        seed=args.sketchSeed, frac_bits=args.fracBits, precision=args.precision)
                 pairs = sim.most_similar_item_pairs(idx, s, cnt, prep.item_id)
             prep.close()
             with open(args.output, "w") as out:

@@ -63,6 +63,29 @@ def item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_SIMILA
         bank.close()
 
 
+def exact_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM,
+                          threshold: float | None = None, frac_bits: int = 1, dtype: str = "f16",
+                          precision: str = "rescored", ctx=None):
+    """RowSimilarityJob with CosineSimilarity, exactly (RowSimilarityJob.java:478-559; no sketch, no
+    --maxPrefs down-sampling): the users are renumbered 0..U-1 and every user owns one counter column
+    (depth 1, width U, identity hash), so K1 writes the item x user matrix, K3 computes all pairs on the
+    tensor cores and K5 re-scores the kept candidates in exact integer / FP64 arithmetic.
+    The events must be de-duplicated (one pref per (user, item): `Events.prepare`)."""
+    import torch
+    ctx = ctx or sk.default_context()
+    dev = f"cuda:{ctx.device}"
+    user_t = torch.as_tensor(user).to(dev)
+    users, col = torch.unique(user_t, return_inverse=True)            # plumbing: dense user numbers
+    width = max(int(users.numel()), 1)
+    bank = sk.SketchBank(num_items, width, 1, sk.IdentityHashBuilder(), frac_bits, ctx)
+    try:
+        bank.update(torch.as_tensor(row).to(dev), col, torch.as_tensor(pref).to(dev))
+        bank.check()
+        return bank.cosine_topk(k, threshold, True, dtype, precision)
+    finally:
+        bank.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # item-hash sharding (one process per GPU)
 # ------------------------------------------------------------------------------------------------

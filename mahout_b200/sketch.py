@@ -194,6 +194,18 @@ class HashFunction:
         return int(out[0]) if scalar else out
 
 
+class IdentityHashBuilder:
+    """a_i = 1, b_i = 0: h(key) = key mod w.  With keys renumbered 0..U-1 and w >= U every key owns its
+    column, so a depth-1 "sketch" holds the exact vector (RowSimilarityJob's exact cosine on K1-K5)."""
+    seed = None
+
+    def params(self, depth: int):
+        return np.ones(depth, np.int64), np.zeros(depth, np.int64)
+
+    def getHashFunction(self, iteration: int, size: int) -> "HashFunction":
+        return HashFunction(1, 0, int(size))
+
+
 def cm_dims(delta: float, epsilon: float):
     """(w, d) of AbstractCountMinSketch(delta, epsilon); raises CMException on the rejected ranges."""
     w, d = C.c_int32(), C.c_int32()
@@ -213,7 +225,7 @@ class SketchBank:
     def __init__(self, entities: int, width: int, depth: int, hfBuilder: HashFunctionBuilder | int = 42,
                  frac_bits: int = 1, ctx: Context | None = None):
         self.ctx = ctx or default_context()
-        if not isinstance(hfBuilder, HashFunctionBuilder):
+        if not isinstance(hfBuilder, (HashFunctionBuilder, IdentityHashBuilder)):
             hfBuilder = HashFunctionBuilder(int(hfBuilder))
         self.hfBuilder = hfBuilder
         if not (0 < int(depth) <= N.MAX_DEPTH):

@@ -12,13 +12,13 @@ import oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-def _run_job(tmp_path, lines, *extra):
+def _run_job(tmp_path, lines, *extra, measure="SIMILARITY_SKETCH_COSINE"):
     from mahout_b200.itemsimilarity import ItemSimilarityJob
     inp = tmp_path / "prefs.csv"
     inp.write_text("\n".join(lines) + "\n")
     out = tmp_path / "out.tsv"
     rc = ItemSimilarityJob().run(["--input", str(inp), "--output", str(out), "--similarityClassname",
-                                  "SIMILARITY_COSINE", *extra])
+                                  measure, *extra])
     assert rc == 0
     rows = []
     for ln in out.read_text().splitlines():
@@ -35,6 +35,46 @@ def test_complete_job_reference_golden(tmp_path):
     assert rows[0][:2] == (1, 3) and abs(rows[0][2] - 0.45) < 0.01
     assert rows[1][:2] == (2, 3) and abs(rows[1][2] - 0.89) < 0.01
     assert abs(rows[0][2] - 1 / np.sqrt(5)) < 1e-12 and abs(rows[1][2] - 2 / np.sqrt(5)) < 1e-12
+
+
+def test_complete_job_exact_measure_reference_golden(tmp_path):
+    """-s SIMILARITY_COSINE is the exact measure: the same golden without any sketch width to choose"""
+    rows = _run_job(tmp_path, ["2,1,1", "1,2,1", "3,4,1", "1,3,2", "2,3,1"], measure="SIMILARITY_COSINE")
+    assert len(rows) == 2
+    assert rows[0][:2] == (1, 3) and abs(rows[0][2] - 1 / np.sqrt(5)) < 1e-12
+    assert rows[1][:2] == (2, 3) and abs(rows[1][2] - 2 / np.sqrt(5)) < 1e-12
+
+
+def test_exact_measure_movielens_100k_shaped_equals_rowsimilarityjob_oracle():
+    """configs[0]: ItemSimilarityJob -s SIMILARITY_COSINE on 943 x 1682 / 100K prefs against the oracle's
+    restatement of RowSimilarityJob (normalise, dot, top-k).  The two formulas round differently
+    (AB / (|A| |B|) vs sum of normalised products): values within 1e-12, sets equal up to such ties."""
+    from mahout_b200 import similarity as sim
+    from oracle import prep as oprep
+    rng = np.random.Generator(np.random.PCG64(20240001))
+    U, I, n, k = 943, 1682, 100000, 100
+    user = rng.integers(1, U + 1, 2 * n)
+    item = np.minimum(rng.zipf(1.3, 2 * n), I)
+    pref = (rng.integers(1, 11, 2 * n) * 0.5).astype(np.float32)
+    prep = oprep.PreferenceMatrix(user, item, pref)
+    idx, s, cnt = sim.exact_item_similarity(prep.row, prep.user, prep.pref, prep.num_items, k=k)
+    order = np.lexsort((prep.user, prep.row))
+    rowptr = np.zeros(prep.num_items + 1, np.int64)
+    np.add.at(rowptr, prep.row + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    ucol = np.searchsorted(np.unique(prep.user), prep.user[order]).astype(np.int32)
+    eidx, esim, ecnt = orc.rowsim_cosine_topk(prep.num_items, U, rowptr, ucol, prep.pref[order], k)
+    assert (cnt == ecnt).all()
+    for r in range(prep.num_items):
+        c = cnt[r]
+        assert np.allclose(s[r, :c], esim[r, :c], rtol=1e-12, atol=0)
+        if (idx[r, :c] != eidx[r, :c]).any():
+            # only entries tied (to rounding) may swap or straddle the cut
+            kth = esim[r, c - 1]
+            for col in set(idx[r, :c].tolist()) ^ set(eidx[r, :c].tolist()):
+                # an item on one side of the cut only: its value must tie with the k-th to rounding
+                v = s[r, :c][idx[r, :c] == col] if col in idx[r, :c] else esim[r, :c][eidx[r, :c] == col]
+                assert abs(v[0] - kth) <= 1e-12 * kth
 
 
 def test_max_similarities_per_item_and_threshold(tmp_path):
