@@ -269,7 +269,35 @@ typedef struct mb200_cosine_piece {
   int32_t b_blocks;
   /* global index of row l of block g of this piece = l * b_id_mul + g * b_id_add + b_id_base */
   int64_t b_id_mul, b_id_add, b_id_base;
+  /* pull-gather (see mb200_gather_pull): K3 reads block g only once ready_flags[g] == ready_epoch,
+   * and sweeps the blocks starting with first_block.  NULL / 0 / 0 otherwise. */
+  const uint32_t* ready_flags;
+  uint32_t ready_epoch;
+  int32_t first_block;
 } mb200_cosine_piece;
+/* The all-gather fused into K3 (C1 + K3 of SURVEY.md 8e as one kernel's worth of time): every GPU keeps
+ * its normalised rows in a peer-accessible buffer; mb200_gather_pull queues, on the context's copy
+ * stream, one DMA per shard from the owner's memory over NVLink into the local staging operand
+ * [blocks][d][b_count][ld] (own block first, then ring order), each followed by a stream memory
+ * operation that publishes the block's arrival flag.  K3 is launched at once on the compute stream
+ * with the flags in its piece: its TMA producer waits for a block's flag before the first tile of
+ * that block, so the transfer of block g+1 hides behind the tensor-core sweep of block g and no SM
+ * is spent on communication.  The caller provides the cross-rank ordering: all ranks must have
+ * finished K2 before any pull starts, and must not overwrite their rows before every peer's K3 is
+ * done (two stream-ordered barriers per step, see similarity.fused_gather_cosine).
+ *   mb200_peer_alloc   cudaMalloc + a 64-byte IPC handle to send to the other ranks
+ *   mb200_peer_open    map a peer's buffer from its handle (once; mappings persist)
+ *   mb200_gather_wait  block until the queued pulls are complete */
+#define MB200_MAX_BLOCKS 64
+int mb200_peer_alloc(mb200_ctx* ctx, int64_t bytes, void** ptr, void* ipc_handle_64_bytes);
+int mb200_peer_open(mb200_ctx* ctx, const void* ipc_handle_64_bytes, void** ptr);
+int mb200_peer_close(mb200_ctx* ctx, void* ptr);
+int mb200_peer_free(mb200_ctx* ctx, void* ptr);
+int mb200_gather_pull(mb200_ctx* ctx, void* staging_rows, uint32_t* staging_valid,
+                      const void* const* peer_rows, const uint32_t* const* peer_valid, int32_t blocks,
+                      int32_t my_block, int64_t rows_bytes_per_block, int64_t valid_bytes_per_block,
+                      const uint32_t** ready_flags, uint32_t* epoch);
+int mb200_gather_wait(mb200_ctx* ctx);
 int mb200_cosine_begin(mb200_ctx* ctx, const mb200_cosine_args* args, mb200_cosine_job** job);
 int mb200_cosine_push(mb200_cosine_job* job, const mb200_cosine_piece* piece);
 int mb200_cosine_finish(mb200_cosine_job* job, const mb200_cosine_args* fin);

@@ -59,6 +59,7 @@ class CosinePiece(C.Structure):
     _fields_ = [
         ("b_rows", C.c_void_p), ("b_valid", C.c_void_p), ("b_count", C.c_int64), ("b_blocks", C.c_int32),
         ("b_id_mul", C.c_int64), ("b_id_add", C.c_int64), ("b_id_base", C.c_int64),
+        ("ready_flags", C.c_void_p), ("ready_epoch", C.c_uint32), ("first_block", C.c_int32),
     ]
 
 
@@ -109,6 +110,12 @@ _PROTOS = {
     "mb200_prefs_columns": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "mb200_prefs_tables": (C.c_int, [vp, vp, vp]),
     "mb200_prefs_destroy": (C.c_int, [vp]),
+    "mb200_peer_alloc": (C.c_int, [vp, i64, C.POINTER(vp), vp]),
+    "mb200_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "mb200_peer_close": (C.c_int, [vp, vp]),
+    "mb200_peer_free": (C.c_int, [vp, vp]),
+    "mb200_gather_pull": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i64, i64, C.POINTER(vp), C.POINTER(C.c_uint32)]),
+    "mb200_gather_wait": (C.c_int, [vp]),
     "mb200_cosine_begin": (C.c_int, [vp, C.POINTER(CosineArgs), C.POINTER(vp)]),
     "mb200_cosine_push": (C.c_int, [vp, C.POINTER(CosinePiece)]),
     "mb200_cosine_finish": (C.c_int, [vp, C.POINTER(CosineArgs)]),

@@ -52,6 +52,11 @@ struct mb200_ctx {
   std::vector<std::pair<void*, size_t>> ws;
   // grow-only device staging of host-memory arguments (see io_slot in sketch.cu)
   std::pair<void*, size_t> io[3] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
+  // pull-gather: per-block arrival flags written by the copy stream, read by K3 (+ 1 abort word)
+  uint32_t* gather_flags = nullptr;
+  uint32_t* gather_abort = nullptr;
+  uint32_t gather_epoch = 0;
+  cudaEvent_t gather_ev = nullptr;
   int64_t last_fallback_rows = 0;
   struct mb200_cosine_job* active_job = nullptr;  // the cosine stage's workspaces serve one job at a time
 };

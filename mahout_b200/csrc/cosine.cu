@@ -63,6 +63,13 @@ struct CosParams {
   float inv_scale2;
   uint32_t idesc;
   uint64_t policy_a, policy_b;  // L2 eviction priority of the A / B tile loads
+  // pull-gather mode: block g of B is only readable once ready[g] == epoch (written by the copy
+  // stream behind the DMA that brought the block from its owner); rot rotates the block order so
+  // that every GPU starts with the blocks that arrive first
+  const uint32_t* ready;
+  uint32_t epoch;
+  int32_t rot, num_blocks;
+  uint32_t* abort_flag;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -285,9 +292,29 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
         const int4 it = p.items[w];
         const int t0 = it.y, t1 = it.z;
+        int g_seen = -1;
         for (int t = t0; t < t1; t++) {
-          const int g = t / p.tiles_per_block;
-          const int l0 = (t - g * p.tiles_per_block) * BN;
+          const int gs = t / p.tiles_per_block;
+          const int l0 = (t - gs * p.tiles_per_block) * BN;
+          int g = gs + p.rot;
+          if (g >= p.num_blocks) g -= p.num_blocks;
+          if (p.ready != nullptr && g != g_seen) {
+            // the block is still in flight from its owner: wait for the copy stream's signal
+            const volatile uint32_t* flag = p.ready + g;
+            if (*flag != p.epoch) {
+              const long long t_wait = clock64();
+              while (*flag != p.epoch) {
+                __nanosleep(256);
+                if (clock64() - t_wait > 8000000000LL) {  // ~4 s: report instead of hanging the GPU
+                  atomicExch(p.abort_flag, 1u);
+                  break;
+                }
+              }
+            }
+            __threadfence_system();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            g_seen = g;
+          }
           for (int dep = 0; dep < p.depth; dep++) {
             for (int kb = 0; kb < p.kblocks; kb++) {
               mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
@@ -372,8 +399,10 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       bool published = false;
       uint32_t* my_row_thr = p.row_thr + (size_t)it.x * BM + row;
       for (int t = t0; t < t1; t++) {
-        const int g = t / p.tiles_per_block;
-        const int l0 = (t - g * p.tiles_per_block) * BN + half * HALF;
+        const int gs = t / p.tiles_per_block;
+        const int l0 = (t - gs * p.tiles_per_block) * BN + half * HALF;
+        int g = gs + p.rot;
+        if (g >= p.num_blocks) g -= p.num_blocks;
         {
           // lower bounds published by the other lists of this row (other half, other column chunks)
           const uint32_t gt = __ldcg(my_row_thr);
@@ -382,15 +411,22 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         for (int dep = 0; dep < p.depth; dep++, q++) {
           const uint32_t as = q % ACC_STAGES;
           const uint32_t aphase = (q / ACC_STAGES) & 1u;
-          // column validity of my 32-column chunks (uniform per warp), fetched ahead of the wait
+          // column validity of my 32-column chunks (uniform per warp), fetched ahead of the wait --
+          // except in pull-gather mode, where the words arrive with the block
           uint32_t cm[CHUNKS];
           const uint32_t* bv = p.b_valid + ((size_t)g * p.depth + dep) * p.b_vw + (l0 >> 5);
+          if (p.ready == nullptr) {
 #pragma unroll
-          for (int c = 0; c < CHUNKS; c++) cm[c] = __ldg(bv + c);
+            for (int c = 0; c < CHUNKS; c++) cm[c] = __ldg(bv + c);
+          }
           const bool my_valid = (rv >> dep) & 1u;
           const bool last = dep == p.depth - 1;
           mbar_wait(smem_u32(&bar_tfull[as]), aphase);
           fence_after_sync();
+          if (p.ready != nullptr) {
+#pragma unroll
+            for (int c = 0; c < CHUNKS; c++) cm[c] = __ldcv(bv + c);
+          }
           const uint32_t acc_addr = tmem_base + lane_addr + as * BN + half * HALF;
           const uint32_t min_addr = tmem_base + lane_addr + ACC_STAGES * BN + half * HALF;
           // Candidate selection over one 32-column chunk of final values (executed per thread = per row).
@@ -1353,6 +1389,8 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   const int64_t max_id = (pc->b_count - 1) * pc->b_id_mul + (pc->b_blocks - 1) * pc->b_id_add + pc->b_id_base;
   if (pc->b_id_mul <= 0 || pc->b_id_add < 0 || pc->b_id_base < 0 || max_id >= 0xFFFFFFFFLL)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: index mapping out of the 32-bit range");
+  if (pc->ready_flags && !ctx->gather_abort)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_push: ready_flags must come from mb200_gather_pull on this context");
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   const bool trace = getenv("MB200_TRACE") != nullptr;
   double t_last = now_ms();
@@ -1484,6 +1522,11 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   p.b_id_mul = (uint32_t)pc->b_id_mul;
   p.b_id_add = (uint32_t)pc->b_id_add;
   p.b_id_base = (uint32_t)pc->b_id_base;
+  p.num_blocks = pc->b_blocks;
+  p.ready = pc->ready_flags;
+  p.epoch = pc->ready_epoch;
+  p.rot = pc->ready_flags ? (int32_t)(((pc->first_block % pc->b_blocks) + pc->b_blocks) % pc->b_blocks) : 0;
+  p.abort_flag = ctx->gather_abort;
   p.exclude_self = a->exclude_self ? 1 : 0;
   // a list scans its columns in index order iff the blocks do not interleave
   p.nonstrict = (pc->b_blocks > 1 && pc->b_id_add < pc->b_count * pc->b_id_mul) ? 1 : 0;
@@ -1690,6 +1733,14 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
   TRACE("launch K5");
   MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // results are complete on return
   TRACE("sync");
+  if (ctx->gather_abort) {
+    uint32_t ab = 0;
+    MB_CUDA(ctx, cudaMemcpy(&ab, ctx->gather_abort, 4, cudaMemcpyDeviceToHost));
+    if (ab) {
+      cudaMemset(ctx->gather_abort, 0, 4);
+      return mb200_fail(ctx, MB200_ERR_CUDA, "mb200_cosine: a peer block never arrived (pull-gather timed out after ~4 s); results are invalid");
+    }
+  }
   return MB200_OK;
 }
 
@@ -1719,6 +1770,9 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t
   pc.b_id_mul = a->b_id_mul;
   pc.b_id_add = a->b_id_add;
   pc.b_id_base = 0;
+  pc.ready_flags = nullptr;
+  pc.ready_epoch = 0;
+  pc.first_block = 0;
   int rc = job_push_locked(j, &pc);
   if (rc == MB200_OK) rc = job_finish_locked(j, a);
   if (rc != MB200_OK) cudaStreamSynchronize(ctx->stream);
@@ -1808,6 +1862,114 @@ int mb200_cosine_finish(mb200_cosine_job* job, const mb200_cosine_args* fin) {
   if (rc != MB200_OK) cudaStreamSynchronize(ctx->stream);
   job_free(job);
   return rc;
+}
+
+// cuStreamWriteValue32 through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWriteValue32Fn get_write_value_fn(mb200_ctx* ctx) {
+  static StreamWriteValue32Fn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuStreamWriteValue32", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+    mb200_fail(ctx, MB200_ERR_CUDA, "cuStreamWriteValue32 is not available from the driver");
+    return nullptr;
+  }
+  fn = (StreamWriteValue32Fn)ptr;
+  return fn;
+}
+
+int mb200_peer_alloc(mb200_ctx* ctx, int64_t bytes, void** ptr, void* ipc_handle) {
+  if (!ctx || !ptr || !ipc_handle || bytes <= 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_peer_alloc: bad arguments");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  *ptr = nullptr;
+  cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+  if (e != cudaSuccess) return mb200_fail(ctx, MB200_ERR_OOM, "mb200_peer_alloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle, *ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return mb200_fail(ctx, MB200_ERR_CUDA, "mb200_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  return MB200_OK;
+}
+
+int mb200_peer_open(mb200_ctx* ctx, const void* ipc_handle, void** ptr) {
+  if (!ctx || !ptr || !ipc_handle) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_peer_open: bad arguments");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return mb200_fail(ctx, MB200_ERR_CUDA, "mb200_peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  return MB200_OK;
+}
+
+int mb200_peer_close(mb200_ctx* ctx, void* ptr) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_peer_close: ctx is NULL");
+  if (!ptr) return MB200_OK;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MB_CUDA(ctx, cudaIpcCloseMemHandle(ptr));
+  return MB200_OK;
+}
+
+int mb200_peer_free(mb200_ctx* ctx, void* ptr) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_peer_free: ctx is NULL");
+  if (!ptr) return MB200_OK;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MB_CUDA(ctx, cudaFree(ptr));
+  return MB200_OK;
+}
+
+int mb200_gather_pull(mb200_ctx* ctx, void* staging_rows, uint32_t* staging_valid, const void* const* peer_rows,
+                      const uint32_t* const* peer_valid, int32_t blocks, int32_t my_block, int64_t rows_bytes,
+                      int64_t valid_bytes, const uint32_t** ready_flags, uint32_t* epoch) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_gather_pull: ctx is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!staging_rows || !staging_valid || !peer_rows || !peer_valid || !ready_flags || !epoch || blocks <= 0 ||
+      blocks > MB200_MAX_BLOCKS || my_block < 0 || my_block >= blocks || rows_bytes <= 0 || valid_bytes <= 0)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_gather_pull: bad arguments (blocks=%d my_block=%d)", blocks, my_block);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  StreamWriteValue32Fn wv = get_write_value_fn(ctx);
+  if (!wv) return MB200_ERR_CUDA;
+  if (!ctx->gather_flags) {
+    MB_CUDA(ctx, cudaMalloc(&ctx->gather_flags, (MB200_MAX_BLOCKS + 1) * sizeof(uint32_t)));
+    MB_CUDA(ctx, cudaMemset(ctx->gather_flags, 0, (MB200_MAX_BLOCKS + 1) * sizeof(uint32_t)));
+    ctx->gather_abort = ctx->gather_flags + MB200_MAX_BLOCKS;
+    MB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->gather_ev, cudaEventDisableTiming));
+  }
+  const uint32_t ep = ++ctx->gather_epoch;
+  // the pulls start once everything queued so far on the compute stream is done (the caller's
+  // cross-rank barrier sits there), and run on the copy engines beside K3
+  MB_CUDA(ctx, cudaEventRecord(ctx->gather_ev, ctx->stream));
+  MB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gather_ev, 0));
+  for (int s = 0; s < blocks; s++) {
+    const int b = (my_block + s) % blocks;
+    if (!peer_rows[b] || !peer_valid[b]) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_gather_pull: peer pointer %d is NULL", b);
+    MB_CUDA(ctx, cudaMemcpyAsync((char*)staging_rows + (size_t)b * rows_bytes, peer_rows[b], (size_t)rows_bytes,
+                                 cudaMemcpyDeviceToDevice, ctx->copy_stream));
+    MB_CUDA(ctx, cudaMemcpyAsync((char*)staging_valid + (size_t)b * valid_bytes, peer_valid[b], (size_t)valid_bytes,
+                                 cudaMemcpyDeviceToDevice, ctx->copy_stream));
+    CUresult r = wv((CUstream)ctx->copy_stream, (CUdeviceptr)(uintptr_t)(ctx->gather_flags + b), ep, 0);
+    if (r != CUDA_SUCCESS) return mb200_fail(ctx, MB200_ERR_CUDA, "cuStreamWriteValue32 failed with CUresult %d", (int)r);
+  }
+  *ready_flags = ctx->gather_flags;
+  *epoch = ep;
+  return MB200_OK;
+}
+
+int mb200_gather_wait(mb200_ctx* ctx) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_gather_wait: ctx is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  return MB200_OK;
 }
 
 int mb200_cosine_abort(mb200_cosine_job* job) {

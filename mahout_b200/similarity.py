@@ -286,6 +286,109 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
             backend.ctx.set_stream(None)
 
 
+class PeerRows:
+    """This rank's normalised rows and validity words in peer-accessible device memory, the mapped
+    buffers of every other rank (CUDA IPC over NVLink) and the local staging operand of the fused
+    pull-gather (mb200_gather_pull).  Set up once per (shape, group); collective."""
+
+    def __init__(self, ctx, plan, depth: int, width: int, dtype: str = "f16", group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        from .ingest import _view
+        self.ctx, self.plan, self.group = ctx, plan, group
+        G, E_loc = plan.G, plan.rows_per_shard
+        ld = int(N.lib().mb200_row_ld(width))
+        vw = int(N.lib().mb200_valid_words(E_loc))
+        self.rows_bytes, self.valid_bytes = depth * E_loc * ld * 2, depth * vw * 4
+        dev = f"cuda:{ctx.device}"
+        self._own, handles = [], []
+        for nbytes in (self.rows_bytes, self.valid_bytes):
+            p, h = C.c_void_p(), (C.c_char * 64)()
+            N.check(N.lib().mb200_peer_alloc(ctx.handle, nbytes, C.byref(p), C.cast(h, C.c_void_p)), ctx.handle)
+            self._own.append(p)
+            handles.append(bytes(h))
+        tdt = torch.float16 if dtype == "f16" else torch.bfloat16
+        self.rows = _view(self._own[0].value, self.rows_bytes // 2, ctx.device, "<i2").view(tdt).view(depth, E_loc, ld)
+        self.valid = _view(self._own[1].value, self.valid_bytes // 4, ctx.device, "<i4").view(depth, vw)
+        mine = torch.frombuffer(bytearray(handles[0] + handles[1]), dtype=torch.uint8).to(dev)
+        allh = torch.empty(G * 128, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy().tobytes()
+        self._opened = []
+        self.peer_rows = (C.c_void_p * G)()
+        self.peer_valid = (C.c_void_p * G)()
+        for g in range(G):
+            if g == plan.rank:
+                self.peer_rows[g], self.peer_valid[g] = self._own[0].value, self._own[1].value
+                continue
+            for j, arr in enumerate((self.peer_rows, self.peer_valid)):
+                q = C.c_void_p()
+                hb = (C.c_char * 64).from_buffer_copy(allh[g * 128 + j * 64:g * 128 + (j + 1) * 64])
+                N.check(N.lib().mb200_peer_open(ctx.handle, C.cast(hb, C.c_void_p), C.byref(q)), ctx.handle)
+                self._opened.append(q)
+                arr[g] = q.value
+        self.staging_rows = torch.empty((G, depth, E_loc, ld), dtype=tdt, device=dev)
+        self.staging_valid = torch.empty((G, depth, vw), dtype=torch.int32, device=dev)
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def barrier(self):
+        """stream-ordered cross-rank barrier (a one-word all-reduce on the current stream)"""
+        import torch.distributed as dist
+        dist.all_reduce(self.token, group=self.group)
+
+    def pull(self):
+        """queue the DMA pulls of every shard + their arrival flags; returns (flags_ptr, epoch)"""
+        import ctypes as C
+        from . import _native as N
+        flags, epoch = C.c_void_p(), C.c_uint32()
+        N.check(N.lib().mb200_gather_pull(
+            self.ctx.handle, C.c_void_p(self.staging_rows.data_ptr()), C.c_void_p(self.staging_valid.data_ptr()),
+            C.cast(self.peer_rows, C.c_void_p), C.cast(self.peer_valid, C.c_void_p), self.plan.G, self.plan.rank,
+            self.rows_bytes, self.valid_bytes, C.byref(flags), C.byref(epoch)), self.ctx.handle)
+        return flags.value, epoch.value
+
+    def close(self):
+        from . import _native as N
+        import torch
+        if getattr(self, "_own", None) is None:
+            return
+        torch.cuda.synchronize(self.ctx.device)
+        self.barrier()                       # nobody is still reading my buffers
+        torch.cuda.synchronize(self.ctx.device)
+        self.rows = self.valid = None
+        for q in self._opened:
+            N.lib().mb200_peer_close(self.ctx.handle, q)
+        for p in self._own:
+            N.lib().mb200_peer_free(self.ctx.handle, p)
+        self._own = None
+
+
+def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype: str = "f16",
+                        precision: str = "tensor", a_counters=None, b_counters=None, out=None):
+    """C1 fused into K3: `peers.rows` / `peers.valid` hold this rank's normalised rows (K2 output).  One
+    stream-ordered barrier makes every rank's rows final, the copy engines then pull the shards over
+    NVLink while K3 -- launched immediately, once, over all blocks -- waits block by block on the arrival
+    flags; a second barrier keeps every rank's rows alive until all peers have read them.  The context's
+    stream must be the current torch stream (the NCCL barriers are ordered with K2 / K3 through it)."""
+    G = plan.G
+    peers.barrier()
+    ready = peers.pull()
+    job = backend.begin(plan, peers.rows, peers.valid, k, threshold, dtype, precision)
+    try:
+        job.push(peers.staging_rows, peers.staging_valid, id_mul=G, id_add=1, ready=ready, first_block=plan.rank)
+        if precision == "rescored":
+            res = job.finish(a_counters=a_counters, b_counters=b_counters, b_id=(G, 1), out=out)
+        else:
+            res = job.finish(out=out)
+    except BaseException:
+        job.abort()
+        raise
+    peers.barrier()
+    return res
+
+
 def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM,
                             threshold: float | None = None, width: int = 4096, depth: int = 4, seed: int = 42,
                             frac_bits: int = 1, dtype: str = "f16", precision: str = "tensor",

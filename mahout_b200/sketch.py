@@ -410,13 +410,18 @@ class CosineJob:
         N.check(N.lib().mb200_cosine_begin(ctx.handle, C.byref(args), C.byref(h)), ctx.handle)
         self._h = h
 
-    def push(self, b_rows, b_valid, id_mul: int = 1, id_add: int = 0, id_base: int = 0):
+    def push(self, b_rows, b_valid, id_mul: int = 1, id_add: int = 0, id_base: int = 0, ready=None,
+             first_block: int = 0):
         """b_rows [blocks, d, b_count, ld], b_valid [blocks, d, valid_words(b_count)];
-        global index of row l of block g = l * id_mul + g * id_add + id_base."""
+        global index of row l of block g = l * id_mul + g * id_add + id_base.
+        ready = (flags_ptr, epoch) from mb200_gather_pull: K3 waits for every block's arrival flag and
+        sweeps the blocks starting with first_block."""
         pc = N.CosinePiece()
         pc.b_rows, pc.b_valid = b_rows.data_ptr(), b_valid.data_ptr()
         pc.b_blocks, pc.b_count = int(b_rows.shape[0]), int(b_rows.shape[2])
         pc.b_id_mul, pc.b_id_add, pc.b_id_base = int(id_mul), int(id_add), int(id_base)
+        if ready is not None:
+            pc.ready_flags, pc.ready_epoch, pc.first_block = ready[0], int(ready[1]), int(first_block)
         self._keep += [b_rows, b_valid]
         N.check(N.lib().mb200_cosine_push(self._h, C.byref(pc)), self.ctx.handle)
 

@@ -161,6 +161,37 @@ def _nccl_worker(rank, world, port, q):
                                             k=20, width=1024, depth=4, precision=precision, chunk_rows=256)
         for x, y in zip(piped, res[precision]):
             assert x.tobytes() == y.tobytes(), f"pipelined {precision} result differs"
+    # the all-gather fused into K3 (DMA pulls over NVLink + arrival flags): same answer, three epochs
+    import ctypes as C
+    from mahout_b200 import _native as NV
+    from mahout_b200 import sketch as sk
+    ctx = sk.default_context()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    plan = sim.ShardPlan(N, world, rank)
+    be = sim.GpuShardBackend(ctx)
+    be.build(plan, *plan.my_events(row, user, pref), 1024, 4, 42, 1)
+    peers = sim.PeerRows(ctx, plan, 4, 1024)
+    fused_ok = True
+    for precision in ("tensor", "rescored"):
+        want = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N, k=20, width=1024,
+                                           depth=4, precision=precision, gather_result=False)
+        for rep in range(3):
+            NV.check(NV.lib().mb200_bank_normalize(be.bank.handle, NV.DTYPE_F16, C.c_void_p(peers.rows.data_ptr()),
+                                                   C.c_void_p(peers.valid.data_ptr())), ctx.handle)
+            kw = {}
+            if precision == "rescored":
+                a_cnt = be.counters()
+                kw = dict(a_counters=a_cnt, b_counters=sim._all_gather(a_cnt, world, None))
+            got = sim.fused_gather_cosine(be, plan, peers, 20, precision=precision, **kw)
+            fused_ok &= all(torch.equal(x.cpu(), torch.as_tensor(y).cpu()) for x, y in zip(got, want))
+    peers.close()
+    be.close()
+    res["fused_ok"] = bool(fused_ok)
+    ok = torch.tensor([int(fused_ok)], device=f"cuda:{rank}")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    res["fused_ok"] = bool(ok.item())
     if rank == 0:
         q.put((row, user, pref, res))
     dist.barrier()
@@ -190,6 +221,7 @@ def test_sharded_two_gpus_nccl():
     oidx, osim, ocnt = orc.bank_cosine_topk(ref, 20)
     idx, s, cnt = res["rescored"]
     assert (cnt == ocnt).all() and (idx == oidx).all() and s.tobytes() == osim.tobytes()
+    assert res["fused_ok"], "fused pull-gather result differs from the all-gather + K3 result"
     idx, s, cnt = res["tensor"]
     assert (cnt == ocnt).all()
     dense = orc.bank_cosine_dense(ref)

@@ -4,14 +4,14 @@ import torch, torch.distributed as dist
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{rank}"))
-rt = C.CDLL("libcudart.so.12")
+rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
 class H(C.Structure): _fields_ = [("r", C.c_char * 64)]
 p = C.c_void_p()
 assert rt.cudaMalloc(C.byref(p), 1 << 26) == 0
 h = H()
 rc = rt.cudaIpcGetMemHandle(C.byref(h), p)
 print(rank, "cudaIpcGetMemHandle rc", rc, flush=True)
-mine = torch.frombuffer(bytearray(bytes(h.r)), dtype=torch.uint8).cuda()
+mine = torch.frombuffer(bytearray(C.string_at(C.byref(h), 64)), dtype=torch.uint8).cuda()
 allh = torch.empty(world * 64, dtype=torch.uint8, device="cuda")
 dist.all_gather_into_tensor(allh, mine)
 allh = allh.cpu().numpy().tobytes()
