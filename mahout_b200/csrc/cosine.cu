@@ -1277,15 +1277,15 @@ struct mb200_cosine_job {
   bool pending = false;                      // lists of the last push not merged yet
   MergeParams mp;                            // ... described here (context workspace memory)
   int pushes = 0;
+  size_t ws_state = 0;                       // workspace slots of row_thr, best, best_bound
   size_t ws_base = 0, ws_next = 0;           // workspace slots [ws_base, ws_next) belong to the pending push
 };
 
+// the job's own state lives in context workspace slots [ws_state, ws_state + 3) (cudaMalloc / cudaFree
+// per job cost up to hundreds of ms on a process holding tens of GB -- they synchronise the device)
 static void job_free(mb200_cosine_job* j) {
   if (!j) return;
   if (j->ctx->active_job == j) j->ctx->active_job = nullptr;
-  cudaFree(j->row_thr);
-  cudaFree(j->best);
-  cudaFree(j->best_bound);
   delete j;
 }
 
@@ -1327,14 +1327,20 @@ static int job_begin_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t w
   const float scale = a->dtype == MB200_DTYPE_F16 ? F16_SCALE : 1.0f;
   j->scale2 = scale * scale;
   j->eps_rel = a->dtype == MB200_DTYPE_F16 ? 0x1.0p-10f : 0x1.0p-6f;
-  j->ws_base = j->ws_next = ws_base;
+  j->ws_state = ws_base;
+  j->ws_base = j->ws_next = ws_base + 3;
   const size_t rows_pad = (size_t)j->num_m * BM;
-  cudaError_t e = cudaMalloc(&j->row_thr, rows_pad * sizeof(uint32_t));
-  if (e != cudaSuccess) {
-    delete j;
-    return mb200_fail(ctx, MB200_ERR_OOM, "mb200_cosine_begin: cannot allocate row thresholds: %s", cudaGetErrorString(e));
+  {
+    Workspace ws(ctx);
+    ws.next = j->ws_state;
+    void* q = nullptr;
+    if (ws.get(rows_pad * sizeof(uint32_t), &q) != MB200_OK) {
+      delete j;
+      return MB200_ERR_OOM;
+    }
+    j->row_thr = (uint32_t*)q;
   }
-  e = cudaMemsetAsync(j->row_thr, 0, rows_pad * sizeof(uint32_t), ctx->stream);
+  cudaError_t e = cudaMemsetAsync(j->row_thr, 0, rows_pad * sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) {
     job_free(j);
     return mb200_fail(ctx, MB200_ERR_CUDA, "mb200_cosine_begin: %s", cudaGetErrorString(e));
@@ -1357,10 +1363,13 @@ static int job_merge_pending(mb200_cosine_job* j, bool to_carry, const mb200_cos
   if (to_carry) {
     const size_t rows_pad = (size_t)j->num_m * BM;
     if (!j->best) {
-      cudaError_t e = cudaMalloc(&j->best, rows_pad * CAP * sizeof(unsigned long long));
-      if (e == cudaSuccess) e = cudaMalloc(&j->best_bound, rows_pad * sizeof(float));
-      if (e != cudaSuccess)
-        return mb200_fail(ctx, MB200_ERR_OOM, "mb200_cosine_push: cannot allocate the carry state: %s", cudaGetErrorString(e));
+      Workspace ws(ctx);
+      ws.next = j->ws_state + 1;
+      void *q0 = nullptr, *q1 = nullptr;
+      MB_CHECK(ws.get(rows_pad * CAP * sizeof(unsigned long long), &q0));
+      MB_CHECK(ws.get(rows_pad * sizeof(float), &q1));
+      j->best = (unsigned long long*)q0;
+      j->best_bound = (float*)q1;
     }
     mp.carry_out = j->best;
     mp.carry_bound_out = j->best_bound;

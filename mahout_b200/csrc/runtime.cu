@@ -21,7 +21,7 @@ int mb200_fail(mb200_ctx* ctx, int code, const char* fmt, ...) {
 }
 
 int Workspace::get(size_t bytes, void** out) {
-  if (next >= ctx->ws.size()) ctx->ws.emplace_back(nullptr, 0);
+  while (next >= ctx->ws.size()) ctx->ws.emplace_back(nullptr, 0);
   auto& slot = ctx->ws[next++];
   if (slot.second < bytes || !slot.first) {
     if (slot.first) cudaFree(slot.first);
