@@ -41,7 +41,7 @@ static constexpr int COS_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 
 static constexpr float F16_SCALE = 4096.0f;  // rows are stored as x/||x|| * 2^12 in FP16
 
 struct CosParams {
-  const int4* items;        // work items (m block, first tile, end tile, -)
+  const int4* items;        // work items (m block, first tile, end tile, tile stride)
   int32_t num_items;
   int32_t total_tiles, tiles_per_block;
   int32_t depth, kblocks, stages;
@@ -293,7 +293,7 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         const int4 it = p.items[w];
         const int t0 = it.y, t1 = it.z;
         int g_seen = -1;
-        for (int t = t0; t < t1; t++) {
+        for (int t = t0; t < t1; t += it.w) {
           const int gs = t / p.tiles_per_block;
           const int l0 = (t - gs * p.tiles_per_block) * BN;
           int g = gs + p.rot;
@@ -340,7 +340,7 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
       const int4 it = p.items[w];
       const int t0 = it.y, t1 = it.z;
-      for (int t = t0; t < t1; t++) {
+      for (int t = t0; t < t1; t += it.w) {
         for (int dep = 0; dep < p.depth; dep++, q++) {
           const uint32_t as = q % ACC_STAGES;
           const uint32_t aphase = (q / ACC_STAGES) & 1u;
@@ -398,7 +398,7 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       float bound = -INFINITY;
       bool published = false;
       uint32_t* my_row_thr = p.row_thr + (size_t)it.x * BM + row;
-      for (int t = t0; t < t1; t++) {
+      for (int t = t0; t < t1; t += it.w) {
         const int gs = t / p.tiles_per_block;
         const int l0 = (t - gs * p.tiles_per_block) * BN + half * HALF;
         int g = gs + p.rot;
@@ -415,15 +415,17 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           // except in pull-gather mode, where the words arrive with the block
           uint32_t cm[CHUNKS];
           const uint32_t* bv = p.b_valid + ((size_t)g * p.depth + dep) * p.b_vw + (l0 >> 5);
-          if (p.ready == nullptr) {
+          // (if the block has already landed they can be fetched ahead as well)
+          const bool early = p.ready == nullptr || *((const volatile uint32_t*)p.ready + g) == p.epoch;
+          if (early) {
 #pragma unroll
-            for (int c = 0; c < CHUNKS; c++) cm[c] = __ldg(bv + c);
+            for (int c = 0; c < CHUNKS; c++) cm[c] = p.ready == nullptr ? __ldg(bv + c) : __ldcv(bv + c);
           }
           const bool my_valid = (rv >> dep) & 1u;
           const bool last = dep == p.depth - 1;
           mbar_wait(smem_u32(&bar_tfull[as]), aphase);
           fence_after_sync();
-          if (p.ready != nullptr) {
+          if (!early) {
 #pragma unroll
             for (int c = 0; c < CHUNKS; c++) cm[c] = __ldcv(bv + c);
           }
@@ -1461,6 +1463,7 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   {
     // item order inside a group: groups of Gm row blocks x all S chunks run together, chunk-major
     std::vector<std::vector<int32_t>> slots((size_t)num_m);
+    const bool strided = pc->ready_flags != nullptr;
     auto emit = [&](int mb, int me, int S) {
       const int ct = (T + S - 1) / S;
       const int Sr = (T + ct - 1) / ct;
@@ -1470,7 +1473,10 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
         for (int sI = 0; sI < Sr; sI++)
           for (int m = m0; m < m1; m++) {
             slots[m].push_back((int32_t)items.size());
-            items.push_back(make_int4(m, sI * ct, std::min(T, (sI + 1) * ct), 0));
+            // pull-gather: chunk sI takes every Sr-th tile, so that every CTA starts in the first
+            // (local) block and follows the blocks in their order of arrival
+            if (strided) items.push_back(make_int4(m, sI, T, Sr));
+            else items.push_back(make_int4(m, sI * ct, std::min(T, (sI + 1) * ct), 1));
           }
       }
     };
@@ -1538,7 +1544,8 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   p.abort_flag = ctx->gather_abort;
   p.exclude_self = a->exclude_self ? 1 : 0;
   // a list scans its columns in index order iff the blocks do not interleave
-  p.nonstrict = (pc->b_blocks > 1 && pc->b_id_add < pc->b_count * pc->b_id_mul) ? 1 : 0;
+  p.nonstrict = ((pc->b_blocks > 1 && pc->b_id_add < pc->b_count * pc->b_id_mul) ||
+                 (pc->ready_flags && pc->b_blocks > 1)) ? 1 : 0;
   {
     const double thr = a->threshold > 0.0 ? a->threshold : 0.0;
     const double slack = j->rescored ? (1.0 - (double)j->eps_rel) : (1.0 - 1e-6);

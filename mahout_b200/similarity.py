@@ -389,14 +389,57 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
     return res
 
 
+def _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_result, num_items):
+    """sharded_item_similarity over fused_gather_cosine: K2 writes straight into the peer-accessible rows"""
+    import ctypes as C
+    import torch
+    from . import _native as N
+    ctx, world = backend.ctx, plan.G
+    dev = torch.device(f"cuda:{ctx.device}")
+    cur = torch.cuda.current_stream(dev)
+    prev = ctx.stream_ptr
+    comp = torch.cuda.Stream(dev) if prev is None else torch.cuda.ExternalStream(prev, dev)
+    comp.wait_stream(cur)
+    if prev is None:
+        ctx.set_stream(comp.cuda_stream)
+    peers = None
+    try:
+        with torch.cuda.stream(comp):
+            peers = PeerRows(ctx, plan, backend.bank.d, backend.bank.w, dtype, group)
+            N.check(N.lib().mb200_bank_normalize(backend.bank.handle, sk._DTYPES[dtype], C.c_void_p(peers.rows.data_ptr()),
+                                                 C.c_void_p(peers.valid.data_ptr())), ctx.handle)
+            kw = {}
+            if precision == "rescored":
+                a_cnt = backend.counters()
+                kw = dict(a_counters=a_cnt, b_counters=_all_gather(a_cnt, world, group))
+            idx, sim, cnt = fused_gather_cosine(backend, plan, peers, k, threshold, dtype, precision, **kw)
+            if gather_result:
+                parts = [_all_gather(t, world, group).cpu().numpy() for t in (idx, sim, cnt)]      # C3
+                out = tuple(plan.assemble(list(p)) for p in parts)
+            else:
+                out = (idx, sim, cnt)
+            peers.close()
+            peers = None
+        cur.wait_stream(comp)
+    finally:
+        if prev is None:
+            ctx.sync()
+            ctx.set_stream(None)
+    backend.close()
+    return out
+
+
 def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM,
                             threshold: float | None = None, width: int = 4096, depth: int = 4, seed: int = 42,
                             frac_bits: int = 1, dtype: str = "f16", precision: str = "tensor",
-                            group=None, backend=None, gather_result: bool = True, chunk_rows: int = 0):
+                            group=None, backend=None, gather_result: bool = True, chunk_rows: int = 0,
+                            fused: bool | None = None):
     """One call per rank (torch.distributed initialised; NCCL on GPUs).  `row, user, pref` are the
     events this rank holds (any subset of the stream: they are first routed to their owners).
     chunk_rows > 0 selects the pipelined form (`pipelined_cosine`): the all-gather runs in chunks of that
-    many rows per shard, overlapped with K3.
+    many rows per shard, overlapped with K3.  fused (default on GPUs with world > 1 and chunk_rows == 0)
+    selects `fused_gather_cosine`: the shards are pulled over NVLink by the copy engines while one K3
+    launch consumes them in order of arrival.
     Returns (idx, sim, cnt) for all N items on every rank when gather_result, else this rank's
     shard in local row order."""
     import torch
@@ -419,6 +462,10 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
         row, user, pref = np.asarray(row, np.int64), np.asarray(user, np.int64), np.asarray(pref, np.float32)
         lrow, luser, lpref = plan.my_events(row, user, pref)
     backend.build(plan, lrow, luser, lpref, width, depth, seed, frac_bits)
+    if fused is None:
+        fused = world > 1 and chunk_rows == 0 and isinstance(backend, GpuShardBackend)
+    if fused and world > 1:
+        return _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_result, num_items)
     a_rows, a_valid = backend.normalized(dtype)
     a_cnt = backend.counters() if precision == "rescored" else None
     if world > 1 and chunk_rows > 0:

@@ -176,7 +176,7 @@ def _nccl_worker(rank, world, port, q):
     fused_ok = True
     for precision in ("tensor", "rescored"):
         want = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N, k=20, width=1024,
-                                           depth=4, precision=precision, gather_result=False)
+                                           depth=4, precision=precision, gather_result=False, fused=False)
         for rep in range(3):
             NV.check(NV.lib().mb200_bank_normalize(be.bank.handle, NV.DTYPE_F16, C.c_void_p(peers.rows.data_ptr()),
                                                    C.c_void_p(peers.valid.data_ptr())), ctx.handle)
