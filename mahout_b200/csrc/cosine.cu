@@ -1422,10 +1422,23 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   //            everywhere).
   const int P = ctx->num_sms;
   const int smax = std::min(T, 32);
+  // One tile step (all depths of one 128 x BN tile) takes d * kblocks * t_mma on the tensor pipe.  In
+  // the same time the wave pulls, from HBM, the A blocks of its P/s distinct row blocks (an A block is
+  // re-read for every B tile: 148 x 4 MB does not fit L2) and s B tiles: with s = 1 that alone is
+  // ~6 TB/s -- the HBM roofline, measured as 59 % DRAM utilisation already at s = 2
+  // (profiles/r1_k_cosine_v3_ncu.txt).  Cutting the rows into s >= 2 column chunks lets s CTAs share
+  // every A block through L2.
+  const double t_mma_tile = (double)a->depth * (ld / BK) * (2.0 * BM * BN * BK) / (1500e12 / P);   // s per tile step
+  auto dram_tile = [&](long long nblocks, int s) {
+    const double rows = (double)std::min<long long>(nblocks, std::max(1, P / s));
+    const double bytes = (rows * BM + (double)s * BN) * ld * 2.0 * a->depth;
+    return bytes / 5.5e12;
+  };
   auto wave_cost = [&](long long nblocks, int s) {
     const long long waves = (nblocks * s + P - 1) / P;
     const int ct = (T + s - 1) / s;
-    return (double)waves * ((double)ct + 3.0) * (1.0 + 0.01 * s);
+    const double slow = std::max(1.0, dram_tile(nblocks, s) / t_mma_tile);
+    return (double)waves * ((double)ct * slow + 3.0) * (1.0 + 0.01 * s);
   };
   int S_main = 1, S_tail = 1, main_blocks = 0;
   {
@@ -1438,13 +1451,17 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
         main_blocks = num_m;
       }
     }
-    const int full = num_m / P * P, R = num_m - full;
-    if (full > 0 && R > 0) {
-      for (int s = 1; s <= smax; s++) {
-        const double cost = wave_cost(full, 1) + wave_cost(R, s);
+    // tail shape: the largest number of row blocks that fills whole waves with sm chunks each, the
+    // remaining R blocks cut finer
+    for (int sm = 1; sm <= std::min(smax, 4); sm++) {
+      const int per_wave = std::max(1, P / sm);
+      const int full = num_m / per_wave * per_wave, R = num_m - full;
+      if (full <= 0 || R <= 0) continue;
+      for (int s = sm; s <= smax; s++) {
+        const double cost = wave_cost(full, sm) + wave_cost(R, s);
         if (cost < best * 0.999) {
           best = cost;
-          S_main = 1;
+          S_main = sm;
           S_tail = s;
           main_blocks = full;
         }
@@ -1458,6 +1475,26 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
       main_blocks = num_m;
     }
   }
+  if (const char* ev = getenv("MB200_COS_MAIN")) {    // tuning override: chunks of the full waves
+    const int sm = atoi(ev);
+    if (sm >= 1 && sm <= std::min(T, 8)) {
+      const int per_wave = std::max(1, P / sm);
+      S_main = sm;
+      main_blocks = num_m / per_wave * per_wave;
+      const int R = num_m - main_blocks;
+      double best = 1e300;
+      S_tail = sm;
+      for (int s = sm; s <= smax && R > 0; s++) {
+        const double cost = wave_cost(R, s);
+        if (cost < best * 0.999) {
+          best = cost;
+          S_tail = s;
+        }
+      }
+    }
+  }
+  if (trace) fprintf(stderr, "[mb200 trace] plan: num_m=%d T=%d main=%d blocks x %d chunks, tail x %d chunks\n", num_m, T,
+                     main_blocks, S_main, S_tail);
   std::vector<int4> items;
   std::vector<int32_t> slot_ptr((size_t)num_m + 1, 0), slot_of;
   {
