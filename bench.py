@@ -375,7 +375,7 @@ def run_ours(args):
                     "bound": "PCIe: 12 B/event over the host link"},
             "roofline": {"bound": "hbm", "kernel": "k_update_single", "achieved": achieved, "peak": peaks["hbm"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm"],
-                         # ncu --set full (profiles/r1_k_update_single_ncu.txt): 3.056 GB of DRAM traffic per
+                         # ncu --set full (profiles/r1_k_update_single_v2_ncu.txt): 3.056 GB of DRAM traffic per
                          # 2.5e8-event launch = 12.2 B/event; the counters (32 MiB) stay in L2
                          "traffic": 12.2 * n,
                          "peak_source": peaks["source"], "algorithmic_bytes_per_event": ALGO_BYTES_PER_EVENT,
@@ -649,8 +649,9 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                          "frac_of_burst_peak": achieved / peaks["bf16_burst"], "peak_source": peaks["source"],
                          "flops_per_launch": flops_rank, "kernel_ms_per_launch": k3_s * 1e3,
                          # ncu --set full of this kernel on this workload at 1 GPU
-                         # (profiles/r1_k_cosine_final_ncu.txt): dram read 69.06 GB + write 0.79 GB
-                         "traffic": 69.85e9 if world == 1 else None},
+                         # (profiles/r1_k_cosine_v3_ncu.txt): dram read 82.71 GB + write 0.62 GB -- the A blocks
+                         # are re-read for every B tile ("Scheduling")
+                         "traffic": 83.32e9 if world == 1 else None},
             "e2e": {"value": pairs / e2e["rescored"], "unit": "pairs/s", "ms_per_job": e2e["rescored"] * 1e3,
                     "h2d_bytes_per_step": 20 * n_local, "d2h_bytes_per_step": plan.rows_per_shard * (C3_K * 16 + 4),
                     "tensor_precision": {"value": pairs / e2e["tensor"], "ms_per_job": e2e["tensor"] * 1e3},

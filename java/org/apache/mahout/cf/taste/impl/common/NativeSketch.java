@@ -66,6 +66,22 @@ public final class NativeSketch {
   public static native void cosineTopK(long bank, int k, double threshold, boolean excludeSelf, int dtype,
                                        int precision, long[] outIdx, double[] outSim, int[] outCnt);
 
+  /**
+   * Ingest on the GPU.  parsePrefs = ToEntityPrefsMapper.map over one text split held in a direct
+   * buffer (ToEntityPrefsMapper.java:56-76); prepare = idToIndex + ItemIDIndexReducer +
+   * ToUserVectorsReducer (last pref of a (user, index) pair wins, minPrefsPerUser); updateFromPrefs feeds
+   * the prepared, still device-resident events to mb200_bank_update (entity = matrix row, key = userID).
+   */
+  public static native long parsePrefs(long ctx, ByteBuffer text, long bytes, boolean booleanData, float ratingShift,
+                                       boolean transpose);
+  public static native long eventCount(long events);
+  public static native void destroyEvents(long events);
+  public static native long prepare(long events, int minPrefsPerUser);
+  public static native void prefsInfo(long prefs, long[] info);
+  public static native void prefsTables(long prefs, long[] itemId, int[] indexValues);
+  public static native void updateFromPrefs(long bank, long prefs);
+  public static native void destroyPrefs(long prefs);
+
   /** mb200_host_alloc / mb200_host_free wrapped as a direct ByteBuffer. */
   public static native ByteBuffer allocPinned(long bytes);
   public static native void freePinned(ByteBuffer buffer);

@@ -112,4 +112,57 @@ JNIEXPORT jobject JNICALL JNI_FN(allocPinned)(JNIEnv* env, jclass c, jlong bytes
 JNIEXPORT void JNICALL JNI_FN(freePinned)(JNIEnv* env, jclass c, jobject buffer) {
   mb200_host_free((*env)->GetDirectBufferAddress(env, buffer));
 }
+/* ---- ingest (PreparePreferenceMatrixJob on the GPU) ------------------------------------------------ */
+JNIEXPORT jlong JNICALL JNI_FN(parsePrefs)(JNIEnv* env, jclass c, jlong ctx, jobject text, jlong bytes,
+                                           jboolean booleanData, jfloat ratingShift, jboolean transpose) {
+  mb200_events* ev = NULL;
+  CHECK(mb200_events_parse((mb200_ctx*)(intptr_t)ctx, (const char*)(*env)->GetDirectBufferAddress(env, text), bytes,
+                           MB200_MEM_HOST, booleanData, ratingShift, transpose, &ev), (mb200_ctx*)(intptr_t)ctx);
+  return (jlong)(intptr_t)ev;
+}
+
+JNIEXPORT jlong JNICALL JNI_FN(eventCount)(JNIEnv* env, jclass c, jlong events) {
+  int64_t n = 0;
+  CHECK(mb200_events_count((mb200_events*)(intptr_t)events, &n), NULL);
+  return n;
+}
+
+JNIEXPORT void JNICALL JNI_FN(destroyEvents)(JNIEnv* env, jclass c, jlong events) {
+  mb200_events_destroy((mb200_events*)(intptr_t)events);
+}
+
+JNIEXPORT jlong JNICALL JNI_FN(prepare)(JNIEnv* env, jclass c, jlong events, jint minPrefsPerUser) {
+  mb200_prefs* p = NULL;
+  CHECK(mb200_events_prepare((mb200_events*)(intptr_t)events, minPrefsPerUser, &p), NULL);
+  return (jlong)(intptr_t)p;
+}
+
+/* info[0..2] = surviving events, items (matrix rows), users */
+JNIEXPORT void JNICALL JNI_FN(prefsInfo)(JNIEnv* env, jclass c, jlong prefs, jlongArray info) {
+  int64_t v[3] = {0, 0, 0};
+  CHECK(mb200_prefs_info((mb200_prefs*)(intptr_t)prefs, &v[0], &v[1], &v[2]), NULL);
+  (*env)->SetLongArrayRegion(env, info, 0, 3, (const jlong*)v);
+}
+
+JNIEXPORT void JNICALL JNI_FN(prefsTables)(JNIEnv* env, jclass c, jlong prefs, jlongArray itemId, jintArray indexValues) {
+  jlong* pi = (*env)->GetLongArrayElements(env, itemId, NULL);
+  jint* px = (*env)->GetIntArrayElements(env, indexValues, NULL);
+  int rc = mb200_prefs_tables((mb200_prefs*)(intptr_t)prefs, (int64_t*)pi, (int32_t*)px);
+  (*env)->ReleaseLongArrayElements(env, itemId, pi, 0);
+  (*env)->ReleaseIntArrayElements(env, indexValues, px, 0);
+  CHECK(rc, NULL);
+}
+
+/* K1 straight from the prepared (device-resident) events: entity = row, key = user, inc = pref */
+JNIEXPORT void JNICALL JNI_FN(updateFromPrefs)(JNIEnv* env, jclass c, jlong bank, jlong prefs) {
+  int64_t *row = NULL, *user = NULL, n = 0;
+  float* pref = NULL;
+  CHECK(mb200_prefs_info((mb200_prefs*)(intptr_t)prefs, &n, NULL, NULL), NULL);
+  CHECK(mb200_prefs_columns((mb200_prefs*)(intptr_t)prefs, &row, &user, &pref), NULL);
+  CHECK(mb200_bank_update((mb200_bank*)(intptr_t)bank, row, user, pref, n, MB200_MEM_DEVICE), NULL);
+}
+
+JNIEXPORT void JNICALL JNI_FN(destroyPrefs)(JNIEnv* env, jclass c, jlong prefs) {
+  mb200_prefs_destroy((mb200_prefs*)(intptr_t)prefs);
+}
 /* clearBank, check, queryMany, read, cmDims follow the same pattern (one C call each). */

@@ -9,6 +9,7 @@
 typedef int32_t jint;
 typedef int64_t jlong;
 typedef double jdouble;
+typedef float jfloat;
 typedef unsigned char jboolean;
 typedef void* jobject;
 typedef jobject jclass;
@@ -28,5 +29,6 @@ struct JNINativeInterface_ {
   void (*ReleaseIntArrayElements)(JNIEnv*, jintArray, jint*, jint);
   void* (*GetDirectBufferAddress)(JNIEnv*, jobject);
   jobject (*NewDirectByteBuffer)(JNIEnv*, void*, jlong);
+  void (*SetLongArrayRegion)(JNIEnv*, jlongArray, jint, jint, const jlong*);
 };
 #endif
