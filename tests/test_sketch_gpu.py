@@ -255,6 +255,63 @@ def test_cosine_cm_user_similarity(mb, ctx):
     cm.close()
 
 
+def test_cosine_cm_per_user_config_and_estimate_preference(mb, ctx):
+    """The reference's per-pair sizing (u1's sketch rebuilt with u2's (delta, epsilon), CosineCM.java:84-96)
+    with a CountMinSketchConfig, and GenericUserBasedRecommender.doEstimatePreference (:134-184) over a
+    neighbourhood -- against the oracle's sketches."""
+    import math
+    from mahout_b200.cmconfig import CountMinSketchConfig
+    from mahout_b200.cosinecm import CosineCM
+    rng = np.random.Generator(np.random.PCG64(33))
+    n, users, items = 2500, 30, 200
+    user = rng.integers(1, users + 1, n).astype(np.int64)
+    item = rng.integers(1, items, n).astype(np.int64)
+    pref = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
+    ids, counts = np.unique(user, return_counts=True)
+    cfg = CountMinSketchConfig(1.0)
+    cfg.configure(ids, counts, items)
+    hfb = mb.HashFunctionBuilder(7)
+    cm = CosineCM(user, item, pref, 128, 3, hfb, ctx=ctx, config=cfg)
+    for u1, u2 in [(1, 2), (5, 9), (9, 5), (3, 3)]:
+        w, d = orc.cm_dims(cfg.getDelta(u2), cfg.getEpsilon(u2))
+        a, b = orc.hash_params(7, d)
+        c1, c2 = np.zeros((d, w)), np.zeros((d, w))
+        orc.cm_update(c1, w, d, a, b, item[user == u1], pref[user == u1].astype(np.float64))
+        orc.cm_update(c2, w, d, a, b, item[user == u2], pref[user == u2].astype(np.float64))
+        want = orc.cm_cosine(c1, c2, w, d)
+        want = want if math.isnan(want) else orc.clamp_similarity(want)
+        got = cm.userSimilarityPerUserConfig(u1, u2)
+        assert (math.isnan(got) and math.isnan(want)) or abs(got - want) < 1e-12
+    # doEstimatePreference over the shared-size bank
+    w, d = 128, 3
+    a, b = orc.hash_params(7, d)
+    ref = {}
+    for u in ids:
+        c = np.zeros((d, w))
+        orc.cm_update(c, w, d, a, b, item[user == u], pref[user == u].astype(np.float64))
+        ref[int(u)] = c
+    the_user, nb, it = 4, [2, 4, 6, 8, 10, 12], int(item[user == 6][0])
+    preference = total = 0.0
+    count = 0
+    for u in nb:
+        if u == the_user:
+            continue
+        p = float(np.float32(orc.cm_get(ref[u], w, d, a, b, it)))
+        if p == 0.0:
+            continue
+        s = orc.clamp_similarity(orc.cm_cosine(ref[the_user], ref[u], w, d))
+        if not math.isnan(s):
+            preference += s * p
+            total += s
+            count += 1
+    want = math.nan if count <= 1 else float(np.float32(preference / total))
+    got = cm.doEstimatePreference(the_user, nb, it)
+    assert (math.isnan(got) and math.isnan(want)) or got == want
+    assert math.isnan(cm.doEstimatePreference(the_user, [], it))
+    assert math.isnan(cm.doEstimatePreference(the_user, [the_user], it))
+    cm.close()
+
+
 def test_full_size_properties_config2(mb, ctx):
     """Size-independent properties at BASELINE config-2 scale (2^28 device-generated Zipf events,
     d=4 x W=2^20): every sketch row holds exactly the total mass, the update is linear (two halves
