@@ -38,7 +38,7 @@ extern "C" {
 #define MB200_MEM_HOST 0
 #define MB200_MEM_DEVICE 1
 
-#define MB200_MAX_DEPTH 16
+#define MB200_MAX_DEPTH 32 /* CountMinSketchConfig searches depths 1..24 (CountMinSketchConfig.java:28-29) */
 
 /* element type of the normalised sketch rows fed to the tensor cores */
 #define MB200_DTYPE_F16 0  /* rows scaled by 2^8; 11-bit significand (TF32-grade) at BF16 MMA rate */

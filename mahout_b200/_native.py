@@ -18,7 +18,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 DTYPE_F16, DTYPE_BF16 = 0, 1
 PRECISION_TENSOR, PRECISION_RESCORED = 0, 1
 K_UPDATE, K_NORMALIZE, K_COSINE, K_RESCORE, K_PARSE, K_PREPARE = 0, 1, 2, 3, 4, 5
-MAX_DEPTH = 16
+MAX_DEPTH = 32
 
 
 class NativeError(RuntimeError):
