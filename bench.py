@@ -546,13 +546,22 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
     if world > 1:
         b_cnt = torch.empty((world,) + tuple(a_cnt.shape), dtype=a_cnt.dtype, device=dev)
         dist.all_gather_into_tensor(b_cnt.view(-1, C3_DEPTH, C3_WIDTH), a_cnt)
+    step("rescored", b_cnt)                 # untimed: first-touch allocation of the re-score workspaces
     barrier()
     ctx.reset_profile()
-    t0 = time.perf_counter()
-    ridx, rs, rcnt = step("rescored", b_cnt)
+    r_reps = max(1, min(steps, 3))
+    e0.record(stream)
+    for _ in range(r_reps):
+        ridx, rs, rcnt = step("rescored", b_cnt)
+    e1.record(stream)
     barrier()
-    rescored_ms = (time.perf_counter() - t0) * 1e3
-    r5_ms, _ = ctx.kernel_time(N.K_RESCORE)
+    rescored_ms = e0.elapsed_time(e1) / r_reps
+    if world > 1:
+        t = torch.tensor([rescored_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rescored_ms = float(t.item())
+    r5_ms, r5_n = ctx.kernel_time(N.K_RESCORE)
+    r5_ms /= max(r5_n, 1)
     fallback = last_fallback_rows(ctx)
     ctx.set_profiling(False)
 

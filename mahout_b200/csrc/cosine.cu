@@ -82,6 +82,10 @@ __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_
 template <>
 __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// One CTA per sketch row.  Rows of up to 256 x NORM_VPT counters are read ONCE with 16-byte loads and
+// held in registers between the norm and the conversion (8 B read + 2 B written per counter: the
+// kernel's whole HBM traffic); wider rows take the two-pass path.
+static constexpr int NORM_VPT = 16;
 template <typename OutT>
 __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__ counters, long long E,
                                                    int d, int W, int ld, float scale,
@@ -92,12 +96,29 @@ __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__
   const long long e = bid / d;
   const int i = (int)(bid % d);
   const long long* row = counters + (size_t)bid * W;
+  OutT* o = out + ((size_t)i * E + e) * ld;
+  const bool in_regs = (W & 1) == 0 && W <= 256 * NORM_VPT;
+  long long v[NORM_VPT];
   double ss = 0.0;
-  for (int j = threadIdx.x; j < W; j += blockDim.x) {
-    double x = (double)row[j];
-    ss += x * x;
+  if (in_regs) {
+    const longlong2* row2 = reinterpret_cast<const longlong2*>(row);
+    const int pairs = W >> 1;
+#pragma unroll
+    for (int t = 0; t < NORM_VPT / 2; t++) {
+      const int j = t * 256 + threadIdx.x;
+      longlong2 x = make_longlong2(0, 0);
+      if (j < pairs) x = __ldg(row2 + j);
+      v[2 * t] = x.x;
+      v[2 * t + 1] = x.y;
+      ss += (double)x.x * (double)x.x + (double)x.y * (double)x.y;
+    }
+  } else {
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      const double x = (double)row[j];
+      ss += x * x;
+    }
   }
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
   double tot = 0.0;
@@ -105,10 +126,26 @@ __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__
   for (int w = 0; w < 8; w++) tot += red[w];
   const double nrm = sqrt(tot);
   const double inv = nrm > 0.0 ? (double)scale / nrm : 0.0;
-  OutT* o = out + ((size_t)i * E + e) * ld;
-  for (int j = threadIdx.x; j < ld; j += blockDim.x) {
-    float v = j < W ? (float)((double)row[j] * inv) : 0.0f;
-    o[j] = to_out<OutT>(v);
+  if (in_regs) {
+    // ld is even and the row base is 4-byte aligned: two 16-bit outputs per store
+    const int pairs_ld = ld >> 1, pairs = W >> 1;
+#pragma unroll
+    for (int t = 0; t < NORM_VPT / 2; t++) {
+      const int j = t * 256 + threadIdx.x;
+      if (j < pairs_ld) {
+        const float a = j < pairs ? (float)((double)v[2 * t] * inv) : 0.0f;
+        const float b = j < pairs ? (float)((double)v[2 * t + 1] * inv) : 0.0f;
+        OutT two[2] = {to_out<OutT>(a), to_out<OutT>(b)};
+        *reinterpret_cast<uint32_t*>(o + 2 * j) = *reinterpret_cast<const uint32_t*>(two);
+      }
+    }
+    for (int j = (NORM_VPT / 2) * 256 + threadIdx.x; j < pairs_ld; j += 256)   // padding beyond the register tile
+      *reinterpret_cast<uint32_t*>(o + 2 * j) = 0u;
+  } else {
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) {
+      const float x = j < W ? (float)((double)row[j] * inv) : 0.0f;
+      o[j] = to_out<OutT>(x);
+    }
   }
   if (threadIdx.x == 0 && nrm > 0.0) atomicOr(&valid[(size_t)i * vw + (e >> 5)], 1u << (e & 31));
 }

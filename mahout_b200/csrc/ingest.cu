@@ -71,7 +71,6 @@ static constexpr int PT = 256;          // threads per CTA
 static constexpr int PB = 16;           // bytes per thread
 static constexpr int TILE = PT * PB;    // bytes per tile
 static constexpr int LOOK = 496;        // look-ahead staged behind the tile (longer lines read global memory)
-static constexpr int SLEN = 1 + TILE + LOOK;
 
 enum { PERR_NONE = 0, PERR_LONG = 1, PERR_TOKENS = 2, PERR_FLOAT = 3, PERR_FIXUPS = 4 };
 
@@ -95,58 +94,74 @@ struct ParseArgs {
   int fix_cap;
 };
 
+// One staged tile: s[o] = byte base + o for o in [0, TILE + LOOK), '\n' beyond the end of the buffer.
 struct Tile {
   const unsigned char* g;
   long long n, base;
-  const unsigned char* s;  // s[0] = byte base-1, s[1 + i] = byte base + i
-  // byte at absolute position pos; a virtual '\n' sits before the buffer and behind its end
-  __device__ __forceinline__ unsigned char at(long long pos) const {
-    if (pos < 0 || pos >= n) return '\n';
-    const long long o = pos - base + 1;
-    return (o >= 0 && o < SLEN) ? s[o] : __ldg(g + pos);
+  const unsigned char* s;
+  // byte at tile offset o >= 0; a virtual '\n' sits behind the end of the buffer
+  __device__ __forceinline__ unsigned char at(int o) const {
+    if (o < TILE + LOOK) return s[o];
+    const long long pos = base + o;
+    return pos < n ? __ldg(g + pos) : (unsigned char)'\n';
   }
-  __device__ __forceinline__ bool eol(long long pos) const {
-    const unsigned char c = at(pos);
-    return c == '\n' || (c == '\r' && at(pos + 1) == '\n');
+  __device__ __forceinline__ bool eol(int o) const {
+    const unsigned char c = at(o);
+    return c == '\n' || (c == '\r' && at(o + 1) == '\n');
   }
-  // a non-empty line starts at pos
-  __device__ __forceinline__ bool starts(long long pos) const { return at(pos - 1) == '\n' && !eol(pos); }
 };
 
-__device__ __forceinline__ void stage_tile(const unsigned char* g, long long n, long long base, unsigned char* s) {
-  if (threadIdx.x == 0) s[0] = base > 0 ? __ldg(g + base - 1) : (unsigned char)'\n';
+// Stage bytes [base, base + TILE + LOOK) with 16-byte loads and stores; *s_prev = byte base - 1.
+__device__ __forceinline__ void stage_tile(const unsigned char* g, long long n, long long base, unsigned char* s,
+                                           unsigned char* s_prev) {
+  if (threadIdx.x == 0) *s_prev = base > 0 ? __ldg(g + base - 1) : (unsigned char)'\n';
   const long long end = base + TILE + LOOK < n ? base + TILE + LOOK : n;
   const int have = (int)(end - base);
+  int done = 0;
   if ((((uintptr_t)(g + base)) & 15) == 0) {
-    // s + 1 is not 16-byte aligned: 16-byte global loads, byte stores
     const int vec = have >> 4;
-    for (int v = threadIdx.x; v < vec; v += PT) {
-      const uint4 x = __ldg(reinterpret_cast<const uint4*>(g + base) + v);
-      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-      for (int j = 0; j < 16; j++) s[1 + v * 16 + j] = (unsigned char)(w[j >> 2] >> ((j & 3) * 8));
-    }
-    for (int i = (vec << 4) + threadIdx.x; i < have; i += PT) s[1 + i] = __ldg(g + base + i);
-  } else {
-    for (int i = threadIdx.x; i < have; i += PT) s[1 + i] = __ldg(g + base + i);
+    for (int v = threadIdx.x; v < vec; v += PT)
+      reinterpret_cast<uint4*>(s)[v] = __ldg(reinterpret_cast<const uint4*>(g + base) + v);
+    done = vec << 4;
   }
-  for (int i = have + threadIdx.x; i < TILE + LOOK; i += PT) s[1 + i] = '\n';
+  for (int i = done + threadIdx.x; i < have; i += PT) s[i] = __ldg(g + base + i);
+  for (int i = have + threadIdx.x; i < TILE + LOOK; i += PT) s[i] = '\n';
   __syncthreads();
+}
+
+// bit j of the result <=> byte j of the 16 bytes equals c
+__device__ __forceinline__ unsigned eq_mask16(const uint4& x, unsigned c4) {
+  const unsigned w[4] = {x.x, x.y, x.z, x.w};
+  unsigned m = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const unsigned t = __vcmpeq4(w[k], c4) & 0x01010101u;   // bits 0, 8, 16, 24
+    m |= ((t * 0x10204080u) >> 28) << (4 * k);             // gathered into one nibble
+  }
+  return m;
+}
+
+// bit j <=> a non-empty line starts at byte j of this thread's 16 bytes.  A line starts behind a '\n'
+// (or at offset 0 of the buffer) unless it is empty: "\n" or "\r\n" follow immediately.  Positions
+// behind the end of the buffer hold '\n' padding and can never start a line.
+__device__ __forceinline__ unsigned line_starts16(const unsigned char* s, unsigned char prev_byte) {
+  const int o = threadIdx.x * PB;
+  const uint4 x = *reinterpret_cast<const uint4*>(s + o);
+  const unsigned nl = eq_mask16(x, 0x0A0A0A0Au), cr = eq_mask16(x, 0x0D0D0D0Du);
+  const unsigned prev_nl = (threadIdx.x == 0 ? prev_byte : s[o - 1]) == '\n' ? 1u : 0u;
+  const unsigned next_nl = s[o + PB] == '\n' ? 1u : 0u;   // LOOK >= 1 byte is always staged
+  const unsigned eol = nl | (cr & ((nl >> 1) | (next_nl << 15)));
+  return ((nl << 1) | prev_nl) & ~eol & 0xFFFFu;
 }
 
 __global__ void __launch_bounds__(PT) k_count_lines(const unsigned char* __restrict__ text, long long bytes,
                                                     long long num_tiles, long long* __restrict__ counts) {
-  __shared__ unsigned char s[SLEN + 15];
+  __shared__ __align__(16) unsigned char s[TILE + LOOK];
+  __shared__ unsigned char s_prev;
   __shared__ int s_w[PT / 32];
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const long long base = tile * TILE;
-    stage_tile(text, bytes, base, s);
-    Tile tv{text, bytes, base, s};
-    int c = 0;
-    const long long p0 = base + (long long)threadIdx.x * PB;
-#pragma unroll
-    for (int j = 0; j < PB; j++)
-      if (p0 + j < bytes && tv.starts(p0 + j)) c++;
+    stage_tile(text, bytes, tile * TILE, s, &s_prev);
+    int c = __popc(line_starts16(s, s_prev));
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -189,7 +204,7 @@ __global__ void __launch_bounds__(1024) k_scan(const long long* __restrict__ in,
 
 // Long.parseLong: optional sign, at least one digit, range checked.  Leaves q on the first byte after
 // the digits.
-__device__ __forceinline__ bool parse_long(const Tile& tv, long long& q, long long* out) {
+__device__ __forceinline__ bool parse_long(const Tile& tv, int& q, long long* out) {
   unsigned char c = tv.at(q);
   bool neg = false;
   if (c == '-' || c == '+') {
@@ -217,7 +232,7 @@ __device__ __forceinline__ bool is_delim(unsigned char c) { return c == ',' || c
 
 // Float.parseFloat of the token [q, e) (already trimmed).  1 = value decided and correctly rounded,
 // 0 = leave it to the host, -1 would be a syntax error -- also left to the host, which owns the message.
-__device__ int parse_float_token(const Tile& tv, long long q, long long e, float* out) {
+__device__ int parse_float_token(const Tile& tv, int q, int e, float* out) {
   if (q >= e) return 0;
   unsigned char c = tv.at(q);
   bool neg = false;
@@ -262,18 +277,15 @@ __device__ int parse_float_token(const Tile& tv, long long q, long long e, float
 }
 
 __global__ void __launch_bounds__(PT) k_parse_lines(const ParseArgs a) {
-  __shared__ unsigned char s[SLEN + 15];
+  __shared__ __align__(16) unsigned char s[TILE + LOOK];
+  __shared__ unsigned char s_prev;
   __shared__ int s_w[PT / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
     const long long base = tile * TILE;
-    stage_tile(a.text, a.bytes, base, s);
+    stage_tile(a.text, a.bytes, base, s, &s_prev);
     Tile tv{a.text, a.bytes, base, s};
-    const long long p0 = base + (long long)threadIdx.x * PB;
-    unsigned flags = 0;
-#pragma unroll
-    for (int j = 0; j < PB; j++)
-      if (p0 + j < a.bytes && tv.starts(p0 + j)) flags |= 1u << j;
+    unsigned flags = line_starts16(s, s_prev);
     // exclusive scan of the per-thread line counts over the CTA
     const int c = __popc(flags);
     int inc = c;
@@ -289,8 +301,9 @@ __global__ void __launch_bounds__(PT) k_parse_lines(const ParseArgs a) {
     while (flags) {
       const int j = __ffs(flags) - 1;
       flags &= flags - 1;
-      const long long p = p0 + j;
-      long long q = p, u = 0, it = 0;
+      const int p = threadIdx.x * PB + j;   // tile offset of the line start
+      int q = p;
+      long long u = 0, it = 0;
       int err = PERR_NONE;
       float pref = 1.0f;
       if (!parse_long(tv, q, &u)) err = PERR_LONG;
@@ -304,15 +317,15 @@ __global__ void __launch_bounds__(PT) k_parse_lines(const ParseArgs a) {
           err = PERR_LONG;
         } else if (!a.boolean_data) {
           q++;
-          long long e = q;
+          int e = q;
           while (!tv.eol(e) && !is_delim(tv.at(e))) e++;
-          long long tq = q, te = e;           // String.trim(): strip bytes <= ' '
+          int tq = q, te = e;           // String.trim(): strip bytes <= ' '
           while (tq < te && tv.at(tq) <= ' ') tq++;
           while (te > tq && tv.at(te - 1) <= ' ') te--;
           if (e == q) {
             // an empty third token is only legal when nothing but delimiters follows (String.split
             // drops trailing empty strings)
-            long long r = e;
+            int r = e;
             while (is_delim(tv.at(r))) r++;
             if (!tv.eol(r)) err = PERR_FLOAT;
           } else {
@@ -323,8 +336,8 @@ __global__ void __launch_bounds__(PT) k_parse_lines(const ParseArgs a) {
               const int k = atomicAdd(a.fix_count, 1);
               if (k < a.fix_cap) {
                 a.fix_line[k] = slot;
-                a.fix_pos[k] = tq;
-                a.fix_len[k] = (int)(te - tq < 0x7fffffff ? te - tq : 0x7fffffff);
+                a.fix_pos[k] = base + tq;
+                a.fix_len[k] = te - tq;
               } else {
                 err = PERR_FIXUPS;
               }
@@ -334,8 +347,9 @@ __global__ void __launch_bounds__(PT) k_parse_lines(const ParseArgs a) {
         }
       }
       if (err != PERR_NONE) {
-        const unsigned long long old = atomicMin(a.err_pos, (unsigned long long)p);
-        if ((unsigned long long)p < old) *a.err_code = err;  // best effort: the code of the first line
+        const unsigned long long pos = (unsigned long long)(base + p);
+        const unsigned long long old = atomicMin(a.err_pos, pos);
+        if (pos < old) *a.err_code = err;  // best effort: the code of the first line
       }
       a.user[slot] = a.transpose ? it : u;
       a.item[slot] = a.transpose ? u : it;
