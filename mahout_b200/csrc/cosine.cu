@@ -631,15 +631,35 @@ __global__ void __launch_bounds__(256) k_merge(const MergeParams p) {
   uint32_t rthr = p.row_thr[r];
   unsigned long long* pend = s_pend[wib];
   int npend = 0;
+  bool have_best = p.carry_in != nullptr;
   auto fold = [&]() {
+    if (!have_best) {
+      // first fold of the row (the only one for most rows): nothing to merge with, sort the
+      // pending keys alone -- 256 keys instead of 512
+      unsigned long long k8[CAP / 32];
 #pragma unroll
-    for (int u = 0; u < CAP / 32; u++) {
-      const int e = u * 32 + lane;
-      key[CAP / 32 + u] = e < npend ? pend[e] : 0ull;
+      for (int u = 0; u < CAP / 32; u++) {
+        const int e = u * 32 + lane;
+        k8[u] = e < npend ? pend[e] : 0ull;
+      }
+      __syncwarp();
+      warp_sort_desc<CAP / 32>(k8, lane);
+#pragma unroll
+      for (int u = 0; u < CAP / 32; u++) {
+        key[u] = k8[u];
+        key[CAP / 32 + u] = 0ull;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < CAP / 32; u++) {
+        const int e = u * 32 + lane;
+        key[CAP / 32 + u] = e < npend ? pend[e] : 0ull;
+      }
+      __syncwarp();
+      warp_sort_desc<2 * CAP / 32>(key, lane);
     }
-    __syncwarp();
+    have_best = true;
     npend = 0;
-    warp_sort_desc<2 * CAP / 32>(key, lane);
     // truncate to ksel; the best value dropped here bounds everything dropped later as well
     unsigned long long kfirst = 0ull;  // first key beyond the cut (ksel < CAP always)
 #pragma unroll

@@ -72,9 +72,7 @@ class ItemSimilarityJob:
             return -1
         try:
             # PreparePreferenceMatrixJob on the GPU: the text goes to the device once, the events stay there
-            with open(args.input, "rb") as f:
-                text = f.read()
-            events = ingest.Events.parse(text, boolean_data=_bool(args.booleanData))
+            events = ingest.Events.parse_file(args.input, boolean_data=_bool(args.booleanData))
             prep = events.prepare(args.minPrefsPerUser)
             events.close()
             if prep.num_items == 0:

@@ -405,7 +405,10 @@ def _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_res
     peers = None
     try:
         with torch.cuda.stream(comp):
-            peers = PeerRows(ctx, plan, backend.bank.d, backend.bank.w, dtype, group)
+            try:
+                peers = PeerRows(ctx, plan, backend.bank.d, backend.bank.w, dtype, group)
+            except sk.N.NativeError:
+                return None
             N.check(N.lib().mb200_bank_normalize(backend.bank.handle, sk._DTYPES[dtype], C.c_void_p(peers.rows.data_ptr()),
                                                  C.c_void_p(peers.valid.data_ptr())), ctx.handle)
             kw = {}
@@ -465,7 +468,10 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
     if fused is None:
         fused = world > 1 and chunk_rows == 0 and isinstance(backend, GpuShardBackend)
     if fused and world > 1:
-        return _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_result, num_items)
+        out = _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_result, num_items)
+        if out is not None:
+            return out
+        # peer mappings are not available on this box (CUDA IPC refused): NCCL all-gather, then K3
     a_rows, a_valid = backend.normalized(dtype)
     a_cnt = backend.counters() if precision == "rescored" else None
     if world > 1 and chunk_rows > 0:
