@@ -264,3 +264,20 @@ def test_job_misuse(mb, ctx):
     idx, sim, cnt = job.finish()
     assert idx.shape == (256, 4)
     bank.close()
+
+
+@pytest.mark.parametrize("E,d,w,k", [(1, 2, 64, 3), (2, 1, 8, 5), (5, 20, 40, 4), (200, 24, 128, 7), (131, 3, 4100, 6)])
+def test_topk_edge_shapes(mb, ctx, E, d, w, k):
+    """one or two entities, k beyond the number of entities, tiny and non-multiple-of-64 widths, wide rows
+    (two-pass normalise), depths up to CountMinSketchConfig's 24"""
+    bank, ref = _make_bank(mb, ctx, E, d, w, 30 * E + 10, seed=E + d + w + k)
+    for precision in ("rescored", "tensor"):
+        idx, sim, cnt = bank.cosine_topk(k, precision=precision)
+        oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+        assert (cnt == ocnt).all()
+        if precision == "rescored":
+            assert (idx == oidx).all() and sim.tobytes() == osim.tobytes()
+        else:
+            m = oidx >= 0
+            assert np.allclose(np.sort(sim, axis=1), np.sort(osim, axis=1), rtol=2e-3, atol=0)
+    bank.close()
