@@ -37,7 +37,7 @@ ITEMS, USERS, ZIPF_S = 10_000_000, 1_000_000, 1.1
 ALGO_BYTES_PER_EVENT = 20 + DEPTH * 16   # 20 B event + d x (8 B read + 8 B write)
 C3_USERS, C3_ITEMS, C3_EVENTS, C3_WIDTH, C3_DEPTH, C3_K = 138_493, 26_744, 20_000_000, 4096, 4, 50
 C3_SEED = 20240003
-C3_CHUNK_ROWS = 1024       # rows per shard and all-gather chunk of the pipelined multi-GPU cosine step
+C3_CHUNKS = 4              # all-gather chunks per step of the pipelined multi-GPU cosine form
 METRIC = "sketch_updates_per_sec"
 UNIT = "events/s"
 
@@ -493,12 +493,13 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
     if world > 1:
         be = sim.GpuShardBackend(ctx)
         be.bank = bank
+        chunk_rows = (plan.rows_per_shard + C3_CHUNKS * 256 - 1) // (C3_CHUNKS * 256) * 256
 
         def step_piped():
             N.check(N.lib().mb200_bank_normalize(bank.handle, N.DTYPE_F16, C.c_void_p(a_rows.data_ptr()),
                                                  C.c_void_p(a_valid.data_ptr())), ctx.handle)
             return sim.pipelined_cosine(be, plan, a_rows, a_valid, C3_K, None, "f16", "tensor", None,
-                                        C3_CHUNK_ROWS, None)
+                                        chunk_rows, None)
 
         for _ in range(warmup):
             step_piped()
@@ -647,7 +648,7 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
             "ms_per_step_fused_pull_gather": fused_ms, "fused_equals_one_shot": fused_equal,
             "fused_k3_ms_per_launch": (fk3_ms / max(fk3_n, 1)) if (world > 1 and fk3_n) else None,
             "fused_error": fused_err,
-            "pipelined_chunk_rows": C3_CHUNK_ROWS if world > 1 else None, "steps": steps, "warmup": warmup, "n_gpus": world, "scaling": "strong",
+            "pipelined_chunk_rows": chunk_rows if world > 1 else None, "steps": steps, "warmup": warmup, "n_gpus": world, "scaling": "strong",
             "dtype": "f16 rows (x/||x|| * 2^12), f32 accumulate in TMEM; re-score in exact int64/f64",
             "config": {"workload": "configs[2]: MovieLens-20M-shaped synthetic (138493 users x 26744 items, 2e7 "
                                    "Zipf(1.1) events), sketch d=4 x W=4096, cosine top-50 per item",
