@@ -180,6 +180,9 @@ int mb200_id_to_index(mb200_ctx* ctx, const int64_t* ids, int64_t n, int32_t* ou
 int mb200_events_prepare(mb200_events* ev, int32_t min_prefs_per_user, mb200_prefs** out);
 int mb200_prefs_info(mb200_prefs* p, int64_t* n, int64_t* num_items, int64_t* num_users);
 int mb200_prefs_columns(mb200_prefs* p, int64_t** row, int64_t** user, float** pref); /* DEVICE */
+/* DEVICE column: a dense number 0..num_users-1 per surviving event's user -- the counter column of the
+ * exact measure (bank of depth 1, width num_users, hash parameters a = 1, b = 0) */
+int mb200_prefs_user_columns(mb200_prefs* p, int64_t** ucol);
 /* HOST tables of num_items entries: row -> itemID written to the output, row -> index */
 int mb200_prefs_tables(mb200_prefs* p, int64_t* item_id, int32_t* index_values);
 int mb200_prefs_destroy(mb200_prefs* p);

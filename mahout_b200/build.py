@@ -80,7 +80,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    _build_cli(force)
     return LIB
+
+
+CLI_SRC = os.path.join(CSRC, "cli_itemsimilarity.cpp")
+CLI_BIN = os.path.join(HERE, "bin", "mahout_b200_itemsimilarity")
+
+
+def _build_cli(force: bool = False) -> str:
+    """the native host-side driver (C++, C ABI only) next to the library it drives"""
+    os.makedirs(os.path.dirname(CLI_BIN), exist_ok=True)
+    stale = (force or not os.path.exists(CLI_BIN)
+             or os.path.getmtime(CLI_BIN) < max(os.path.getmtime(CLI_SRC), os.path.getmtime(LIB)))
+    if stale:
+        cxx = shutil.which("g++") or "g++"
+        cmd = [cxx, "-O2", "-std=c++17", "-Wall", CLI_SRC, "-o", CLI_BIN, "-L", HERE, "-lmahout_b200",
+               "-Wl,-rpath,$ORIGIN/.."]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {CLI_SRC}:\n{r.stdout}\n{r.stderr}")
+    return CLI_BIN
 
 
 if __name__ == "__main__":

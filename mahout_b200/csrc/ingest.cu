@@ -43,6 +43,7 @@ struct mb200_prefs {
   int64_t n = 0, num_items = 0, num_users = 0;
   long long* row = nullptr;   // dense row number of the event's item index
   long long* user = nullptr;
+  long long* ucol = nullptr;  // dense number 0..num_users-1 of the event's user (arbitrary but fixed order)
   float* pref = nullptr;
   std::vector<int64_t> item_id;       // row -> minimum itemID with that index
   std::vector<int32_t> index_values;  // row -> idToIndex value (ascending)
@@ -60,6 +61,7 @@ static void prefs_free(mb200_prefs* p) {
   if (!p) return;
   cudaFree(p->row);
   cudaFree(p->user);
+  cudaFree(p->ucol);
   cudaFree(p->pref);
   delete p;
 }
@@ -488,14 +490,16 @@ __global__ void __launch_bounds__(256) k_prep_flags(const PrepArgs a) {
     if (a.keep[t] && a.ucount[a.uslot[t]] < a.min_prefs) a.keep[t] = 0;
 }
 
-__global__ void __launch_bounds__(256) k_count_users(const int* __restrict__ ucount, unsigned long long slots,
-                                                     int min_prefs, unsigned long long* __restrict__ out) {
-  unsigned long long c = 0;
+// users that survive minPrefsPerUser get dense numbers 0..U-1 (the order is that of the atomics: any
+// numbering serves -- the numbers only name counter columns of the exact measure)
+__global__ void __launch_bounds__(256) k_number_users(const int* __restrict__ ucount, unsigned long long slots,
+                                                      int min_prefs, int* __restrict__ unum,
+                                                      unsigned long long* __restrict__ out) {
   for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < slots;
-       s += (unsigned long long)gridDim.x * blockDim.x)
-    c += (ucount[s] >= min_prefs && ucount[s] > 0) ? 1 : 0;
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+       s += (unsigned long long)gridDim.x * blockDim.x) {
+    const bool ok = ucount[s] >= min_prefs && ucount[s] > 0;
+    unum[s] = ok ? (int)atomicAdd(out, 1ull) : -1;
+  }
 }
 
 // occupied slots of the index table -> (index, min itemID) pairs, unordered
@@ -540,8 +544,9 @@ __global__ void __launch_bounds__(CT) k_keep_counts(const unsigned char* __restr
 __global__ void __launch_bounds__(CT) k_compact(const PrepArgs a, long long num_tiles,
                                                 const long long* __restrict__ tile_off,
                                                 const float* __restrict__ pref, const int* __restrict__ sorted_idx,
-                                                long long num_items, long long* __restrict__ out_row,
-                                                long long* __restrict__ out_user, float* __restrict__ out_pref) {
+                                                long long num_items, const int* __restrict__ unum,
+                                                long long* __restrict__ out_row, long long* __restrict__ out_user,
+                                                long long* __restrict__ out_ucol, float* __restrict__ out_pref) {
   __shared__ int s_w[CT / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -572,6 +577,7 @@ __global__ void __launch_bounds__(CT) k_compact(const PrepArgs a, long long num_
         }
         out_row[slot] = lo;
         out_user[slot] = a.user[t];
+        out_ucol[slot] = unum[a.uslot[t]];
         out_pref[slot] = pref[t];
         slot++;
       }
@@ -860,7 +866,7 @@ int mb200_events_prepare(mb200_events* ev, int32_t min_prefs_per_user, mb200_pre
   a.min_prefs = min_prefs_per_user;
   unsigned long long *d_nusers = nullptr, *d_nidx = nullptr;
   long long *d_counts = nullptr, *d_off = nullptr, *d_total = nullptr, *d_uid = nullptr;
-  int *d_uidx = nullptr, *d_sorted = nullptr;
+  int *d_uidx = nullptr, *d_sorted = nullptr, *d_unum = nullptr;
   const long long num_tiles = ceil_div64(n, CT * CPT);
 #define PM_TRY(expr)                                                                         \
   do {                                                                                       \
@@ -882,6 +888,7 @@ int mb200_events_prepare(mb200_events* ev, int32_t min_prefs_per_user, mb200_pre
   PM_TRY(sc.get(&a.pslot, (size_t)n));
   PM_TRY(sc.get(&a.keep, (size_t)n));
   PM_TRY(sc.get(&d_nusers, 1));
+  PM_TRY(sc.get(&d_unum, (size_t)slots + 1));
   PM_TRY(sc.get(&d_nidx, 1));
   PM_TRY(sc.get(&d_counts, (size_t)num_tiles));
   PM_TRY(sc.get(&d_off, (size_t)num_tiles));
@@ -900,7 +907,7 @@ int mb200_events_prepare(mb200_events* ev, int32_t min_prefs_per_user, mb200_pre
     k_prep_insert<<<grid, 256, 0, ctx->stream>>>(a);
     k_prep_mark<<<grid, 256, 0, ctx->stream>>>(a);
     k_prep_flags<<<grid, 256, 0, ctx->stream>>>(a);
-    k_count_users<<<grid_for(ctx, (long long)((slots + 1 + 255) / 256), 16), 256, 0, ctx->stream>>>(a.ucount, slots + 1, min_prefs_per_user, d_nusers);
+    k_number_users<<<grid_for(ctx, (long long)((slots + 1 + 255) / 256), 16), 256, 0, ctx->stream>>>(a.ucount, slots + 1, min_prefs_per_user, d_unum, d_nusers);
   }
   ctx->launches += 4;
   PM_TRY(cudaGetLastError());
@@ -943,9 +950,11 @@ int mb200_events_prepare(mb200_events* ev, int32_t min_prefs_per_user, mb200_pre
     PM_TRY(cudaMalloc(&pm->row, (size_t)total * 8));
     PM_TRY(cudaMalloc(&pm->user, (size_t)total * 8));
     PM_TRY(cudaMalloc(&pm->pref, (size_t)total * 4));
+    PM_TRY(cudaMalloc(&pm->ucol, (size_t)total * 8));
     {
       ProfScope prof(ctx, MB200_K_PREPARE);
-      k_compact<<<cgrid, CT, 0, ctx->stream>>>(a, num_tiles, d_off, ev->pref, d_sorted, (long long)nidx, pm->row, pm->user, pm->pref);
+      k_compact<<<cgrid, CT, 0, ctx->stream>>>(a, num_tiles, d_off, ev->pref, d_sorted, (long long)nidx, d_unum, pm->row, pm->user,
+                                               pm->ucol, pm->pref);
     }
     ctx->launches++;
     PM_TRY(cudaGetLastError());
@@ -969,6 +978,12 @@ int mb200_prefs_columns(mb200_prefs* p, int64_t** row, int64_t** user, float** p
   if (row) *row = (int64_t*)p->row;
   if (user) *user = (int64_t*)p->user;
   if (pref) *pref = p->pref;
+  return MB200_OK;
+}
+
+int mb200_prefs_user_columns(mb200_prefs* p, int64_t** ucol) {
+  if (!p || !ucol) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_prefs_user_columns: NULL argument");
+  *ucol = (int64_t*)p->ucol;
   return MB200_OK;
 }
 

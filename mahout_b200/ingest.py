@@ -177,20 +177,24 @@ class PreparedPrefs:
                                            self.index_values.ctypes.data_as(C.c_void_p)), ctx.handle)
         r, u, p = C.c_void_p(), C.c_void_p(), C.c_void_p()
         N.check(N.lib().mb200_prefs_columns(handle, C.byref(r), C.byref(u), C.byref(p)), ctx.handle)
+        uc = C.c_void_p()
+        N.check(N.lib().mb200_prefs_user_columns(handle, C.byref(uc)), ctx.handle)
         if self.n:
             d = ctx.device
             self.row, self.user, self.pref = (_view(r.value, self.n, d, "<i8"), _view(u.value, self.n, d, "<i8"),
                                               _view(p.value, self.n, d, "<f4"))
+            self.ucol = _view(uc.value, self.n, d, "<i8")       # dense user number (exact measure's column)
         else:
             import torch
             dev = f"cuda:{ctx.device}"
             self.row = torch.empty(0, dtype=torch.int64, device=dev)
             self.user = torch.empty(0, dtype=torch.int64, device=dev)
             self.pref = torch.empty(0, dtype=torch.float32, device=dev)
+            self.ucol = torch.empty(0, dtype=torch.int64, device=dev)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self.ctx._h is not None:
-            self.row = self.user = self.pref = None
+            self.row = self.user = self.pref = self.ucol = None
             try:
                 N.lib().mb200_prefs_destroy(self._h)
             except Exception:

@@ -82,7 +82,8 @@ class ItemSimilarityJob:
                 if args.similarityClassname in EXACT_MEASURES:
                     idx, s, cnt = sim.exact_item_similarity(
                         prep.row, prep.user, prep.pref, prep.num_items, k=args.maxSimilaritiesPerItem,
-                        threshold=args.threshold, frac_bits=args.fracBits, precision=args.precision)
+                        threshold=args.threshold, frac_bits=args.fracBits, precision=args.precision,
+                        ucol=prep.ucol, num_users=prep.num_users)
                 else:
                     idx, s, cnt = sim.item_similarity(
                         prep.row, prep.user, prep.pref, prep.num_items, k=args.maxSimilaritiesPerItem,
@@ -92,7 +93,7 @@ class ItemSimilarityJob:
             prep.close()
             with open(args.output, "w") as out:
                 for a, b, v in pairs:
-                    out.write(f"{a}\t{b}\t{v!r}\n")
+                    out.write(f"{a}\t{b}\t{sim.java_double_to_string(v)}\n")
         except Exception as e:   # AbstractJob: failures surface as a non-zero exit code
             print(f"itemsimilarity failed: {e}", file=sys.stderr)
             return -1

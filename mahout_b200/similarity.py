@@ -30,6 +30,34 @@ DEFAULT_MIN_PREFS_PER_USER = 1
 # ------------------------------------------------------------------------------------------------
 # ingest: PreparePreferenceMatrixJob runs on the GPU (mahout_b200/ingest.py over csrc/ingest.cu)
 # ------------------------------------------------------------------------------------------------
+def java_double_to_string(v: float) -> str:
+    """Double.toString: the shortest digits that round-trip, decimal notation for 1e-3 <= |v| < 1e7, otherwise
+    computerised scientific notation (`9.765625E-4`); what TextOutputFormat writes for the similarity."""
+    import decimal
+    import math
+    if math.isnan(v):
+        return "NaN"
+    if math.isinf(v):
+        return "Infinity" if v > 0 else "-Infinity"
+    if v == 0.0:
+        return "-0.0" if math.copysign(1.0, v) < 0 else "0.0"
+    sign, digits, exp = decimal.Decimal(repr(float(v))).as_tuple()
+    digits = "".join(map(str, digits))
+    stripped = digits.rstrip("0") or "0"
+    exp += len(digits) - len(stripped)
+    digits = stripped
+    exp10 = len(digits) + exp - 1
+    if -3 <= exp10 < 7:
+        if exp10 >= 0:
+            digits = digits.ljust(exp10 + 1, "0")
+            out = digits[:exp10 + 1] + "." + (digits[exp10 + 1:] or "0")
+        else:
+            out = "0." + "0" * (-exp10 - 1) + digits
+    else:
+        out = digits[0] + "." + (digits[1:] or "0") + "E" + str(exp10)
+    return ("-" if sign else "") + out
+
+
 def most_similar_item_pairs(idx, sim, cnt, item_id=None):
     """MostSimilarItemPairsMapper / Reducer: per-row top-k entries -> (minID, maxID) keys, the
     duplicate of a symmetric pair collapses to one value; ordered by (a, b)
@@ -65,7 +93,7 @@ def item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_SIMILA
 
 def exact_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM,
                           threshold: float | None = None, frac_bits: int = 1, dtype: str = "f16",
-                          precision: str = "rescored", ctx=None):
+                          precision: str = "rescored", ctx=None, ucol=None, num_users: int | None = None):
     """RowSimilarityJob with CosineSimilarity, exactly (RowSimilarityJob.java:478-559; no sketch, no
     --maxPrefs down-sampling): the users are renumbered 0..U-1 and every user owns one counter column
     (depth 1, width U, identity hash), so K1 writes the item x user matrix, K3 computes all pairs on the
@@ -74,9 +102,11 @@ def exact_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MAX_
     import torch
     ctx = ctx or sk.default_context()
     dev = f"cuda:{ctx.device}"
-    user_t = torch.as_tensor(user).to(dev)
-    users, col = torch.unique(user_t, return_inverse=True)            # plumbing: dense user numbers
-    width = max(int(users.numel()), 1)
+    if ucol is not None:
+        col, width = ucol, max(int(num_users), 1)                     # dense user numbers from Events.prepare
+    else:
+        users, col = torch.unique(torch.as_tensor(user).to(dev), return_inverse=True)      # plumbing
+        width = max(int(users.numel()), 1)
     bank = sk.SketchBank(num_items, width, 1, sk.IdentityHashBuilder(), frac_bits, ctx)
     try:
         bank.update(torch.as_tensor(row).to(dev), col, torch.as_tensor(pref).to(dev))

@@ -134,3 +134,31 @@ def test_jni_glue_type_checks():
     subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-parameter",
                            "-I", os.path.join(ROOT, "tests", "jni_stub"), "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "jni", "mahout_b200_jni.c")])
+
+
+def test_native_cli_builds_and_rejects_bad_arguments(tmp_path):
+    """mahout_b200_itemsimilarity (C++ host driver over the C ABI): AbstractJob's -1 on bad arguments, and no
+    CPU fallback when there is no device."""
+    import subprocess
+    import torch
+    from mahout_b200 import build
+    build.build()
+    exe = build.CLI_BIN
+    assert os.path.exists(exe)
+    p = tmp_path / "in.csv"
+    p.write_text("1,2,1\n")
+    out = str(tmp_path / "o")
+    assert subprocess.run([exe]).returncode == 255                                         # missing required options
+    assert subprocess.run([exe, "-i", str(p), "-o", out, "-s", "SIMILARITY_TANIMOTO_COEFFICIENT"]).returncode == 255
+    assert subprocess.run([exe, "-i", str(p), "-o", out, "-s", "SIMILARITY_COSINE", "-m", "0"]).returncode == 255
+    assert subprocess.run([exe, "-i", str(p), "-o", out, "-s", "SIMILARITY_COSINE", "--bogus", "1"]).returncode == 255
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "-i", str(p), "-o", out, "-s", "SIMILARITY_COSINE"], capture_output=True, text=True)
+        assert r.returncode == 255 and "no CPU fallback" in r.stderr
+        assert not os.path.exists(out)
+
+
+def test_java_double_to_string():
+    from mahout_b200.similarity import java_double_to_string as j
+    assert [j(v) for v in (0.4472135954999579, 1.0, 0.001, 0.0009765625, 1e7, 9999999.0, 1e-10, 100.0, -3.25, 0.0)] == \
+        ["0.4472135954999579", "1.0", "0.001", "9.765625E-4", "1.0E7", "9999999.0", "1.0E-10", "100.0", "-3.25", "0.0"]

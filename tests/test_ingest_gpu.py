@@ -169,3 +169,24 @@ def test_item_similarity_job_from_text_equals_oracle_pipeline(ing, tmp_path):
     orc.bank_update(ref, d, w, a, b, pm.row, pm.user, pm.pref)
     oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
     assert got == orc.most_similar_item_pairs(oidx, osim, ocnt, pm.item_id)
+
+
+@pytest.mark.parametrize("measure", ["SIMILARITY_COSINE", "SIMILARITY_SKETCH_COSINE"])
+def test_native_cli_equals_python_job(tmp_path, measure):
+    """the C++ host driver (mahout_b200_itemsimilarity) and the Python mirror write the same file, byte for byte"""
+    import subprocess
+    from mahout_b200 import build
+    from mahout_b200.itemsimilarity import ItemSimilarityJob
+    rng = np.random.Generator(np.random.PCG64(18))
+    n = 20000
+    lines = [f"{u}\t{i * 3}\t{p}" for u, i, p in zip(rng.integers(1, 400, n), rng.integers(1, 250, n),
+                                                     rng.integers(1, 11, n) * 0.5)]
+    inp = tmp_path / "prefs.tsv"
+    inp.write_text("\n".join(lines) + "\n")
+    flags = ["-s", measure, "-m", "7", "-mp", "2", "--sketchWidth", "512", "--sketchDepth", "3", "--threshold", "0.05"]
+    py_out, cc_out = tmp_path / "py.tsv", tmp_path / "cc.tsv"
+    assert ItemSimilarityJob().run(["-i", str(inp), "-o", str(py_out), *flags]) == 0
+    r = subprocess.run([build.CLI_BIN, "-i", str(inp), "-o", str(cc_out), *flags], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert py_out.read_text() == cc_out.read_text()
+    assert len(py_out.read_text().splitlines()) > 100
