@@ -461,7 +461,7 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
             br, bv = a_rows.unsqueeze(0), a_valid.unsqueeze(0)
         return cosine_topk_blocks(ctx, a_rows, a_valid, br, bv, C3_DEPTH, C3_WIDTH, C3_K, a_id=(world, rank),
                                   b_id=b_id, dtype="f16", precision=precision,
-                                  a_counters=a_cnt if precision == "rescored" else None, b_counters=b_cnt)
+                                  a_counters=a_cnt if precision != "tensor" else None, b_counters=b_cnt if precision != "tensor" else None)
 
     def barrier():
         if world > 1:

@@ -47,7 +47,11 @@ extern "C" {
 /* cosine precision modes */
 #define MB200_PRECISION_TENSOR 0   /* similarities straight from the FP32 tensor accumulators      */
 #define MB200_PRECISION_RESCORED 1 /* tensor cores select k+margin candidates, which are re-scored
-                                      from the hi+lo split rows in FP64 (default)                  */
+                                      exactly from the integer counters: similarities bit-equal to
+                                      DoubleCountMinSketch.cosine, top-k sets exact (default)      */
+#define MB200_PRECISION_CERTIFIED 2 /* top-k SETS exact, similarities from the tensor cores (<= 1e-3
+                                      relative): only the candidates whose membership the tensor
+                                      values cannot decide are re-scored exactly                  */
 
 typedef struct mb200_ctx mb200_ctx;
 typedef struct mb200_bank mb200_bank;
@@ -119,6 +123,8 @@ int mb200_bank_destroy(mb200_bank* bank);
 int mb200_bank_clear(mb200_bank* bank);
 /* device pointer of the raw int64 counters (for an NCCL all-reduce of replica sketches) */
 int mb200_bank_counters(mb200_bank* bank, void** device_ptr, int64_t* cells);
+/* 64-byte CUDA IPC handle of the counters: another rank maps them with mb200_peer_open */
+int mb200_bank_ipc_handle(mb200_bank* bank, void* ipc_handle_64_bytes);
 
 /* DoubleCountMinSketch.update(key, increment) for n events (DoubleCountMinSketch.java:72-80):
  * C[entity[t]][i][h_i(key[t])] += inc[t] for i < d.  `entity` may be NULL when entities == 1.
@@ -246,6 +252,11 @@ typedef struct mb200_cosine_args {
    * of the B row (block g, row l) -> g * tiles_per_block * block_n + l */
   float* dense_out;
   int64_t dense_ld;
+  /* MB200_PRECISION_CERTIFIED across GPUs: instead of one gathered b_counters array, a HOST array of
+   * b_blocks DEVICE pointers, block g -> that shard's counters [b_count][d][width] (the local bank, or
+   * a peer's bank mapped with mb200_bank_ipc_handle + mb200_peer_open).  Only the handful of
+   * candidates the tensor values cannot decide are read through them.  NULL otherwise. */
+  const int64_t* const* b_counter_blocks;
 } mb200_cosine_args;
 
 int mb200_cosine_topk(mb200_ctx* ctx, const mb200_cosine_args* args);

@@ -16,7 +16,7 @@ ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_INEXACT, ERR_RANGE = -1, -2, -3, -4, -5
 ERR_NO_DEVICE, ERR_CM_DELTA, ERR_CM_EPSILON, ERR_UNSUPPORTED = -6, -7, -8, -9
 MEM_HOST, MEM_DEVICE = 0, 1
 DTYPE_F16, DTYPE_BF16 = 0, 1
-PRECISION_TENSOR, PRECISION_RESCORED = 0, 1
+PRECISION_TENSOR, PRECISION_RESCORED, PRECISION_CERTIFIED = 0, 1, 2
 K_UPDATE, K_NORMALIZE, K_COSINE, K_RESCORE, K_PARSE, K_PREPARE = 0, 1, 2, 3, 4, 5
 MAX_DEPTH = 32
 
@@ -51,6 +51,7 @@ class CosineArgs(C.Structure):
         ("a_counters", C.c_void_p), ("b_counters", C.c_void_p),
         ("out_idx", C.c_void_p), ("out_sim", C.c_void_p), ("out_cnt", C.c_void_p),
         ("dense_out", C.c_void_p), ("dense_ld", C.c_int64),
+        ("b_counter_blocks", C.c_void_p),
     ]
 
 
@@ -85,6 +86,7 @@ _PROTOS = {
     "mb200_bank_create_params": (C.c_int, [vp, i64, i32, i32, vp, vp, i32, C.POINTER(vp)]),
     "mb200_bank_destroy": (C.c_int, [vp]),
     "mb200_bank_clear": (C.c_int, [vp]),
+    "mb200_bank_ipc_handle": (C.c_int, [vp, vp]),
     "mb200_bank_counters": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
     "mb200_bank_update": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
     "mb200_bank_update_f64": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),

@@ -605,6 +605,7 @@ struct MergeParams {
   int32_t* out_cnt;
   // RESCORED outputs
   uint32_t* cand_id;       // [a_count][CAP]
+  float* cand_val;         // [a_count][CAP] scaled tensor values of the candidates (CERTIFIED), or NULL
   int32_t* cand_cnt;       // [a_count]
   float* cand_bound;       // [a_count] (scaled tensor value; -inf = nothing was ever dropped)
 };
@@ -716,6 +717,7 @@ __global__ void __launch_bounds__(256) k_merge(const MergeParams p) {
       const int e = u * 32 + lane;
       const bool have = key[u] != 0ull;
       p.cand_id[(size_t)r * CAP + e] = have ? ~(uint32_t)key[u] : 0xFFFFFFFFu;
+      if (p.cand_val) p.cand_val[(size_t)r * CAP + e] = have ? __uint_as_float(ord2f((uint32_t)(key[u] >> 32))) : 0.0f;
       n += __popc(__ballot_sync(0xffffffffu, have));
     }
     if (lane == 0) {
@@ -752,12 +754,14 @@ __global__ void __launch_bounds__(256) k_merge(const MergeParams p) {
 struct RescoreParams {
   const long long* a_counters;  // [a_count][d][W]
   const long long* b_counters;  // [blocks][b_count][d][W]
+  const long long* const* b_blocks_ptr;  // or: one pointer per block (peer-mapped banks), each [b_count][d][W]
   int64_t a_count, b_count;
   int32_t d, W, blocks;
   uint32_t a_id_mul, a_id_off, b_id_mul, b_id_add;
   const uint32_t* cand_id;
   const int32_t* cand_cnt;
   const float* cand_bound;
+  const float* cand_val;       // CERTIFIED: tensor values of the candidates
   float inv_scale2;
   float eps_rel;               // relative error bound of the tensor-core values
   int32_t k;
@@ -779,12 +783,18 @@ __device__ __forceinline__ void b_locate(const RescoreParams& p, uint32_t id, lo
   }
 }
 
+// first counter of sketch row (block g, local row l, depth i)
+__device__ __forceinline__ const long long* b_row(const RescoreParams& p, long long g, long long l, int i) {
+  const long long* base = p.b_blocks_ptr ? p.b_blocks_ptr[g] : p.b_counters + (size_t)g * p.b_count * p.d * p.W;
+  return base + ((size_t)l * p.d + i) * p.W;
+}
+
 #define TWO53 9007199254740992.0
 #define JAVA_MAX_DOUBLE 1.7976931348623157e308
 
 // Ordering, certification and output of one row's re-scored candidates; executed by one warp.
 __device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long r, int n, const double* s_min,
-                                               int bad_flag, int lane) {
+                                               int bad_flag, int lane, bool certified_elsewhere = false) {
   // warp 0: order the candidates by (exact sim desc, index asc), certify, write the top-k
   double sim[CAP / 32];
   uint32_t idv[CAP / 32];
@@ -857,7 +867,7 @@ __device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long
     // k-th exact value clears that.
     const float b = p.cand_bound[r];
     int flag = bad_flag;
-    if (b > -INFINITY) {
+    if (b > -INFINITY && !certified_elsewhere) {
       const double ub = (double)(b * p.inv_scale2) * (1.0 + (double)p.eps_rel) + (double)p.eps_rel * 1e-3;
       if (!(kth > ub)) flag = 1;
     }
@@ -907,7 +917,7 @@ __global__ void __launch_bounds__(256) k_rescore(const RescoreParams p) {
         const uint32_t id = p.cand_id[(size_t)r * CAP + c];
         long long g, l;
         b_locate(p, id, g, l);
-        const long long* brow = p.b_counters + (((size_t)g * p.b_count + l) * p.d + i) * p.W + j0;
+        const long long* brow = b_row(p, g, l, i) + j0;
         long long bb = 0, ab = 0;
         double mag = 0.0;
         int badb = 0;
@@ -962,6 +972,166 @@ __global__ void __launch_bounds__(256) k_rescore(const RescoreParams p) {
     __syncthreads();
   }
   if (warp == 0) rescore_finish(p, r, n, s_min, s_bad, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b, CERTIFIED form: the top-k SET is exact, the similarities are the tensor-core values (<= 2^-10
+// relative) -- the contract of the north star at a fraction of the full re-score.  With value bounds
+// L = v(1-eps), U = v(1+eps) a candidate is surely in when fewer than k others can beat it and
+// surely out when k others surely do; in the sorted list only the entries
+//     rank <  k with v <= v[k]   / (1 - 2 eps)      (v[k]   = the (k+1)-th tensor value)
+//     rank >= k with v >= v[k-1] / (1 + 2 eps)      (v[k-1] = the k-th)
+// are uncertain -- usually none or a handful -- and only those (plus entries within 2 eps of the
+// threshold) are re-scored exactly from the int64 counters.  If the uncertain band reaches what was
+// dropped earlier (bound) the row takes the exact full-row path.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_certify(const RescoreParams p) {
+  __shared__ long long s_a[RESCORE_SEG];
+  __shared__ double s_fin[CAP];                // final value per candidate (tensor or exact)
+  __shared__ double s_min[CAP];                // exact running min of the selected candidates
+  __shared__ long long s_ab[CAP], s_bb[CAP];
+  __shared__ double s_mag[CAP];
+  __shared__ int s_sel[CAP];                   // candidate slots that need the exact value
+  __shared__ double s_red[8];
+  __shared__ long long s_redi[8];
+  __shared__ int s_bad, s_nsel, s_flag;
+  const long long r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.cand_cnt[r];
+  const float* val = p.cand_val + (size_t)r * CAP;   // sorted descending
+  if (tid == 0) {
+    s_bad = 0;
+    s_nsel = 0;
+    s_flag = 0;
+  }
+  __syncthreads();
+  const float e2 = 2.0f * p.eps_rel;
+  const int k = p.k;
+  const float vk = n > 0 ? val[min(k, n) - 1] : 0.0f;                 // k-th (or last) tensor value
+  const float vk1 = n > k ? val[k] : -INFINITY;                       // (k+1)-th
+  const float band_hi = vk1 / (1.0f - e2), band_lo = vk / (1.0f + e2);
+  const float thr = (float)(p.threshold / (double)p.inv_scale2);      // threshold in the scaled domain
+  for (int c = tid; c < CAP; c += blockDim.x) {
+    s_min[c] = JAVA_MAX_DOUBLE;
+    if (c < n) {
+      const float v = val[c];
+      s_fin[c] = (double)(v * p.inv_scale2);
+      const bool near_cut = (c < k && v <= band_hi) || (c >= k && v >= band_lo);
+      const bool near_thr = p.threshold > 0.0 && fabsf(v - thr) <= e2 * thr + 1e-30f;
+      if (near_cut || near_thr) s_sel[atomicAdd(&s_nsel, 1)] = c;
+    }
+  }
+  if (tid == 0) {
+    // everything dropped before the merge must be surely out
+    const float b = p.cand_bound[r];
+    if (b > -INFINITY && n >= k && !(b < band_lo)) s_flag = 1;
+    if (b > -INFINITY && n < k) s_flag = 1;
+  }
+  __syncthreads();
+  const int nsel = s_nsel;
+  if (nsel == 0 && !s_flag) {
+    // nothing is uncertain: the merged order (tensor value desc, index asc) is the answer
+    if (warp == 0) {
+      int admitted = 0;
+      for (int e0 = 0; e0 < k; e0 += 32) {
+        const int e = e0 + lane;
+        const bool ok = e < n && e < k && s_fin[e < CAP ? e : 0] >= p.threshold && s_fin[e < CAP ? e : 0] > 4.9e-324;
+        if (e < k) {
+          p.out_idx[(size_t)r * k + e] = ok ? (long long)p.cand_id[(size_t)r * CAP + e] : -1LL;
+          p.out_sim[(size_t)r * k + e] = ok ? s_fin[e] : 0.0;
+        }
+        admitted += __popc(__ballot_sync(0xffffffffu, ok));
+      }
+      if (lane == 0) {
+        p.out_cnt[r] = admitted;
+        p.row_flag[r] = 0;
+      }
+    }
+    return;
+  }
+  const long long* arow = p.a_counters + (size_t)r * p.d * p.W;
+  for (int i = 0; i < p.d && nsel > 0 && !s_flag; i++) {
+    for (int c = tid; c < nsel; c += blockDim.x) {
+      s_ab[c] = 0;
+      s_bb[c] = 0;
+      s_mag[c] = 0.0;
+    }
+    long long aa = 0;
+    double amag = 0.0;
+    int bad = 0;
+    for (int j0 = 0; j0 < p.W; j0 += RESCORE_SEG) {
+      const int seg = min(RESCORE_SEG, p.W - j0);
+      __syncthreads();
+      for (int j = tid; j < seg; j += blockDim.x) {
+        const long long x = arow[(size_t)i * p.W + j0 + j];
+        s_a[j] = x;
+        if (x >= (1LL << 31) || x <= -(1LL << 31)) bad = 1;
+        aa += x * x;
+        amag += (double)x * (double)x;
+      }
+      __syncthreads();
+      for (int c = warp; c < nsel; c += 8) {
+        const uint32_t id = p.cand_id[(size_t)r * CAP + s_sel[c]];
+        long long g, l;
+        b_locate(p, id, g, l);
+        const long long* brow = b_row(p, g, l, i) + j0;
+        long long bb = 0, ab = 0;
+        double mag = 0.0;
+        int badb = 0;
+        for (int j = lane; j < seg; j += 32) {
+          const long long y = __ldg(brow + j);
+          const long long x = s_a[j];
+          if (y >= (1LL << 31) || y <= -(1LL << 31)) badb = 1;
+          bb += y * y;
+          ab += x * y;
+          mag += fabs((double)y * (double)y) + fabs((double)x * (double)y);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          bb += __shfl_xor_sync(0xffffffffu, bb, o);
+          ab += __shfl_xor_sync(0xffffffffu, ab, o);
+          mag += __shfl_xor_sync(0xffffffffu, mag, o);
+          badb |= __shfl_xor_sync(0xffffffffu, badb, o);
+        }
+        if (lane == 0) {
+          s_bb[c] += bb;
+          s_ab[c] += ab;
+          s_mag[c] += mag;
+          if (badb) s_bad = 1;
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      aa += __shfl_xor_sync(0xffffffffu, aa, o);
+      amag += __shfl_xor_sync(0xffffffffu, amag, o);
+    }
+    if (lane == 0) {
+      s_redi[warp] = aa;
+      s_red[warp] = amag;
+    }
+    if (bad) s_bad = 1;
+    __syncthreads();
+    long long AA = 0;
+    double AAm = 0.0;
+    for (int w = 0; w < 8; w++) {
+      AA += s_redi[w];
+      AAm += s_red[w];
+    }
+    if (AAm >= TWO53 * 0.5 && tid == 0) s_bad = 1;
+    const double sqa = sqrt((double)AA);
+    for (int c = tid; c < nsel; c += blockDim.x) {
+      if (s_mag[c] >= TWO53 * 0.5) s_bad = 1;
+      const double den = __dmul_rn(sqa, sqrt((double)s_bb[c]));
+      if (den != 0.0) {
+        const double cs = __ddiv_rn((double)s_ab[c], den);
+        s_min[c] = cs < s_min[c] ? cs : s_min[c];
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int c = tid; c < nsel; c += blockDim.x) s_fin[s_sel[c]] = s_min[c];   // JAVA_MAX_DOUBLE = not comparable
+  __syncthreads();
+  if (warp == 0) rescore_finish(p, r, n, s_fin, s_bad | s_flag, lane, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1102,7 +1272,7 @@ __global__ void __launch_bounds__(256) k_exact_rows(const RescoreParams p, const
   double* out = scratch + (size_t)blockIdx.x * total_cols;
   for (long long col = threadIdx.x; col < total_cols; col += blockDim.x) {
     const long long g = col / p.b_count, l = col % p.b_count;
-    const long long* brow = p.b_counters + ((size_t)g * p.b_count + l) * p.d * p.W;
+    const long long* brow = b_row(p, g, l, 0);
     double mn = JAVA_MAX_DOUBLE;
     for (int i = 0; i < p.d; i++) {
       double va = 0.0, vb = 0.0, vab = 0.0;
@@ -1326,7 +1496,8 @@ static double now_ms() {
 struct mb200_cosine_job {
   mb200_ctx* ctx = nullptr;
   mb200_cosine_args a;           // begin arguments (A side, shape, k, threshold, ...)
-  bool rescored = false;
+  bool rescored = false;   // candidates are re-scored from the counters (RESCORED and CERTIFIED)
+  bool certified = false;
   int ksel = 0, BN = 256, num_m = 0, ld = 0;
   float scale2 = 1.f, eps_rel = 0.f;
   uint32_t* row_thr = nullptr;               // [num_m * BM], job-owned
@@ -1361,13 +1532,14 @@ static int job_begin_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t w
   if (a->k <= 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: k must be positive (got %d)", a->k);
   if (a->dtype != MB200_DTYPE_F16 && a->dtype != MB200_DTYPE_BF16)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad dtype %d", a->dtype);
-  if (a->precision != MB200_PRECISION_TENSOR && a->precision != MB200_PRECISION_RESCORED)
+  if (a->precision != MB200_PRECISION_TENSOR && a->precision != MB200_PRECISION_RESCORED &&
+      a->precision != MB200_PRECISION_CERTIFIED)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: bad precision %d", a->precision);
   if (a->a_id_mul <= 0 || a->a_id_off < 0 || (a->a_count - 1) * a->a_id_mul + a->a_id_off >= 0xFFFFFFFFLL)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: index mapping out of the 32-bit range");
   if (a->block_n != 0 && a->block_n != 128 && a->block_n != 256)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: block_n must be 0, 128 or 256");
-  const bool rescored = a->precision == MB200_PRECISION_RESCORED;
+  const bool rescored = a->precision != MB200_PRECISION_TENSOR;
   // candidates kept per row: k + margin, at most CAP - 64
   const int margin = rescored ? std::max(14, a->k / 4) : 0;
   int ksel = (a->k + margin + 31) / 32 * 32;
@@ -1379,6 +1551,7 @@ static int job_begin_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t w
   j->ctx = ctx;
   j->a = *a;
   j->rescored = rescored;
+  j->certified = a->precision == MB200_PRECISION_CERTIFIED;
   j->ksel = ksel;
   j->BN = a->block_n == 128 ? 128 : 256;
   j->num_m = (int)((a->a_count + BM - 1) / BM);
@@ -1708,8 +1881,9 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: NULL pointer argument");
   if (!j->pending) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_finish: nothing was pushed");
   const bool rescored = j->rescored;
-  if (rescored && (!fin->a_counters || !fin->b_counters))
-    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: MB200_PRECISION_RESCORED needs a_counters and b_counters");
+  if (rescored && (!fin->a_counters || (!fin->b_counters && !(j->certified && fin->b_counter_blocks))))
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG,
+                      "mb200_cosine_topk: MB200_PRECISION_RESCORED needs a_counters and b_counters (CERTIFIED: or b_counter_blocks)");
   bool contiguous = false;
   if (rescored) {
     if (fin->b_count <= 0 || fin->b_blocks <= 0)
@@ -1728,14 +1902,16 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
   const int64_t total_b = fin->b_count * fin->b_blocks;
 
   // merge (+ re-score)
-  DevBuf d_cand, d_ccnt, d_cbound, d_flag, d_fcount;
+  DevBuf d_cand, d_ccnt, d_cbound, d_flag, d_fcount, d_cval;
   if (rescored) {
     MB_CHECK(d_cand.alloc(ws, (size_t)a->a_count * CAP * sizeof(uint32_t)));
     MB_CHECK(d_ccnt.alloc(ws, (size_t)a->a_count * sizeof(int32_t)));
     MB_CHECK(d_cbound.alloc(ws, (size_t)a->a_count * sizeof(float)));
     MB_CHECK(d_flag.alloc(ws, (size_t)a->a_count * sizeof(int32_t)));
     MB_CHECK(d_fcount.alloc(ws, 2 * sizeof(int32_t)));
+    MB_CHECK(d_cval.alloc(ws, j->certified ? (size_t)a->a_count * CAP * sizeof(float) : 4));
     MB_CUDA(ctx, cudaMemsetAsync(d_fcount.p, 0, 2 * sizeof(int32_t), ctx->stream));
+    j->mp.cand_val = j->certified ? (float*)d_cval.p : nullptr;
     j->mp.cand_id = (uint32_t*)d_cand.p;
     j->mp.cand_cnt = (int32_t*)d_ccnt.p;
     j->mp.cand_bound = (float*)d_cbound.p;
@@ -1750,6 +1926,15 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       memset(&rp, 0, sizeof(rp));
       rp.a_counters = (const long long*)fin->a_counters;
       rp.b_counters = (const long long*)fin->b_counters;
+      DevBuf d_bptr;
+      if (j->certified && fin->b_counter_blocks) {
+        // peer-mapped banks: the few uncertain candidates are read from their owners over NVLink
+        MB_CHECK(d_bptr.alloc(ws, (size_t)fin->b_blocks * sizeof(void*)));
+        MB_CUDA(ctx, cudaMemcpyAsync(d_bptr.p, fin->b_counter_blocks, (size_t)fin->b_blocks * sizeof(void*),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        rp.b_blocks_ptr = (const long long* const*)d_bptr.p;
+        rp.b_counters = nullptr;
+      }
       rp.a_count = a->a_count;
       rp.b_count = fin->b_count;
       rp.d = a->depth;
@@ -1771,6 +1956,11 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       rp.out_cnt = fin->out_cnt;
       rp.row_flag = (int32_t*)d_flag.p;
       rp.flag_count = (int32_t*)d_fcount.p;
+      rp.cand_val = mp.cand_val;
+      if (j->certified) {
+        k_certify<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp);
+        ctx->launches++;
+      } else {
       // narrow (int32) copies + per-row statistics; the generic int64 kernel is kept for banks whose
       // counters do not fit 31 bits
       const bool same = fin->a_counters == fin->b_counters && fin->b_blocks == 1 && a->a_count == fin->b_count;
@@ -1814,6 +2004,7 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       else
         k_rescore<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp);
       ctx->launches++;
+      }
       int32_t nflag = 0;
       MB_CUDA(ctx, cudaMemcpyAsync(&nflag, d_fcount.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1868,8 +2059,8 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t
     return mb200_fail(ctx, MB200_ERR_BAD_ARG,
                       "mb200_cosine_topk: B indices must be contiguous blocks (mul=1, add=b_count) or interleaved "
                       "shards (mul=b_blocks, add=1)");
-  if (a->precision == MB200_PRECISION_RESCORED && (!a->a_counters || !a->b_counters))
-    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: MB200_PRECISION_RESCORED needs a_counters and b_counters");
+  if (a->precision != MB200_PRECISION_TENSOR && (!a->a_counters || !a->b_counters))
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: MB200_PRECISION_RESCORED / _CERTIFIED need a_counters and b_counters");
   mb200_cosine_job* j = nullptr;
   MB_CHECK(job_begin_locked(ctx, a, ws_base, &j));
   mb200_cosine_piece pc;

@@ -677,6 +677,15 @@ int mb200_bank_counters(mb200_bank* bk, void** device_ptr, int64_t* cells) {
   return MB200_OK;
 }
 
+int mb200_bank_ipc_handle(mb200_bank* bk, void* ipc_handle) {
+  if (!bk || !ipc_handle) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_ipc_handle: NULL argument");
+  mb200_ctx* ctx = bk->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MB_CUDA(ctx, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle, bk->counters));
+  return MB200_OK;
+}
+
 int mb200_bank_update(mb200_bank* bk, const int64_t* entity, const int64_t* key, const float* inc,
                       int64_t n, int mem) {
   return bank_update_impl<float>(bk, entity, key, inc, n, mem);

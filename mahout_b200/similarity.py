@@ -290,7 +290,7 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
             else:
                 gather()
                 job.push(out.clone(), vout.clone(), id_mul=G, id_add=1, id_base=c0 * G)
-        if precision == "rescored":
+        if precision != "tensor":
             # the exact re-score reads the counters of arbitrary peers: gathered whole, behind the rows
             if cuda:
                 with torch.cuda.stream(comm):
@@ -363,6 +363,35 @@ class PeerRows:
         self.staging_valid = torch.empty((G, depth, vw), dtype=torch.int32, device=dev)
         self.token = torch.zeros(1, dtype=torch.int32, device=dev)
 
+    def map_counters(self, bank):
+        """Map every rank's counter bank (CUDA IPC): `counter_blocks[g]` then points at shard g's counters
+        [E_loc][d][w] -- MB200_PRECISION_CERTIFIED reads the few undecided candidates through them, so
+        the counters are never gathered.  Collective; call after the banks are built."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        G, ctx = self.plan.G, self.ctx
+        h = (C.c_char * 64)()
+        N.check(N.lib().mb200_bank_ipc_handle(bank.handle, C.cast(h, C.c_void_p)), ctx.handle)
+        dev = f"cuda:{ctx.device}"
+        mine = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(dev)
+        allh = torch.empty(G * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        allh = allh.cpu().numpy().tobytes()
+        own, _ = bank.counters_ptr()
+        self.counter_blocks = (C.c_void_p * G)()
+        for g in range(G):
+            if g == self.plan.rank:
+                self.counter_blocks[g] = own
+                continue
+            q = C.c_void_p()
+            hb = (C.c_char * 64).from_buffer_copy(allh[g * 64:(g + 1) * 64])
+            N.check(N.lib().mb200_peer_open(ctx.handle, C.cast(hb, C.c_void_p), C.byref(q)), ctx.handle)
+            self._opened.append(q)
+            self.counter_blocks[g] = q.value
+        return self.counter_blocks
+
     def barrier(self):
         """stream-ordered cross-rank barrier (a one-word all-reduce on the current stream)"""
         import torch.distributed as dist
@@ -396,7 +425,7 @@ class PeerRows:
 
 
 def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype: str = "f16",
-                        precision: str = "tensor", a_counters=None, b_counters=None, out=None):
+                        precision: str = "tensor", a_counters=None, b_counters=None, out=None, counter_blocks=None):
     """C1 fused into K3: `peers.rows` / `peers.valid` hold this rank's normalised rows (K2 output).  One
     stream-ordered barrier makes every rank's rows final, the copy engines then pull the shards over
     NVLink while K3 -- launched immediately, once, over all blocks -- waits block by block on the arrival
@@ -408,8 +437,9 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
     job = backend.begin(plan, peers.rows, peers.valid, k, threshold, dtype, precision)
     try:
         job.push(peers.staging_rows, peers.staging_valid, id_mul=G, id_add=1, ready=ready, first_block=plan.rank)
-        if precision == "rescored":
-            res = job.finish(a_counters=a_counters, b_counters=b_counters, b_id=(G, 1), out=out)
+        if precision != "tensor":
+            res = job.finish(a_counters=a_counters, b_counters=b_counters, b_id=(G, 1), out=out,
+                             counter_blocks=counter_blocks, b_count=plan.rows_per_shard)
         else:
             res = job.finish(out=out)
     except BaseException:
@@ -442,7 +472,9 @@ def _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_res
             N.check(N.lib().mb200_bank_normalize(backend.bank.handle, sk._DTYPES[dtype], C.c_void_p(peers.rows.data_ptr()),
                                                  C.c_void_p(peers.valid.data_ptr())), ctx.handle)
             kw = {}
-            if precision == "rescored":
+            if precision == "certified":
+                kw = dict(a_counters=backend.counters(), counter_blocks=peers.map_counters(backend.bank))
+            elif precision != "tensor":
                 a_cnt = backend.counters()
                 kw = dict(a_counters=a_cnt, b_counters=_all_gather(a_cnt, world, group))
             idx, sim, cnt = fused_gather_cosine(backend, plan, peers, k, threshold, dtype, precision, **kw)
@@ -503,7 +535,7 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
             return out
         # peer mappings are not available on this box (CUDA IPC refused): NCCL all-gather, then K3
     a_rows, a_valid = backend.normalized(dtype)
-    a_cnt = backend.counters() if precision == "rescored" else None
+    a_cnt = backend.counters() if precision != "tensor" else None
     if world > 1 and chunk_rows > 0:
         # C1 in row chunks, overlapped with K3 through the incremental cosine job
         idx, sim, cnt = pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precision, group,
@@ -515,7 +547,7 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
         else:
             b_rows, b_valid = a_rows.unsqueeze(0), a_valid.unsqueeze(0)
         b_cnt = None
-        if precision == "rescored":
+        if precision != "tensor":
             b_cnt = _all_gather(a_cnt, world, group) if world > 1 else a_cnt
         idx, sim, cnt = backend.cosine(plan, a_rows, a_valid, b_rows, b_valid, k, threshold, dtype, precision,
                                        a_cnt, b_cnt)

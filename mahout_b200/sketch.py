@@ -349,7 +349,7 @@ class SketchBank:
 
 
 _DTYPES = {"f16": N.DTYPE_F16, "bf16": N.DTYPE_BF16}
-_PRECISIONS = {"tensor": N.PRECISION_TENSOR, "rescored": N.PRECISION_RESCORED}
+_PRECISIONS = {"tensor": N.PRECISION_TENSOR, "rescored": N.PRECISION_RESCORED, "certified": N.PRECISION_CERTIFIED}
 
 
 def cosine_topk_blocks(ctx: Context, a_rows, a_valid, b_rows, b_valid, depth: int, width: int, k: int,
@@ -425,9 +425,11 @@ class CosineJob:
         self._keep += [b_rows, b_valid]
         N.check(N.lib().mb200_cosine_push(self._h, C.byref(pc)), self.ctx.handle)
 
-    def finish(self, a_counters=None, b_counters=None, b_id=(1, 0), out=None):
-        """Returns (idx, sim, cnt) device tensors.  precision="rescored" needs the resident counters:
-        a_counters [a_count, d, w], b_counters [blocks, b_count, d, w] with b_id = (id_mul, id_add)."""
+    def finish(self, a_counters=None, b_counters=None, b_id=(1, 0), out=None, counter_blocks=None, b_count=None):
+        """Returns (idx, sim, cnt) device tensors.  precision="rescored" / "certified" need the resident
+        counters: a_counters [a_count, d, w], b_counters [blocks, b_count, d, w] with b_id = (id_mul, id_add);
+        "certified" alternatively takes counter_blocks, a ctypes array of one device pointer per block
+        (peer-mapped banks of b_count rows each) instead of the gathered b_counters."""
         import torch
         dev = f"cuda:{self.ctx.device}"
         if out is None:
@@ -438,8 +440,13 @@ class CosineJob:
         fin = N.CosineArgs()
         fin.out_idx, fin.out_sim, fin.out_cnt = idx.data_ptr(), sim.data_ptr(), cnt.data_ptr()
         if a_counters is not None:
-            fin.a_counters, fin.b_counters = a_counters.data_ptr(), b_counters.data_ptr()
-            fin.b_blocks, fin.b_count = int(b_counters.shape[0]), int(b_counters.shape[1])
+            fin.a_counters = a_counters.data_ptr()
+            if counter_blocks is not None:
+                fin.b_counter_blocks = C.cast(counter_blocks, C.c_void_p)
+                fin.b_blocks, fin.b_count = len(counter_blocks), int(b_count)
+            else:
+                fin.b_counters = b_counters.data_ptr()
+                fin.b_blocks, fin.b_count = int(b_counters.shape[0]), int(b_counters.shape[1])
             fin.b_id_mul, fin.b_id_add = b_id
         h, self._h = self._h, None
         N.check(N.lib().mb200_cosine_finish(h, C.byref(fin)), self.ctx.handle)

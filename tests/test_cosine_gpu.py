@@ -281,3 +281,56 @@ def test_topk_edge_shapes(mb, ctx, E, d, w, k):
             m = oidx >= 0
             assert np.allclose(np.sort(sim, axis=1), np.sort(osim, axis=1), rtol=2e-3, atol=0)
     bank.close()
+
+
+@pytest.mark.parametrize("E,d,w,k", [(300, 4, 512, 10), (1000, 4, 4096, 50), (257, 1, 256, 100), (129, 2, 192, 5)])
+def test_topk_certified_sets_equal_oracle(mb, ctx, E, d, w, k):
+    """MB200_PRECISION_CERTIFIED: the top-k SETS are the oracle's, the similarities are tensor-core values
+    (<= 1e-3 relative), ordered by the returned value"""
+    bank, ref = _make_bank(mb, ctx, E, d, w, 60 * E, seed=3 * E + k, empty=(0, 17))
+    idx, sim, cnt = bank.cosine_topk(k, precision="certified")
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    dense = orc.bank_cosine_dense(ref)
+    assert (cnt == ocnt).all()
+    for r in range(E):
+        c = cnt[r]
+        assert set(idx[r, :c].tolist()) == set(oidx[r, :c].tolist()), r
+        want = dense[r, idx[r, :c]]
+        assert (np.abs(sim[r, :c] - want) <= REL_TOL * np.abs(want)).all()
+        assert (np.diff(sim[r, :c]) <= 0).all()
+    bank.close()
+
+
+def test_certified_ties_threshold_and_sharded_blocks(mb, ctx):
+    """exact ties straddling the cut, a threshold inside the value range, and the sharded block layout"""
+    import torch
+    from mahout_b200.sketch import cosine_topk_blocks
+    E, d, w, k = 140, 2, 128, 3
+    bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+    ent = np.repeat(np.arange(E), 3).astype(np.int64)
+    key = np.tile(np.array([5, 9, 11]), E).astype(np.int64)
+    key[3 * 100:] += 1000
+    inc = np.tile(np.array([1.0, 2.0, 0.5], np.float32), E)
+    bank.update(ent, key, inc)
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((E, d, w))
+    orc.bank_update(ref, d, w, a, b, ent, key, inc)
+    idx, sim, cnt = bank.cosine_topk(k, precision="certified")
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    assert (cnt == ocnt).all() and (idx == oidx).all()           # all ties: exact values decide, lower index wins
+    bank.close()
+    E, d, w, k, G = 600, 4, 512, 12, 3
+    full, ref = _make_bank(mb, ctx, E, d, w, 50 * E, seed=9, empty=(5,))
+    b_rows, b_valid, b_cnt = _shards(mb, ctx, full, G)
+    dense = orc.bank_cosine_dense(ref)
+    for thr in (None, 0.3):
+        oidx, osim, ocnt = orc.bank_cosine_topk(ref, k, threshold=thr if thr else orc.NO_THRESHOLD)
+        for g in range(G):
+            idx, sim, cnt = cosine_topk_blocks(ctx, b_rows[g], b_valid[g], b_rows, b_valid, d, w, k, a_id=(G, g),
+                                               b_id=(G, 1), threshold=thr, precision="certified",
+                                               a_counters=b_cnt[g], b_counters=b_cnt)
+            idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+            assert (cnt == ocnt[g::G]).all()
+            for l in range(E // G):
+                assert set(idx[l, :cnt[l]].tolist()) == set(oidx[g::G][l, :cnt[l]].tolist())
+    full.close()

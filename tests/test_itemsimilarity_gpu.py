@@ -153,6 +153,9 @@ def _nccl_worker(rank, world, port, q):
     user = rng.integers(1, 3000, n).astype(np.int64)
     pref = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
     res = {}
+    # certified across GPUs: the undecided candidates are read from the peers' banks over NVLink (no gather)
+    res["certified"] = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N,
+                                                   k=20, width=1024, depth=4, precision="certified")
     for precision in ("rescored", "tensor"):
         res[precision] = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N,
                                                      k=20, width=1024, depth=4, precision=precision)
@@ -222,6 +225,10 @@ def test_sharded_two_gpus_nccl():
     idx, s, cnt = res["rescored"]
     assert (cnt == ocnt).all() and (idx == oidx).all() and s.tobytes() == osim.tobytes()
     assert res["fused_ok"], "fused pull-gather result differs from the all-gather + K3 result"
+    idx, s, cnt = res["certified"]
+    assert (cnt == ocnt).all()
+    for r in range(777):
+        assert set(idx[r, :cnt[r]].tolist()) == set(oidx[r, :cnt[r]].tolist()), r
     idx, s, cnt = res["tensor"]
     assert (cnt == ocnt).all()
     dense = orc.bank_cosine_dense(ref)
