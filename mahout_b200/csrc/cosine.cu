@@ -793,13 +793,14 @@ __device__ __forceinline__ const long long* b_row(const RescoreParams& p, long l
 #define JAVA_MAX_DOUBLE 1.7976931348623157e308
 
 // Ordering, certification and output of one row's re-scored candidates; executed by one warp.
-__device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long r, int n, const double* s_min,
-                                               int bad_flag, int lane, bool certified_elsewhere = false) {
+template <int NPL>   // 32 * NPL >= n sorted entries
+__device__ __forceinline__ void rescore_finish_t(const RescoreParams& p, long long r, int n, const double* s_min,
+                                                 int bad_flag, int lane, bool certified_elsewhere) {
   // warp 0: order the candidates by (exact sim desc, index asc), certify, write the top-k
-  double sim[CAP / 32];
-  uint32_t idv[CAP / 32];
+  double sim[NPL];
+  uint32_t idv[NPL];
 #pragma unroll
-  for (int u = 0; u < CAP / 32; u++) {
+  for (int u = 0; u < NPL; u++) {
     const int c = u * 32 + lane;
     sim[u] = -INFINITY;
     idv[u] = 0xFFFFFFFFu;
@@ -812,13 +813,13 @@ __device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long
   }
   // bitonic sort on (sim desc, id asc) with 96-bit keys
 #pragma unroll
-  for (int k = 2; k <= CAP; k <<= 1) {
+  for (int k = 2; k <= 32 * NPL; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
       if (j >= 32) {
         const int js = j >> 5;
 #pragma unroll
-        for (int s = 0; s < CAP / 32; s++) {
+        for (int s = 0; s < NPL; s++) {
           if ((s & js) == 0) {
             const bool desc = (((s * 32) & k) == 0);
             const bool a_first = sim[s] > sim[s | js] || (sim[s] == sim[s | js] && idv[s] <= idv[s | js]);
@@ -830,7 +831,7 @@ __device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long
         }
       } else {
 #pragma unroll
-        for (int s = 0; s < CAP / 32; s++) {
+        for (int s = 0; s < NPL; s++) {
           const double os = __shfl_xor_sync(0xffffffffu, sim[s], j);
           const uint32_t oi = __shfl_xor_sync(0xffffffffu, idv[s], j);
           const int e = s * 32 + lane;
@@ -849,7 +850,7 @@ __device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long
   int admitted = 0;
   double kth = -INFINITY;  // exact value of the k-th result (or -inf if fewer than k)
 #pragma unroll
-  for (int u = 0; u < CAP / 32; u++) {
+  for (int u = 0; u < NPL; u++) {
     const int e = u * 32 + lane;
     const bool ok = sim[u] > -INFINITY && e < p.k;
     if (e < p.k) {
@@ -859,6 +860,10 @@ __device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long
     admitted += __popc(__ballot_sync(0xffffffffu, ok));
     const double v = __shfl_sync(0xffffffffu, sim[u], (p.k - 1) & 31);
     if (u == ((p.k - 1) >> 5)) kth = v;
+  }
+  for (int e = 32 * NPL + lane; e < p.k; e += 32) {   // k beyond the sorted window: nothing there
+    p.out_idx[(size_t)r * p.k + e] = -1LL;
+    p.out_sim[(size_t)r * p.k + e] = 0.0;
   }
   if (lane == 0) {
     p.out_cnt[r] = admitted;
@@ -874,6 +879,14 @@ __device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long
     p.row_flag[r] = flag;
     if (flag) atomicAdd(p.flag_count, 1);
   }
+}
+
+// the sort network is sized by the number of candidates (k = 50 keeps 64: a quarter of the CAP-wide sort)
+__device__ __forceinline__ void rescore_finish(const RescoreParams& p, long long r, int n, const double* s_min,
+                                               int bad_flag, int lane, bool certified_elsewhere = false) {
+  if (n <= 64 && p.k <= 64) rescore_finish_t<2>(p, r, n, s_min, bad_flag, lane, certified_elsewhere);
+  else if (n <= 128 && p.k <= 128) rescore_finish_t<4>(p, r, n, s_min, bad_flag, lane, certified_elsewhere);
+  else rescore_finish_t<CAP / 32>(p, r, n, s_min, bad_flag, lane, certified_elsewhere);
 }
 
 #define RESCORE_SEG 4096  /* counters of one A row segment staged in shared memory */
@@ -990,9 +1003,9 @@ __global__ void __launch_bounds__(256) k_certify(const RescoreParams p) {
   __shared__ double s_fin[CAP];                // final value per candidate (tensor or exact)
   __shared__ double s_min[CAP];                // exact running min of the selected candidates
   __shared__ long long s_ab[CAP], s_bb[CAP];
-  __shared__ double s_mag[CAP];
+  __shared__ int s_bmax[CAP];
   __shared__ int s_sel[CAP];                   // candidate slots that need the exact value
-  __shared__ double s_red[8];
+  __shared__ int s_redm[8];
   __shared__ long long s_redi[8];
   __shared__ int s_bad, s_nsel, s_flag;
   const long long r = blockIdx.x;
@@ -1054,10 +1067,10 @@ __global__ void __launch_bounds__(256) k_certify(const RescoreParams p) {
     for (int c = tid; c < nsel; c += blockDim.x) {
       s_ab[c] = 0;
       s_bb[c] = 0;
-      s_mag[c] = 0.0;
+      s_bmax[c] = 0;
     }
     long long aa = 0;
-    double amag = 0.0;
+    int amax = 0;
     int bad = 0;
     for (int j0 = 0; j0 < p.W; j0 += RESCORE_SEG) {
       const int seg = min(RESCORE_SEG, p.W - j0);
@@ -1065,61 +1078,74 @@ __global__ void __launch_bounds__(256) k_certify(const RescoreParams p) {
       for (int j = tid; j < seg; j += blockDim.x) {
         const long long x = arow[(size_t)i * p.W + j0 + j];
         s_a[j] = x;
+        // counters beyond 31 bits send the row to the exact full-row path; below that the products
+        // are single IMAD.WIDEs and the running maxima bound every partial sum
         if (x >= (1LL << 31) || x <= -(1LL << 31)) bad = 1;
-        aa += x * x;
-        amag += (double)x * (double)x;
+        const int xi = (int)x;
+        aa += (long long)xi * xi;
+        const int ax = xi < 0 ? -xi : xi;
+        amax = ax > amax ? ax : amax;
       }
       __syncthreads();
-      for (int c = warp; c < nsel; c += 8) {
+      // few candidates: several warps share one (slices of the segment), so that all 8 warps keep loads
+      // in flight -- the rows of the undecided candidates may live in a peer's HBM, one NVLink hop away
+      const int wpc = nsel >= 8 ? 1 : (nsel >= 4 ? 2 : (nsel >= 2 ? 4 : 8));
+      const int per_round = 8 / wpc;
+      for (int c0 = 0; c0 < nsel; c0 += per_round) {
+        const int c = c0 + warp / wpc, part = warp % wpc;
+        if (c >= nsel) continue;
         const uint32_t id = p.cand_id[(size_t)r * CAP + s_sel[c]];
         long long g, l;
         b_locate(p, id, g, l);
         const long long* brow = b_row(p, g, l, i) + j0;
+        const int lo = (int)((long long)seg * part / wpc), hi = (int)((long long)seg * (part + 1) / wpc);
         long long bb = 0, ab = 0;
-        double mag = 0.0;
-        int badb = 0;
-        for (int j = lane; j < seg; j += 32) {
+        int bmax = 0, badb = 0;
+#pragma unroll 4
+        for (int j = lo + lane; j < hi; j += 32) {
           const long long y = __ldg(brow + j);
-          const long long x = s_a[j];
           if (y >= (1LL << 31) || y <= -(1LL << 31)) badb = 1;
-          bb += y * y;
-          ab += x * y;
-          mag += fabs((double)y * (double)y) + fabs((double)x * (double)y);
+          const int yi = (int)y, xi = (int)s_a[j];
+          bb += (long long)yi * yi;
+          ab += (long long)xi * yi;
+          const int ay = yi < 0 ? -yi : yi;
+          bmax = ay > bmax ? ay : bmax;
         }
         for (int o = 16; o > 0; o >>= 1) {
           bb += __shfl_xor_sync(0xffffffffu, bb, o);
           ab += __shfl_xor_sync(0xffffffffu, ab, o);
-          mag += __shfl_xor_sync(0xffffffffu, mag, o);
+          bmax = max(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
           badb |= __shfl_xor_sync(0xffffffffu, badb, o);
         }
         if (lane == 0) {
-          s_bb[c] += bb;
-          s_ab[c] += ab;
-          s_mag[c] += mag;
+          atomicAdd((unsigned long long*)&s_bb[c], (unsigned long long)bb);
+          atomicAdd((unsigned long long*)&s_ab[c], (unsigned long long)ab);
+          atomicMax(&s_bmax[c], bmax);
           if (badb) s_bad = 1;
         }
       }
     }
     for (int o = 16; o > 0; o >>= 1) {
       aa += __shfl_xor_sync(0xffffffffu, aa, o);
-      amag += __shfl_xor_sync(0xffffffffu, amag, o);
+      amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     }
     if (lane == 0) {
       s_redi[warp] = aa;
-      s_red[warp] = amag;
+      s_redm[warp] = amax;
     }
     if (bad) s_bad = 1;
     __syncthreads();
     long long AA = 0;
-    double AAm = 0.0;
+    int AM = 0;
     for (int w = 0; w < 8; w++) {
       AA += s_redi[w];
-      AAm += s_red[w];
+      AM = max(AM, s_redm[w]);
     }
-    if (AAm >= TWO53 * 0.5 && tid == 0) s_bad = 1;
     const double sqa = sqrt((double)AA);
     for (int c = tid; c < nsel; c += blockDim.x) {
-      if (s_mag[c] >= TWO53 * 0.5) s_bad = 1;
+      // every partial sum of the reference's FP64 loops stays an exact integer below 2^52
+      const double big = (double)max(AM, s_bmax[c]);
+      if (big * big * (double)p.W >= TWO53 * 0.5) s_bad = 1;
       const double den = __dmul_rn(sqa, sqrt((double)s_bb[c]));
       if (den != 0.0) {
         const double cs = __ddiv_rn((double)s_ab[c], den);
