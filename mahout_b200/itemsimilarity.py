@@ -53,7 +53,10 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--sketchDepth", type=int, default=4)
     ap.add_argument("--sketchSeed", type=int, default=42)
     ap.add_argument("--fracBits", type=int, default=1)
-    ap.add_argument("--precision", default="rescored", choices=["rescored", "tensor"])
+    ap.add_argument("--precision", default="rescored", choices=["rescored", "certified", "tensor"])
+    ap.add_argument("--similarityMatrixOutput", default=None,
+                    help="also write phase 1's output: SequenceFile<IntWritable,VectorWritable> rows of the "
+                         "similarity matrix (what RecommenderJob / phase 2 read)")
     return ap
 
 
@@ -90,6 +93,9 @@ class ItemSimilarityJob:
                         threshold=args.threshold, width=args.sketchWidth, depth=args.sketchDepth,
                         seed=args.sketchSeed, frac_bits=args.fracBits, precision=args.precision)
                 pairs = sim.most_similar_item_pairs(idx, s, cnt, prep.item_id)
+                if args.similarityMatrixOutput:
+                    from . import seqfile
+                    seqfile.write_similarity_matrix(args.similarityMatrixOutput, idx, s, cnt, prep.num_items)
             prep.close()
             with open(args.output, "w") as out:
                 for a, b, v in pairs:
