@@ -381,6 +381,10 @@ def run_ours(args):
                          "peak_source": peaks["source"], "algorithmic_bytes_per_event": ALGO_BYTES_PER_EVENT,
                          "kernel_ms_per_launch": kern_s * 1e3, "launches_timed": int(k_n),
                          "physical_event_read_GBps": physical,
+                         # frac follows SURVEY.md 8d's algorithmic model (84 B/event as if every counter RMW
+                         # went to HBM); the 32 MiB sketch is L2-resident and the hot-key cache absorbs most
+                         # updates, so the physical DRAM traffic is 12.2 B/event:
+                         "frac_physical_dram": 12.2 * n / kern_s / 1e9 / peaks["hbm"],
                          "atomic_updates_per_s": DEPTH * n / kern_s},
             "cpu_baseline": cpu, "parity": parity, "cosine": cosine,
         }

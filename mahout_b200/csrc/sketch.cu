@@ -164,10 +164,9 @@ __global__ void __launch_bounds__(256) k_update_bank(const UpdateArgs<T> p) {
 // ------------------------------------------------------------------------------------------
 #define CACHE_KEY_XOR 0x8000000000000000ull  /* tag 0 == empty; key Long.MIN_VALUE is never cached */
 
-template <int D>
-__device__ __forceinline__ void cached_event(unsigned long long* tag, unsigned int* lo, int* hi,
-                                             int slots_log2, long long* __restrict__ sketch,
-                                             const HashFamily& hf, long long key, long long q) {
+// returns true when the event was absorbed by the CTA's cache
+__device__ __forceinline__ bool cache_absorb(unsigned long long* tag, unsigned int* lo, int* hi, int slots_log2,
+                                             long long key, long long q) {
   const unsigned long long t = (unsigned long long)key ^ CACHE_KEY_XOR;
   const unsigned int slot =
       (unsigned int)(((unsigned long long)key * 0x9E3779B97F4A7C15ull) >> (64 - slots_log2));
@@ -187,10 +186,14 @@ __device__ __forceinline__ void cached_event(unsigned long long* tag, unsigned i
     const unsigned int old = atomicAdd(&lo[slot], qlo);
     const int h = qhi + ((unsigned int)(old + qlo) < qlo ? 1 : 0);
     if (h != 0) atomicAdd(&hi[slot], h);
-  } else {
-    scatter_event<D>(sketch, hf, key, q);
   }
+  return owned;
 }
+
+// Events the cache does not own are not scattered by the lane that met them -- with ~1/3 of the lanes
+// missing, every warp would run the d hashes + d REDs at 1/3 occupancy.  They are queued per warp in
+// shared memory and drained 32 at a time, every lane busy.
+static constexpr int MISS_Q = 64;  // entries per warp (a trip adds at most 32)
 
 template <typename T, bool VEC, int D>
 __global__ void __launch_bounds__(512, 2) k_update_single(const UpdateArgs<T> p) {
@@ -199,6 +202,8 @@ __global__ void __launch_bounds__(512, 2) k_update_single(const UpdateArgs<T> p)
   unsigned long long* tag = reinterpret_cast<unsigned long long*>(smem_raw);
   unsigned int* lo = reinterpret_cast<unsigned int*>(tag + S);
   int* hi = reinterpret_cast<int*>(lo + S);
+  long long* mq_key = reinterpret_cast<long long*>(hi + S) + (threadIdx.x >> 5) * (2 * MISS_Q);
+  long long* mq_val = mq_key + MISS_Q;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     tag[s] = 0;
     lo[s] = 0;
@@ -206,20 +211,43 @@ __global__ void __launch_bounds__(512, 2) k_update_single(const UpdateArgs<T> p)
   }
   __syncthreads();
 
+  const int lane = threadIdx.x & 31;
+  int qn = 0;  // entries in this warp's miss queue (warp-uniform)
   unsigned int bad = 0;
   unsigned long long maxabs = 0;
   const long long n4 = p.n & ~3LL;
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < n4;
-       base += stride) {
+  // whole warps iterate together: the trip count is made warp-uniform
+  const long long first = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * 4;
+  for (long long wbase = first; wbase < n4; wbase += stride) {
+    const long long base = wbase + (long long)lane * 4;
+    const bool live = base < n4;
     Quad<T> ev;
-    load_quad<T, false, VEC>(p, base, ev);
+    if (live) load_quad<T, false, VEC>(p, base, ev);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      long long q = inc_to_quanta(ev.inc[j], p.qscale, bad, maxabs);
-      if (q != 0) cached_event<D>(tag, lo, hi, p.slots_log2, p.counters, p.hf, ev.key[j], q);
+      bool miss = false;
+      long long q = 0;
+      if (live) {
+        q = inc_to_quanta(ev.inc[j], p.qscale, bad, maxabs);
+        if (q != 0) miss = !cache_absorb(tag, lo, hi, p.slots_log2, ev.key[j], q);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, miss);
+      if (miss) {
+        const int at = qn + __popc(m & ((1u << lane) - 1u));
+        mq_key[at] = ev.key[j];
+        mq_val[at] = q;
+      }
+      qn += __popc(m);
+      __syncwarp();
+      if (qn >= 32) {
+        qn -= 32;
+        scatter_event<D>(p.counters, p.hf, mq_key[qn + lane], mq_val[qn + lane]);
+        __syncwarp();
+      }
     }
   }
+  if (lane < qn) scatter_event<D>(p.counters, p.hf, mq_key[lane], mq_val[lane]);
   if (blockIdx.x == 0 && threadIdx.x < (unsigned)(p.n - n4)) {
     long long t = n4 + threadIdx.x;
     long long q = inc_to_quanta(p.inc[t], p.qscale, bad, maxabs);
@@ -403,7 +431,7 @@ static int launch_update(mb200_bank* bk, const long long* entity, const long lon
   if (bk->E == 1) {
     // single-sketch mode: the entity column (if any) is not needed
     const int threads = 512;
-    const size_t smem = (size_t)(1 << p.slots_log2) * 16;
+    const size_t smem = (size_t)(1 << p.slots_log2) * 16 + (size_t)(threads / 32) * 2 * MISS_Q * sizeof(long long);
     long long want = ceil_div64(n, (int64_t)threads * 4);
     int grid = (int)(want < (long long)ctx->num_sms * 2 ? want : (long long)ctx->num_sms * 2);
 #define LAUNCH_SINGLE(VEC, D)                                                                       \
