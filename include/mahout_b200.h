@@ -125,6 +125,8 @@ int mb200_bank_clear(mb200_bank* bank);
 int mb200_bank_counters(mb200_bank* bank, void** device_ptr, int64_t* cells);
 /* 64-byte CUDA IPC handle of the counters: another rank maps them with mb200_peer_open */
 int mb200_bank_ipc_handle(mb200_bank* bank, void* ipc_handle_64_bytes);
+/* int32 copy of the counters into DEVICE memory out[E][d][W] (INT_MIN where a counter does not fit) */
+int mb200_bank_narrow32(mb200_bank* bank, int32_t* out);
 
 /* DoubleCountMinSketch.update(key, increment) for n events (DoubleCountMinSketch.java:72-80):
  * C[entity[t]][i][h_i(key[t])] += inc[t] for i < d.  `entity` may be NULL when entities == 1.
@@ -257,6 +259,11 @@ typedef struct mb200_cosine_args {
    * a peer's bank mapped with mb200_bank_ipc_handle + mb200_peer_open).  Only the handful of
    * candidates the tensor values cannot decide are read through them.  NULL otherwise. */
   const int64_t* const* b_counter_blocks;
+  /* optional, with b_counter_blocks: int32 copies of the same blocks (mb200_bank_narrow32 into
+   * mb200_peer_alloc memory) -- the undecided candidates are then read at half the NVLink bytes; a
+   * counter that does not fit is stored as INT_MIN and sends the row to the exact full-row path,
+   * which reads b_counter_blocks */
+  const int32_t* const* b_counter_blocks32;
 } mb200_cosine_args;
 
 int mb200_cosine_topk(mb200_ctx* ctx, const mb200_cosine_args* args);

@@ -51,7 +51,7 @@ class CosineArgs(C.Structure):
         ("a_counters", C.c_void_p), ("b_counters", C.c_void_p),
         ("out_idx", C.c_void_p), ("out_sim", C.c_void_p), ("out_cnt", C.c_void_p),
         ("dense_out", C.c_void_p), ("dense_ld", C.c_int64),
-        ("b_counter_blocks", C.c_void_p),
+        ("b_counter_blocks", C.c_void_p), ("b_counter_blocks32", C.c_void_p),
     ]
 
 
@@ -87,6 +87,7 @@ _PROTOS = {
     "mb200_bank_destroy": (C.c_int, [vp]),
     "mb200_bank_clear": (C.c_int, [vp]),
     "mb200_bank_ipc_handle": (C.c_int, [vp, vp]),
+    "mb200_bank_narrow32": (C.c_int, [vp, vp]),
     "mb200_bank_counters": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
     "mb200_bank_update": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
     "mb200_bank_update_f64": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -755,6 +756,7 @@ struct RescoreParams {
   const long long* a_counters;  // [a_count][d][W]
   const long long* b_counters;  // [blocks][b_count][d][W]
   const long long* const* b_blocks_ptr;  // or: one pointer per block (peer-mapped banks), each [b_count][d][W]
+  const int* const* b_blocks32;          // CERTIFIED: optional int32 copies of the blocks (INT_MIN = does not fit)
   int64_t a_count, b_count;
   int32_t d, W, blocks;
   uint32_t a_id_mul, a_id_off, b_id_mul, b_id_add;
@@ -1097,19 +1099,67 @@ __global__ void __launch_bounds__(256) k_certify(const RescoreParams p) {
         const uint32_t id = p.cand_id[(size_t)r * CAP + s_sel[c]];
         long long g, l;
         b_locate(p, id, g, l);
-        const long long* brow = b_row(p, g, l, i) + j0;
         const int lo = (int)((long long)seg * part / wpc), hi = (int)((long long)seg * (part + 1) / wpc);
         long long bb = 0, ab = 0;
         int bmax = 0, badb = 0;
+        if (p.b_blocks32 != nullptr) {
+          // int32 copies of the peers' banks: half the bytes over NVLink
+          const int* brow32 = p.b_blocks32[g] + ((size_t)l * p.d + i) * p.W + j0;
+          auto acc32 = [&](int yi, int j) {
+            if (yi == INT_MIN) badb = 1;
+            const int xi = (int)s_a[j];
+            bb += (long long)yi * yi;
+            ab += (long long)xi * yi;
+            const int ay = yi < 0 ? -yi : yi;
+            bmax = ay > bmax ? ay : bmax;
+          };
+          constexpr int UN4 = 4;
+          int j = lo;
+          if ((((uintptr_t)(brow32 + lo)) & 15) == 0) {
+            for (; j + 128 * UN4 <= hi; j += 128 * UN4) {
+              int4 y[UN4];
+#pragma unroll
+              for (int u = 0; u < UN4; u++) y[u] = __ldg(reinterpret_cast<const int4*>(brow32 + j + u * 128) + lane);
+#pragma unroll
+              for (int u = 0; u < UN4; u++) {
+                const int e = j + u * 128 + 4 * lane;
+                acc32(y[u].x, e);
+                acc32(y[u].y, e + 1);
+                acc32(y[u].z, e + 2);
+                acc32(y[u].w, e + 3);
+              }
+            }
+          }
 #pragma unroll 4
-        for (int j = lo + lane; j < hi; j += 32) {
-          const long long y = __ldg(brow + j);
+          for (int jj = j + lane; jj < hi; jj += 32) acc32(__ldg(brow32 + jj), jj);
+        } else {
+        const long long* brow = b_row(p, g, l, i) + j0;
+        auto acc = [&](long long y, int j) {
           if (y >= (1LL << 31) || y <= -(1LL << 31)) badb = 1;
           const int yi = (int)y, xi = (int)s_a[j];
           bb += (long long)yi * yi;
           ab += (long long)xi * yi;
           const int ay = yi < 0 ? -yi : yi;
           bmax = ay > bmax ? ay : bmax;
+        };
+        // the row may sit in a peer's HBM: 8 x 16-byte loads per lane are issued before the first use
+        // (4 KB in flight per warp), otherwise the NVLink round trip bounds the kernel
+        constexpr int UN = 8;
+        int j = lo;
+        if ((((uintptr_t)(brow + lo)) & 15) == 0) {
+          for (; j + 64 * UN <= hi; j += 64 * UN) {
+            longlong2 y[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) y[u] = __ldg(reinterpret_cast<const longlong2*>(brow + j + u * 64) + lane);
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+              acc(y[u].x, j + u * 64 + 2 * lane);
+              acc(y[u].y, j + u * 64 + 2 * lane + 1);
+            }
+          }
+        }
+#pragma unroll 4
+        for (int jj = j + lane; jj < hi; jj += 32) acc(__ldg(brow + jj), jj);
         }
         for (int o = 16; o > 0; o >>= 1) {
           bb += __shfl_xor_sync(0xffffffffu, bb, o);
@@ -1952,7 +2002,7 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       memset(&rp, 0, sizeof(rp));
       rp.a_counters = (const long long*)fin->a_counters;
       rp.b_counters = (const long long*)fin->b_counters;
-      DevBuf d_bptr;
+      DevBuf d_bptr, d_bptr32;
       if (j->certified && fin->b_counter_blocks) {
         // peer-mapped banks: the few uncertain candidates are read from their owners over NVLink
         MB_CHECK(d_bptr.alloc(ws, (size_t)fin->b_blocks * sizeof(void*)));
@@ -1960,6 +2010,12 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
                                      cudaMemcpyHostToDevice, ctx->stream));
         rp.b_blocks_ptr = (const long long* const*)d_bptr.p;
         rp.b_counters = nullptr;
+        if (fin->b_counter_blocks32) {
+          MB_CHECK(d_bptr32.alloc(ws, (size_t)fin->b_blocks * sizeof(void*)));
+          MB_CUDA(ctx, cudaMemcpyAsync(d_bptr32.p, fin->b_counter_blocks32, (size_t)fin->b_blocks * sizeof(void*),
+                                       cudaMemcpyHostToDevice, ctx->stream));
+          rp.b_blocks32 = (const int* const*)d_bptr32.p;
+        }
       }
       rp.a_count = a->a_count;
       rp.b_count = fin->b_count;
@@ -2189,6 +2245,26 @@ int mb200_cosine_finish(mb200_cosine_job* job, const mb200_cosine_args* fin) {
   if (rc != MB200_OK) cudaStreamSynchronize(ctx->stream);
   job_free(job);
   return rc;
+}
+
+__global__ void __launch_bounds__(256) k_narrow32(const long long* __restrict__ in, long long n, int* __restrict__ out) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long x = in[t];
+    out[t] = (x > 2147483647LL || x < -2147483647LL) ? INT_MIN : (int)x;
+  }
+}
+
+int mb200_bank_narrow32(mb200_bank* bk, int32_t* out) {
+  if (!bk || !out) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_narrow32: NULL argument");
+  mb200_ctx* ctx = bk->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long long n = bk->E * (long long)bk->d * bk->W;
+  const long long want = (n + 255) / 256, cap = (long long)ctx->num_sms * 32;
+  k_narrow32<<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(bk->counters, n, (int*)out);
+  ctx->launches++;
+  MB_CUDA(ctx, cudaGetLastError());
+  return MB200_OK;
 }
 
 // cuStreamWriteValue32 through the runtime's driver entry point (no -lcuda)

@@ -390,7 +390,33 @@ class PeerRows:
             N.check(N.lib().mb200_peer_open(ctx.handle, C.cast(hb, C.c_void_p), C.byref(q)), ctx.handle)
             self._opened.append(q)
             self.counter_blocks[g] = q.value
+        # int32 copies in peer-accessible memory: what the undecided candidates are actually read from
+        E, d, w = bank.E, bank.d, bank.w
+        p32, h32 = C.c_void_p(), (C.c_char * 64)()
+        N.check(N.lib().mb200_peer_alloc(ctx.handle, E * d * w * 4, C.byref(p32), C.cast(h32, C.c_void_p)), ctx.handle)
+        self._own.append(p32)
+        self._narrow_of = (bank, p32)
+        mine = torch.frombuffer(bytearray(bytes(h32)), dtype=torch.uint8).to(dev)
+        dist.all_gather_into_tensor(allh_t := torch.empty(G * 64, dtype=torch.uint8, device=dev), mine, group=self.group)
+        allh = allh_t.cpu().numpy().tobytes()
+        self.counter_blocks32 = (C.c_void_p * G)()
+        for g in range(G):
+            if g == self.plan.rank:
+                self.counter_blocks32[g] = p32.value
+                continue
+            q = C.c_void_p()
+            hb = (C.c_char * 64).from_buffer_copy(allh[g * 64:(g + 1) * 64])
+            N.check(N.lib().mb200_peer_open(ctx.handle, C.cast(hb, C.c_void_p), C.byref(q)), ctx.handle)
+            self._opened.append(q)
+            self.counter_blocks32[g] = q.value
         return self.counter_blocks
+
+    def refresh_narrow(self):
+        """bring this rank's int32 copy up to date with its bank (before the step's first barrier)"""
+        from . import _native as N
+        if getattr(self, "_narrow_of", None) is not None:
+            bank, p32 = self._narrow_of
+            N.check(N.lib().mb200_bank_narrow32(bank.handle, p32), self.ctx.handle)
 
     def barrier(self):
         """stream-ordered cross-rank barrier (a one-word all-reduce on the current stream)"""
@@ -432,6 +458,8 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
     flags; a second barrier keeps every rank's rows alive until all peers have read them.  The context's
     stream must be the current torch stream (the NCCL barriers are ordered with K2 / K3 through it)."""
     G = plan.G
+    if counter_blocks is not None:
+        peers.refresh_narrow()
     peers.barrier()
     ready = peers.pull()
     job = backend.begin(plan, peers.rows, peers.valid, k, threshold, dtype, precision)
@@ -439,7 +467,9 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
         job.push(peers.staging_rows, peers.staging_valid, id_mul=G, id_add=1, ready=ready, first_block=plan.rank)
         if precision != "tensor":
             res = job.finish(a_counters=a_counters, b_counters=b_counters, b_id=(G, 1), out=out,
-                             counter_blocks=counter_blocks, b_count=plan.rows_per_shard)
+                             counter_blocks=counter_blocks, b_count=plan.rows_per_shard,
+                             counter_blocks32=getattr(peers, "counter_blocks32", None) if counter_blocks is not None
+                             else None)
         else:
             res = job.finish(out=out)
     except BaseException:

@@ -425,7 +425,8 @@ class CosineJob:
         self._keep += [b_rows, b_valid]
         N.check(N.lib().mb200_cosine_push(self._h, C.byref(pc)), self.ctx.handle)
 
-    def finish(self, a_counters=None, b_counters=None, b_id=(1, 0), out=None, counter_blocks=None, b_count=None):
+    def finish(self, a_counters=None, b_counters=None, b_id=(1, 0), out=None, counter_blocks=None, b_count=None,
+               counter_blocks32=None):
         """Returns (idx, sim, cnt) device tensors.  precision="rescored" / "certified" need the resident
         counters: a_counters [a_count, d, w], b_counters [blocks, b_count, d, w] with b_id = (id_mul, id_add);
         "certified" alternatively takes counter_blocks, a ctypes array of one device pointer per block
@@ -443,6 +444,8 @@ class CosineJob:
             fin.a_counters = a_counters.data_ptr()
             if counter_blocks is not None:
                 fin.b_counter_blocks = C.cast(counter_blocks, C.c_void_p)
+                if counter_blocks32 is not None:
+                    fin.b_counter_blocks32 = C.cast(counter_blocks32, C.c_void_p)
                 fin.b_blocks, fin.b_count = len(counter_blocks), int(b_count)
             else:
                 fin.b_counters = b_counters.data_ptr()
