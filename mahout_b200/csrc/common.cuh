@@ -81,6 +81,7 @@ struct mb200_bank {
 };
 
 int mb200_fail(mb200_ctx* ctx, int code, const char* fmt, ...);
+extern "C" void mb200_job_release(struct mb200_cosine_job* job);  // cosine.cu (internal)
 void mb200_set_global_error(const char* msg);
 
 #define MB_CUDA(ctx, expr)                                                                   \

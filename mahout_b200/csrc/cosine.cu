@@ -1595,6 +1595,9 @@ static void job_free(mb200_cosine_job* j) {
   delete j;
 }
 
+// a context that is destroyed with a job still open takes the job with it (runtime.cu)
+void mb200_job_release(mb200_cosine_job* j) { job_free(j); }
+
 static int job_begin_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t ws_base, mb200_cosine_job** out) {
   if (!a || !out) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_begin: args/out is NULL");
   *out = nullptr;

@@ -117,6 +117,7 @@ int mb200_destroy(mb200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->active_job) mb200_job_release(ctx->active_job);
   for (auto& s : ctx->spans) {
     cudaEventDestroy(s.beg);
     cudaEventDestroy(s.end);
