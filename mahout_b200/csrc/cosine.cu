@@ -1217,41 +1217,50 @@ __global__ void __launch_bounds__(256) k_certify(const RescoreParams p) {
 // max|a| * max|b| * W < 2^52 (and the same for the squares) -- checked from the row maxima.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rowstats(const long long* __restrict__ counters, int W,
-                                                  int* __restrict__ narrow, unsigned long long* __restrict__ row_max,
-                                                  long long* __restrict__ row_ss,
+                                                  int* __restrict__ narrow, unsigned short* __restrict__ narrow16,
+                                                  unsigned long long* __restrict__ row_max,
+                                                  long long* __restrict__ row_ss, long long* __restrict__ row_sum,
                                                   unsigned long long* __restrict__ global_max) {
   __shared__ unsigned long long s_mx[8];
-  __shared__ long long s_ss[8];
+  __shared__ long long s_ss[8], s_sm[8];
   const size_t rowi = blockIdx.x;
   const long long* row = counters + rowi * W;
   int* out = narrow + rowi * W;
+  unsigned short* out16 = narrow16 + rowi * W;
   unsigned long long mx = 0;
-  long long ss = 0;
+  long long ss = 0, sm = 0;
   for (int j = threadIdx.x; j < W; j += blockDim.x) {
     const long long x = row[j];
     const unsigned long long ax = x < 0 ? (unsigned long long)(-x) : (unsigned long long)x;
     mx = ax > mx ? ax : mx;
     const long long c = x > 2147483647LL ? 2147483647LL : (x < -2147483647LL ? -2147483647LL : x);
     out[j] = (int)c;
+    // biased 16-bit copy (value + 2^15); only read when every counter is below 2^15 in magnitude
+    out16[j] = (unsigned short)((ax < 32768ull ? (int)c : 0) + 32768);
     ss += c * c;  // exact whenever the row passes the magnitude test below
+    sm += c;
   }
   for (int o = 16; o > 0; o >>= 1) {
     const unsigned long long om = __shfl_xor_sync(0xffffffffu, mx, o);
     mx = om > mx ? om : mx;
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
   }
   if ((threadIdx.x & 31) == 0) {
     s_mx[threadIdx.x >> 5] = mx;
     s_ss[threadIdx.x >> 5] = ss;
+    s_sm[threadIdx.x >> 5] = sm;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; w++) {
       mx = s_mx[w] > mx ? s_mx[w] : mx;
       ss += s_ss[w];
+      sm += s_sm[w];
     }
     row_max[rowi] = mx;
     row_ss[rowi] = ss;
+    row_sum[rowi] = sm;
     atomicMax(global_max, mx);
   }
 }
@@ -1263,6 +1272,11 @@ struct Narrow {
   const unsigned long long* b_max;
   const long long* a_ss;
   const long long* b_ss;
+  // 16-bit form: counters + 2^15 as unsigned shorts, and the row sums that undo the bias
+  const unsigned short* a16;
+  const unsigned short* b16;
+  const long long* a_sum;
+  const long long* b_sum;
 };
 
 #define RESCORE32_SEG 8192
@@ -1333,6 +1347,70 @@ __global__ void __launch_bounds__(256) k_rescore32(const RescoreParams p, const 
     __syncthreads();
   }
   if (warp == 0) rescore_finish(p, r, n, s_min, s_bad, lane);
+}
+
+// K5b, 16-bit form (every |counter| < 2^15, W % 8 == 0): rows are read as biased unsigned shorts, two per
+// 32-bit word, so a product is one unsigned IMAD.WIDE and the re-score moves a quarter of the int64
+// bytes.  sum(x y) = sum((x+B)(y+B)) - B (sum x + sum y) - W B^2 with B = 2^15: all exact integers.
+__global__ void __launch_bounds__(256) k_rescore16(const RescoreParams p, const Narrow nw) {
+  __shared__ __align__(16) unsigned int s_a[RESCORE32_SEG / 2];   // one depth row of A, two counters per word
+  __shared__ double s_min[CAP];
+  __shared__ unsigned long long s_ab[CAP];
+  const long long r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.cand_cnt[r];
+  for (int c = tid; c < CAP; c += blockDim.x) s_min[c] = JAVA_MAX_DOUBLE;
+  __syncthreads();
+  const unsigned short* arow = nw.a16 + (size_t)r * p.d * p.W;
+  for (int i = 0; i < p.d && n > 0; i++) {
+    for (int c = tid; c < CAP; c += blockDim.x) s_ab[c] = 0;
+    for (int j0 = 0; j0 < p.W; j0 += RESCORE32_SEG) {
+      const int seg = min(RESCORE32_SEG, p.W - j0);   // multiple of 8
+      __syncthreads();
+      const uint4* a4g = reinterpret_cast<const uint4*>(arow + (size_t)i * p.W + j0);
+      for (int j = tid; j < (seg >> 3); j += blockDim.x) reinterpret_cast<uint4*>(s_a)[j] = __ldg(a4g + j);
+      __syncthreads();
+      for (int c = warp; c < n; c += 8) {
+        const uint32_t id = p.cand_id[(size_t)r * CAP + c];
+        long long g, l;
+        b_locate(p, id, g, l);
+        const uint4* b4 = reinterpret_cast<const uint4*>(nw.b16 + (((size_t)g * p.b_count + l) * p.d + i) * p.W + j0);
+        const uint4* a4 = reinterpret_cast<const uint4*>(s_a);
+        unsigned long long ab = 0;
+#pragma unroll 4
+        for (int j = lane; j < (seg >> 3); j += 32) {
+          const uint4 y = __ldg(b4 + j);
+          const uint4 x = a4[j];
+          const unsigned xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            ab += (unsigned long long)(xs[q] & 0xFFFFu) * (ys[q] & 0xFFFFu);
+            ab += (unsigned long long)(xs[q] >> 16) * (ys[q] >> 16);
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1) ab += __shfl_xor_sync(0xffffffffu, ab, o);
+        if (lane == 0) s_ab[c] += ab;
+      }
+    }
+    __syncthreads();
+    const long long AA = nw.a_ss[(size_t)r * p.d + i];
+    const long long asum = nw.a_sum[(size_t)r * p.d + i];
+    const double sqa = sqrt((double)AA);
+    for (int c = tid; c < n; c += blockDim.x) {
+      const uint32_t id = p.cand_id[(size_t)r * CAP + c];
+      long long g, l;
+      b_locate(p, id, g, l);
+      const size_t bi = ((size_t)g * p.b_count + l) * p.d + i;
+      const long long AB = (long long)s_ab[c] - 32768LL * (asum + nw.b_sum[bi]) - (long long)p.W * (1LL << 30);
+      const double den = __dmul_rn(sqa, sqrt((double)nw.b_ss[bi]));
+      if (den != 0.0) {
+        const double cs = __ddiv_rn((double)AB, den);
+        s_min[c] = cs < s_min[c] ? cs : s_min[c];
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0) rescore_finish(p, r, n, s_min, 0, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2050,41 +2128,56 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       // counters do not fit 31 bits
       const bool same = fin->a_counters == fin->b_counters && fin->b_blocks == 1 && a->a_count == fin->b_count;
       const size_t rows_b = (size_t)total_b * a->depth, rows_a = (size_t)a->a_count * a->depth;
-      DevBuf d_nb, d_bmax, d_bss, d_na, d_amax, d_ass, d_gmax;
+      DevBuf d_nb, d_bmax, d_bss, d_na, d_amax, d_ass, d_gmax, d_nb16, d_bsum, d_na16, d_asum;
       MB_CHECK(d_nb.alloc(ws, rows_b * a->width * sizeof(int)));
       MB_CHECK(d_bmax.alloc(ws, rows_b * 8));
       MB_CHECK(d_bss.alloc(ws, rows_b * 8));
       MB_CHECK(d_gmax.alloc(ws, 8));
+      MB_CHECK(d_nb16.alloc(ws, rows_b * a->width * sizeof(unsigned short)));
+      MB_CHECK(d_bsum.alloc(ws, rows_b * 8));
       MB_CUDA(ctx, cudaMemsetAsync(d_gmax.p, 0, 8, ctx->stream));
       k_rowstats<<<(unsigned)rows_b, 256, 0, ctx->stream>>>((const long long*)fin->b_counters, a->width, (int*)d_nb.p,
-                                                             (unsigned long long*)d_bmax.p, (long long*)d_bss.p,
+                                                             (unsigned short*)d_nb16.p, (unsigned long long*)d_bmax.p,
+                                                             (long long*)d_bss.p, (long long*)d_bsum.p,
                                                              (unsigned long long*)d_gmax.p);
       ctx->launches++;
       Narrow nw;
       nw.b = (const int*)d_nb.p;
       nw.b_max = (const unsigned long long*)d_bmax.p;
       nw.b_ss = (const long long*)d_bss.p;
+      nw.b16 = (const unsigned short*)d_nb16.p;
+      nw.b_sum = (const long long*)d_bsum.p;
       if (same) {
         nw.a = nw.b;
         nw.a_max = nw.b_max;
         nw.a_ss = nw.b_ss;
+        nw.a16 = nw.b16;
+        nw.a_sum = nw.b_sum;
       } else {
         MB_CHECK(d_na.alloc(ws, rows_a * a->width * sizeof(int)));
         MB_CHECK(d_amax.alloc(ws, rows_a * 8));
         MB_CHECK(d_ass.alloc(ws, rows_a * 8));
+        MB_CHECK(d_na16.alloc(ws, rows_a * a->width * sizeof(unsigned short)));
+        MB_CHECK(d_asum.alloc(ws, rows_a * 8));
         k_rowstats<<<(unsigned)rows_a, 256, 0, ctx->stream>>>((const long long*)fin->a_counters, a->width, (int*)d_na.p,
-                                                               (unsigned long long*)d_amax.p, (long long*)d_ass.p,
+                                                               (unsigned short*)d_na16.p, (unsigned long long*)d_amax.p,
+                                                               (long long*)d_ass.p, (long long*)d_asum.p,
                                                                (unsigned long long*)d_gmax.p);
         ctx->launches++;
         nw.a = (const int*)d_na.p;
         nw.a_max = (const unsigned long long*)d_amax.p;
         nw.a_ss = (const long long*)d_ass.p;
+        nw.a16 = (const unsigned short*)d_na16.p;
+        nw.a_sum = (const long long*)d_asum.p;
       }
       unsigned long long gmax = 0;
       MB_CUDA(ctx, cudaMemcpyAsync(&gmax, d_gmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
       MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       TRACE("K3+merge+rowstats");
-      if (gmax < (1ull << 31) && getenv("MB200_RESCORE64") == nullptr)
+      if (gmax < (1ull << 15) && (a->width & 7) == 0 && getenv("MB200_RESCORE64") == nullptr &&
+          getenv("MB200_RESCORE32") == nullptr)
+        k_rescore16<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp, nw);
+      else if (gmax < (1ull << 31) && getenv("MB200_RESCORE64") == nullptr)
         k_rescore32<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp, nw);
       else
         k_rescore<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp);

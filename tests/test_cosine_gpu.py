@@ -334,3 +334,21 @@ def test_certified_ties_threshold_and_sharded_blocks(mb, ctx):
             for l in range(E // G):
                 assert set(idx[l, :cnt[l]].tolist()) == set(oidx[g::G][l, :cnt[l]].tolist())
     full.close()
+
+
+@pytest.mark.parametrize("variant", ["16", "MB200_RESCORE32", "MB200_RESCORE64", "wide_counters"])
+def test_rescore_kernel_variants_bit_equal(mb, ctx, variant, monkeypatch):
+    """the 16-bit biased, 32-bit and 64-bit forms of the exact re-score give the oracle's bits; counters
+    beyond 2^15 quanta select the 32-bit form by themselves"""
+    E, d, w, k = 500, 3, 1024, 25
+    if variant.startswith("MB200"):
+        monkeypatch.setenv(variant, "1")
+    frac_bits = 12 if variant == "wide_counters" else 1            # 2^12 quanta per unit: counters > 2^15
+    bank, ref = _make_bank(mb, ctx, E, d, w, 60 * E, seed=77, empty=(3,), frac_bits=frac_bits)
+    if variant == "wide_counters":
+        assert np.abs(ref).max() * 2 ** frac_bits >= 2 ** 15
+    idx, sim, cnt = bank.cosine_topk(k)
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    assert (cnt == ocnt).all() and (idx == oidx).all()
+    assert sim.tobytes() == osim.tobytes()
+    bank.close()
