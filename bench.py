@@ -227,6 +227,10 @@ def run_ours(args):
         torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     peaks = _peaks()
+    # host buffers of this rank live on the GPU's own NUMA node (matters for the e2e H2D path at N = 8)
+    from mahout_b200.sketch import bind_host_thread_to_gpu
+    orig_affinity = os.sched_getaffinity(0)
+    numa_bound = bind_host_thread_to_gpu(local) if world > 1 else False
 
     ctx = mb.Context(local)
     # one non-default stream carries everything: the library's kernels, NCCL and the timing events
@@ -327,6 +331,8 @@ def run_ours(args):
     del dkey
     e2e_value = world * e2e_n * e2e_steps / e2e_s
 
+    if numa_bound:
+        os.sched_setaffinity(0, orig_affinity)        # the CPU baseline below uses every core again
     # ---- parity + cpu_baseline on rank 0 ---------------------------------------------------------
     cpu = None
     parity = None
@@ -371,7 +377,7 @@ def run_ours(args):
                     "sample": f"{e2e_n} events/step from pinned host memory through mb200_bank_update(MEM_HOST) "
                               "+ mb200_bank_read of the whole sketch; best of 3 repetitions of "
                               f"{e2e_steps} steps",
-                    "repetitions_s": e2e_reps, "pinned_h2d_GBps": h2d_gbps,
+                    "repetitions_s": e2e_reps, "pinned_h2d_GBps": h2d_gbps, "host_threads_bound_to_gpu_numa_node": numa_bound,
                     "bound": "PCIe: 12 B/event over the host link"},
             "roofline": {"bound": "hbm", "kernel": "k_update_single", "achieved": achieved, "peak": peaks["hbm"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm"],

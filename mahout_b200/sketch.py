@@ -82,6 +82,31 @@ class Context:
         return n.value
 
 
+def bind_host_thread_to_gpu(device: int) -> bool:
+    """Pin the calling process to the CPU cores local to `device` (NVML's affinity mask, intersected with
+    what the process may use) so that the pinned host buffers it allocates afterwards are first-touched on
+    the GPU's own NUMA node: with 8 ranks on a two-socket box, buffers on the wrong socket make the H2D
+    copies of mb200_bank_update(MEM_HOST) cross the inter-socket link.  Returns False if nothing was done."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device]) if vis else device
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = local & allowed
+        if not target or target == allowed:
+            return False
+        os.sched_setaffinity(0, target)
+        return True
+    except Exception:
+        return False
+
+
 def default_context() -> Context:
     ctx = getattr(_tls, "ctx", None)
     if ctx is None or ctx._h is None:
