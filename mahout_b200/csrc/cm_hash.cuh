@@ -8,7 +8,7 @@
 // covers negative keys and the Math.abs(Long.MIN_VALUE) < 0 corner of the parameters.
 //
 // Compiles for the device (nvcc) and, for the CPU-side unit test of the folding arithmetic
-// only (tests/hash_host_check.cpp), for the host.
+// only (tests/host/hash_host_check.cpp), for the host.
 #pragma once
 #include <stdint.h>
 

@@ -162,3 +162,27 @@ def test_java_double_to_string():
     from mahout_b200.similarity import java_double_to_string as j
     assert [j(v) for v in (0.4472135954999579, 1.0, 0.001, 0.0009765625, 1e7, 9999999.0, 1e-10, 100.0, -3.25, 0.0)] == \
         ["0.4472135954999579", "1.0", "0.001", "9.765625E-4", "1.0E7", "9999999.0", "1.0E-10", "100.0", "-3.25", "0.0"]
+
+
+def test_hash_folding_arithmetic_on_host(tmp_path):
+    """cm_hash.cuh compiled for the host: both the general 128-bit fold and the small-key path equal
+    BigInteger arithmetic (HashFunction.java:31-34), including negative keys / parameters and the corners."""
+    import random
+    import subprocess
+    exe = str(tmp_path / "hash_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "host", "hash_host_check.cpp"), "-o", exe])
+    P = 2 ** 63 - 25
+    rnd = random.Random(7)
+    cases = []
+    edge = [0, 1, -1, 2 ** 32 - 1, 2 ** 32, 2 ** 31, P - 1, P, P + 1, 2 ** 63 - 1, -2 ** 63, -2 ** 63 + 1, 1682, 10 ** 12]
+    for a in edge[:10]:
+        for k in edge:
+            cases.append((a, rnd.randrange(P), k, rnd.choice([1, 7, 4096, 2 ** 20, 1000003, 2 ** 31 - 1])))
+    for _ in range(20000):
+        k = rnd.choice([rnd.randrange(2 ** 32), rnd.randrange(-2 ** 63, 2 ** 63), rnd.randrange(2 ** 24)])
+        cases.append((rnd.randrange(2 ** 63), rnd.randrange(2 ** 63), k, rnd.choice([4096, 2 ** 20, 1000003, 97])))
+    inp = "".join(f"{a} {b} {k} {w}\n" for a, b, k, w in cases)
+    out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
+    assert len(out) == len(cases)
+    for (a, b, k, w), got in zip(cases, out):
+        assert int(got) == ((a * k + b) % P) % w, (a, b, k, w)
