@@ -718,9 +718,9 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                          "frac_of_burst_peak": achieved / peaks["bf16_burst"], "peak_source": peaks["source"],
                          "flops_per_launch": flops_rank, "kernel_ms_per_launch": k3_s * 1e3,
                          # ncu --set full of this kernel on this workload at 1 GPU
-                         # (profiles/r1_k_cosine_v3_ncu.txt): dram read 82.71 GB + write 0.62 GB -- the A blocks
+                         # (profiles/r1_k_cosine_v4_ncu.txt): dram read 64.33 GB + write 1.01 GB -- the A blocks
                          # are re-read for every B tile ("Scheduling")
-                         "traffic": 83.32e9 if world == 1 else None},
+                         "traffic": 65.34e9 if world == 1 else None},
             "e2e": {"value": pairs / e2e["rescored"], "unit": "pairs/s", "ms_per_job": e2e["rescored"] * 1e3,
                     "h2d_bytes_per_step": 20 * n_local, "d2h_bytes_per_step": plan.rows_per_shard * (C3_K * 16 + 4),
                     "tensor_precision": {"value": pairs / e2e["tensor"], "ms_per_job": e2e["tensor"] * 1e3},
