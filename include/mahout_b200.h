@@ -41,7 +41,7 @@ extern "C" {
 #define MB200_MAX_DEPTH 32 /* CountMinSketchConfig searches depths 1..24 (CountMinSketchConfig.java:28-29) */
 
 /* element type of the normalised sketch rows fed to the tensor cores */
-#define MB200_DTYPE_F16 0  /* rows scaled by 2^8; 11-bit significand (TF32-grade) at BF16 MMA rate */
+#define MB200_DTYPE_F16 0  /* rows scaled by 2^12; 11-bit significand (TF32-grade) at BF16 MMA rate */
 #define MB200_DTYPE_BF16 1
 
 /* cosine precision modes */
@@ -70,9 +70,9 @@ int mb200_release_workspace(mb200_ctx* ctx);
 
 /* kernel ids for mb200_kernel_time */
 #define MB200_K_UPDATE 0     /* K1 sketch update                 */
-#define MB200_K_NORMALIZE 1  /* K2 row norms + split conversion  */
+#define MB200_K_NORMALIZE 1  /* K2 row norms + 16-bit conversion */
 #define MB200_K_COSINE 2     /* K3 tcgen05 S.S^T + top-k epilogue */
-#define MB200_K_RESCORE 3    /* K5 merge + FP64 re-score + sort  */
+#define MB200_K_RESCORE 3    /* K5 merge + exact re-score / certification */
 #define MB200_K_PARSE 4     /* ingest: line count + scan + parse    */
 #define MB200_K_PREPARE 5   /* ingest: hash-table preparation + compaction */
 #define MB200_K_COUNT 6
