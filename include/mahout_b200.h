@@ -84,6 +84,17 @@ int mb200_kernel_time(mb200_ctx* ctx, int kernel_id, double* total_ms, int64_t* 
 int mb200_reset_profile(mb200_ctx* ctx);
 /* number of kernels this library has launched on the context since creation */
 int mb200_launch_count(mb200_ctx* ctx, int64_t* launches);
+/* what the context holds and has done (mb200_stats) */
+typedef struct mb200_stats {
+  int32_t device, num_sms;
+  int64_t launches;            /* kernels launched since creation */
+  int64_t workspace_bytes;     /* grow-only device workspaces of the cosine stage */
+  int64_t staging_bytes;       /* device staging of host-memory arguments and events */
+  int64_t last_fallback_rows;  /* rows of the last cosine call that took the exact full-row path */
+  int32_t cosine_job_active;
+  char device_name[64];
+} mb200_stats;
+int mb200_get_stats(mb200_ctx* ctx, mb200_stats* out);
 
 /* ---- pinned host memory ---------------------------------------------------------------- */
 /* Page-locked host buffers for the MB200_MEM_HOST paths (a JNI binding wraps them with

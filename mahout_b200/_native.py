@@ -55,6 +55,13 @@ class CosineArgs(C.Structure):
     ]
 
 
+class Stats(C.Structure):
+    """struct mb200_stats (include/mahout_b200.h)."""
+    _fields_ = [("device", C.c_int32), ("num_sms", C.c_int32), ("launches", C.c_int64),
+                ("workspace_bytes", C.c_int64), ("staging_bytes", C.c_int64), ("last_fallback_rows", C.c_int64),
+                ("cosine_job_active", C.c_int32), ("device_name", C.c_char * 64)]
+
+
 class CosinePiece(C.Structure):
     """struct mb200_cosine_piece (include/mahout_b200.h)."""
     _fields_ = [
@@ -75,6 +82,7 @@ _PROTOS = {
     "mb200_kernel_time": (C.c_int, [vp, C.c_int, C.POINTER(f64), C.POINTER(i64)]),
     "mb200_reset_profile": (C.c_int, [vp]),
     "mb200_launch_count": (C.c_int, [vp, C.POINTER(i64)]),
+    "mb200_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
     "mb200_host_alloc": (C.c_int, [i64, C.POINTER(vp)]),
     "mb200_host_free": (C.c_int, [vp]),
     "mb200_host_register": (C.c_int, [vp, i64]),

@@ -145,6 +145,25 @@ const char* mb200_last_error(mb200_ctx* ctx) {
   return g_last_error.c_str();
 }
 
+int mb200_get_stats(mb200_ctx* ctx, mb200_stats* out) {
+  if (!ctx || !out) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_get_stats: NULL argument");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  memset(out, 0, sizeof(*out));
+  out->device = ctx->device;
+  out->num_sms = ctx->num_sms;
+  out->launches = ctx->launches;
+  for (auto& w : ctx->ws) out->workspace_bytes += (int64_t)w.second;
+  for (auto& w : ctx->io) out->staging_bytes += (int64_t)w.second;
+  out->staging_bytes += 2 * (int64_t)ctx->stage_bytes;
+  out->last_fallback_rows = ctx->last_fallback_rows;
+  out->cosine_job_active = ctx->active_job ? 1 : 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) {
+    strncpy(out->device_name, prop.name, sizeof(out->device_name) - 1);
+  }
+  return MB200_OK;
+}
+
 int mb200_release_workspace(mb200_ctx* ctx) {
   if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_release_workspace: ctx is NULL");
   std::lock_guard<std::mutex> g(ctx->mu);

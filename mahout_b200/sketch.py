@@ -76,6 +76,12 @@ class Context:
         N.check(N.lib().mb200_kernel_time(self.handle, kernel_id, C.byref(ms), C.byref(n)), self.handle)
         return ms.value, n.value
 
+    def stats(self) -> dict:
+        """mb200_get_stats: device, SMs, kernels launched, workspace / staging bytes held, last fallback rows"""
+        st = N.Stats()
+        N.check(N.lib().mb200_get_stats(self.handle, C.byref(st)), self.handle)
+        return {f: (getattr(st, f).decode() if f == "device_name" else getattr(st, f)) for f, _ in N.Stats._fields_}
+
     def launch_count(self) -> int:
         n = C.c_int64()
         N.check(N.lib().mb200_launch_count(self.handle, C.byref(n)), self.handle)

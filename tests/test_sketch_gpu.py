@@ -348,3 +348,14 @@ def test_full_size_properties_config2(mb, ctx):
     assert pre.read().tobytes() == ref.tobytes()
     for bk in (whole, h1, h2, pre):
         bk.close()
+
+
+def test_context_stats(mb, ctx):
+    st = ctx.stats()
+    assert st["num_sms"] >= 100 and st["launches"] >= 0 and "B200" in st["device_name"]
+    bank = mb.SketchBank(300, 256, 2, 42, 1, ctx)
+    bank.update(np.arange(300), np.arange(300), np.ones(300, np.float32))
+    bank.cosine_topk(5)
+    st2 = ctx.stats()
+    assert st2["launches"] > st["launches"] and st2["workspace_bytes"] > 0 and st2["cosine_job_active"] == 0
+    bank.close()
