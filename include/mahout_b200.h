@@ -64,6 +64,10 @@ const char* mb200_last_error(mb200_ctx* ctx); /* ctx may be NULL: error of the f
  * context's own stream).  Lets the caller bracket calls with its own CUDA events. */
 int mb200_set_stream(mb200_ctx* ctx, void* cuda_stream);
 int mb200_sync(mb200_ctx* ctx);
+/* tunables (defaults are what bench.py measures) */
+#define MB200_OPT_GROUP_MIN_EVENTS 1 /* bank-mode updates of at least this many events are grouped by entity on
+                                        the device first (default 65536; 0 = always; INT64_MAX = never) */
+int mb200_set_option(mb200_ctx* ctx, int option, int64_t value);
 /* the cosine stage keeps its device workspaces (candidate lists, gathered rows of the single-GPU
  * convenience call) on the context between calls; this frees them */
 int mb200_release_workspace(mb200_ctx* ctx);
@@ -75,7 +79,9 @@ int mb200_release_workspace(mb200_ctx* ctx);
 #define MB200_K_RESCORE 3    /* K5 merge + exact re-score / certification */
 #define MB200_K_PARSE 4     /* ingest: line count + scan + parse    */
 #define MB200_K_PREPARE 5   /* ingest: hash-table preparation + compaction */
-#define MB200_K_COUNT 6
+#define MB200_K_GROUP 6     /* K1 bank mode: histogram + scans + the two partition passes in front of K1 */
+#define MB200_K_ROUTE 7     /* sharded ingest: partition by owner GPU + peer scatter */
+#define MB200_K_COUNT 8
 /* when profiling is on every launch of the kernels above is bracketed with CUDA events on the
  * launching stream; mb200_kernel_time syncs and returns the accumulated ms and launch count
  * since the last reset. */
@@ -148,6 +154,12 @@ int mb200_bank_update(mb200_bank* bank, const int64_t* entity, const int64_t* ke
                       const float* inc, int64_t n, int mem);
 int mb200_bank_update_f64(mb200_bank* bank, const int64_t* entity, const int64_t* key,
                           const double* inc, int64_t n, int mem);
+/* The same update for events that are already grouped by entity -- the shape the reference itself works
+ * on: CosineCM.exportProfile walks ONE entity's PreferenceArray into ONE sketch (CosineCM.java:41-58).
+ * row_ptr [entities + 1] (CSR: the events of entity e are [row_ptr[e], row_ptr[e+1]), row_ptr[0] = 0,
+ * row_ptr[entities] = n); key / inc [n].  Skips the device-side grouping passes of mb200_bank_update. */
+int mb200_bank_update_grouped(mb200_bank* bank, const int64_t* row_ptr, const int64_t* key, const float* inc,
+                              int64_t n, int mem);
 /* synchronise and report MB200_ERR_INEXACT / _RANGE / _BAD_ARG (entity out of range) */
 int mb200_bank_check(mb200_bank* bank);
 

@@ -17,7 +17,8 @@ ERR_NO_DEVICE, ERR_CM_DELTA, ERR_CM_EPSILON, ERR_UNSUPPORTED = -6, -7, -8, -9
 MEM_HOST, MEM_DEVICE = 0, 1
 DTYPE_F16, DTYPE_BF16 = 0, 1
 PRECISION_TENSOR, PRECISION_RESCORED, PRECISION_CERTIFIED = 0, 1, 2
-K_UPDATE, K_NORMALIZE, K_COSINE, K_RESCORE, K_PARSE, K_PREPARE = 0, 1, 2, 3, 4, 5
+K_UPDATE, K_NORMALIZE, K_COSINE, K_RESCORE, K_PARSE, K_PREPARE, K_GROUP, K_ROUTE = 0, 1, 2, 3, 4, 5, 6, 7
+OPT_GROUP_MIN_EVENTS = 1
 MAX_DEPTH = 32
 
 
@@ -77,6 +78,7 @@ _PROTOS = {
     "mb200_last_error": (C.c_char_p, [vp]),
     "mb200_set_stream": (C.c_int, [vp, vp]),
     "mb200_sync": (C.c_int, [vp]),
+    "mb200_set_option": (C.c_int, [vp, C.c_int, i64]),
     "mb200_release_workspace": (C.c_int, [vp]),
     "mb200_set_profiling": (C.c_int, [vp, C.c_int]),
     "mb200_kernel_time": (C.c_int, [vp, C.c_int, C.POINTER(f64), C.POINTER(i64)]),
@@ -99,6 +101,7 @@ _PROTOS = {
     "mb200_bank_counters": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
     "mb200_bank_update": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
     "mb200_bank_update_f64": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
+    "mb200_bank_update_grouped": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
     "mb200_bank_check": (C.c_int, [vp]),
     "mb200_bank_read": (C.c_int, [vp, i64, i64, vp, C.c_int]),
     "mb200_bank_query": (C.c_int, [vp, vp, vp, i64, vp, C.c_int]),

@@ -50,6 +50,9 @@ struct mb200_ctx {
   // grow-only device workspaces of the cosine stage (slot i = i-th request of a call); cudaMalloc /
   // cudaFree of a few hundred MB per call would otherwise cost more than the kernels
   std::vector<std::pair<void*, size_t>> ws;
+  // grow-only workspaces of the grouped K1 path (group.cu) and of the event router (route.cu)
+  std::vector<std::pair<void*, size_t>> ws_group;
+  int64_t group_min_events = 1 << 16;  // MB200_OPT_GROUP_MIN_EVENTS
   // grow-only device staging of host-memory arguments (see io_slot in sketch.cu)
   std::pair<void*, size_t> io[3] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
   // pull-gather: per-block arrival flags written by the copy stream, read by K3 (+ 1 abort word)
@@ -81,6 +84,10 @@ struct mb200_bank {
 };
 
 int mb200_fail(mb200_ctx* ctx, int code, const char* fmt, ...);
+// group.cu: bank-mode K1 through device-side grouping (called with ctx->mu held)
+bool mb200_group_applicable(const mb200_bank* bk, int64_t n);
+template <typename T>
+int mb200_group_update(mb200_bank* bk, const long long* entity, const long long* key, const T* inc, int64_t n);
 extern "C" void mb200_job_release(struct mb200_cosine_job* job);  // cosine.cu (internal)
 void mb200_set_global_error(const char* msg);
 

@@ -127,6 +127,8 @@ int mb200_destroy(mb200_ctx* ctx) {
     if (w.first) cudaFree(w.first);
   for (auto& w : ctx->io)
     if (w.first) cudaFree(w.first);
+  for (auto& w : ctx->ws_group)
+    if (w.first) cudaFree(w.first);
   if (ctx->gather_flags) cudaFree(ctx->gather_flags);
   if (ctx->gather_ev) cudaEventDestroy(ctx->gather_ev);
   for (int i = 0; i < 2; i++) {
@@ -174,6 +176,9 @@ int mb200_release_workspace(mb200_ctx* ctx) {
   for (auto& w : ctx->ws)
     if (w.first) cudaFree(w.first);
   ctx->ws.clear();
+  for (auto& w : ctx->ws_group)
+    if (w.first) cudaFree(w.first);
+  ctx->ws_group.clear();
   for (auto& w : ctx->io) {
     if (w.first) cudaFree(w.first);
     w = {nullptr, 0};
@@ -186,6 +191,19 @@ int mb200_set_stream(mb200_ctx* ctx, void* cuda_stream) {
   std::lock_guard<std::mutex> g(ctx->mu);
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return MB200_OK;
+}
+
+int mb200_set_option(mb200_ctx* ctx, int option, int64_t value) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_set_option: ctx is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  switch (option) {
+    case MB200_OPT_GROUP_MIN_EVENTS:
+      if (value < 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_set_option: GROUP_MIN_EVENTS must be >= 0");
+      ctx->group_min_events = value;
+      return MB200_OK;
+    default:
+      return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_set_option: unknown option %d", option);
+  }
 }
 
 int mb200_sync(mb200_ctx* ctx) {

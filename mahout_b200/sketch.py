@@ -65,6 +65,11 @@ class Context:
         N.check(N.lib().mb200_set_stream(self.handle, C.c_void_p(cuda_stream or 0)), self.handle)
         self.stream_ptr = cuda_stream or None
 
+    def set_option(self, option: int, value: int):
+        """mb200_set_option (e.g. N.OPT_GROUP_MIN_EVENTS: bank-mode updates of at least that many events are
+        grouped by entity on the device before K1)"""
+        N.check(N.lib().mb200_set_option(self.handle, int(option), int(value)), self.handle)
+
     def set_profiling(self, on: bool):
         N.check(N.lib().mb200_set_profiling(self.handle, int(on)), self.handle)
 
@@ -301,6 +306,17 @@ class SketchBank:
         mem = _same_mem(k, e, v)
         fn = N.lib().mb200_bank_update_f64 if f64 else N.lib().mb200_bank_update
         N.check(fn(self.handle, e.ptr, k.ptr, v.ptr, k.n, mem), self.ctx.handle)
+
+    def update_grouped(self, row_ptr, key, inc):
+        """The update for events already grouped by entity (CSR: entity e owns [row_ptr[e], row_ptr[e+1])) --
+        one PreferenceArray per entity, as CosineCM.exportProfile walks them (CosineCM.java:41-58)."""
+        r = _Arg(row_ptr, np.int64, "int64")
+        k = _Arg(key, np.int64, "int64")
+        v = _Arg(inc, np.float32, "float32")
+        if r.n != self.E + 1 or v.n != k.n:
+            raise ValueError("row_ptr must have entities + 1 entries; key and inc the same length")
+        mem = _same_mem(r, k, v)
+        N.check(N.lib().mb200_bank_update_grouped(self.handle, r.ptr, k.ptr, v.ptr, k.n, mem), self.ctx.handle)
 
     def check(self):
         N.check(N.lib().mb200_bank_check(self.handle), self.ctx.handle)

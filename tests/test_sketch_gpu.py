@@ -96,6 +96,107 @@ def test_update_bit_exact_host_and_device(mb, ctx, E, d, w, n):
         bank.close()
 
 
+def _zipf_entities(rng, n, E, s=1.2):
+    """entity stream with a heavy head (one entity owns a few windows of the grouped update) and empty tails"""
+    return (np.minimum(rng.zipf(s, n), E) - 1).astype(np.int64)
+
+
+@pytest.mark.parametrize("E,d,w,n,keys", [
+    (1682, 4, 4096, 300000, "small"),      # one partition level, tile path + sparse path
+    (5000, 4, 4096, 400000, "small"),      # two partition levels
+    (40000, 1, 512, 500000, "small"),      # d = 1, mostly sparse entities, many empty ones
+    (3000, 5, 1000, 200000, "mixed"),      # generic depth, non-power-of-two width, keys outside [0, 2^32)
+    (2100, 16, 4096, 150000, "small"),     # the tile (256 KB) does not fit shared memory: direct path on grouped records
+    (2, 4, 4096, 200000, "small"),         # every window inside one entity: shared (atomic) tile flushes
+    (700, 4, 4099, 150000, "small"),       # d * w not a multiple of 4: scalar flush
+])
+def test_grouped_update_bit_exact(mb, ctx, E, d, w, n, keys):
+    """bank-mode K1 through the device-side grouping (group.cu) == the oracle, bit for bit, on host and
+    device inputs; the direct kernel (grouping off) gives the same bank."""
+    import torch
+    from mahout_b200 import _native as N
+    rng = np.random.Generator(np.random.PCG64(77 + E + d))
+    ent = _zipf_entities(rng, n, E)
+    if keys == "small":
+        key = rng.integers(0, 200000, n).astype(np.int64)
+        inc = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
+    else:
+        key = rng.integers(-2 ** 40, 2 ** 40, n).astype(np.int64)
+        key[::3] = rng.integers(0, 1000, key[::3].shape[0])
+        inc = (rng.integers(-20, 21, n) * 0.5).astype(np.float32)
+        inc[::7] = 40000.0                                      # |quanta| >= 2^15: the wide path
+    a, b = orc.hash_params(42, d)
+    want = np.zeros((E, d, w))
+    orc.bank_update(want, d, w, a, b, ent, key, inc)
+    try:
+        for gmin in (0, 1 << 62):
+            ctx.set_option(N.OPT_GROUP_MIN_EVENTS, gmin)
+            for where in ("device", "host"):
+                bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+                if where == "host":
+                    bank.update(ent, key, inc)
+                else:
+                    bank.update(torch.from_numpy(ent).cuda(), torch.from_numpy(key).cuda(), torch.from_numpy(inc).cuda())
+                    bank.update(torch.from_numpy(ent).cuda()[:1000], torch.from_numpy(key).cuda()[:1000],
+                                -torch.from_numpy(inc).cuda()[:1000])      # additive: a second call cancels a prefix
+                    bank.update(torch.from_numpy(ent).cuda()[:1000], torch.from_numpy(key).cuda()[:1000],
+                                torch.from_numpy(inc).cuda()[:1000])
+                bank.check()
+                assert bank.read().tobytes() == want.tobytes(), (gmin, where)
+                bank.close()
+    finally:
+        ctx.set_option(N.OPT_GROUP_MIN_EVENTS, 1 << 16)
+
+
+def test_grouped_csr_update_and_errors(mb, ctx):
+    """mb200_bank_update_grouped: one preference array per entity (CosineCM.exportProfile's shape)."""
+    import torch
+    from mahout_b200 import _native as N
+    rng = np.random.Generator(np.random.PCG64(91))
+    E, d, w, n = 900, 4, 4096, 250000
+    ent = np.sort(_zipf_entities(rng, n, E))
+    key = rng.integers(-5, 2 ** 33, n).astype(np.int64)
+    inc = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
+    row_ptr = np.searchsorted(ent, np.arange(E + 1)).astype(np.int64)
+    a, b = orc.hash_params(42, d)
+    want = np.zeros((E, d, w))
+    orc.bank_update(want, d, w, a, b, ent, key, inc)
+    for where in ("host", "device"):
+        bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+        if where == "host":
+            bank.update_grouped(row_ptr, key, inc)
+        else:
+            bank.update_grouped(torch.from_numpy(row_ptr).cuda(), torch.from_numpy(key).cuda(), torch.from_numpy(inc).cuda())
+        bank.check()
+        assert bank.read().tobytes() == want.tobytes(), where
+        bank.close()
+    bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+    bad = row_ptr.copy()
+    bad[10] = bad[11] + 3
+    with pytest.raises(ValueError):
+        bank.update_grouped(torch.from_numpy(bad).cuda(), torch.from_numpy(key).cuda(), torch.from_numpy(inc).cuda())
+    bank.close()
+    # grouped path keeps the status words: a bad entity and an inexact increment still surface
+    ctx.set_option(N.OPT_GROUP_MIN_EVENTS, 0)
+    try:
+        bank = mb.SketchBank(50, 64, 2, 42, 1, ctx)
+        e = rng.integers(0, 50, 5000).astype(np.int64)
+        e[17] = 50
+        bank.update(e, np.arange(5000), np.ones(5000, np.float32))
+        with pytest.raises(ValueError):
+            bank.check()
+        bank.close()
+        bank = mb.SketchBank(50, 64, 2, 42, 1, ctx)
+        v = np.ones(5000, np.float32)
+        v[99] = 0.3
+        bank.update(rng.integers(0, 50, 5000).astype(np.int64), np.arange(5000), v)
+        with pytest.raises(mb.InexactError):
+            bank.check()
+        bank.close()
+    finally:
+        ctx.set_option(N.OPT_GROUP_MIN_EVENTS, 1 << 16)
+
+
 def test_update_unaligned_and_tail(mb, ctx):
     """odd offsets defeat the 16-byte vector loads; n % 4 != 0 exercises the tail."""
     import torch
