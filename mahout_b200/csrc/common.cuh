@@ -81,6 +81,7 @@ struct mb200_bank {
   long long* counters = nullptr;  // [E][d][W] fixed point
   unsigned long long* flags = nullptr;  // FLAG_WORDS
   double events_total = 0;  // for the conservative range bound
+  bool virgin = true;       // nothing has been added since creation / clear: the counters are all zero
 };
 
 int mb200_fail(mb200_ctx* ctx, int code, const char* fmt, ...);

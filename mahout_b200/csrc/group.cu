@@ -40,7 +40,7 @@ constexpr int U_WINDOW = 32768;              // grouped records per update work 
 constexpr int U_TILE_MIN = 128;              // records of one entity in a window that pay for a tile
 constexpr int Q_NARROW = 1 << 15;            // |quanta| below this: 32 Ki of them cannot overflow an int32
 constexpr int HIST_SLOTS_LOG2 = 12;
-constexpr long long SUB_BATCH = 1LL << 27;   // events grouped per pass (bounds the workspace: 20 B/event)
+constexpr long long SUB_BATCH = 1LL << 30;   // events grouped per pass (u32 record offsets; workspace: 20 B/event)
 
 // ---- block-wide exclusive scan of nb <= 4 * G_THREADS shared-memory words ---------------------------
 // in[] -> out[] (exclusive), returns the total to every thread.  wsum: G_THREADS / 32 + 1 words.
@@ -95,12 +95,10 @@ __global__ void __launch_bounds__(512) k_group_hist(const long long* __restrict_
   }
   __syncthreads();
   unsigned bad = 0;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-    const long long e = __ldg(entity + t);
+  auto count = [&](long long e) {
     if (e < 0 || e >= E) {
       bad++;
-      continue;
+      return;
     }
     const unsigned te = (unsigned)e + 1u;
     const unsigned slot = ((unsigned)e * 0x9E3779B1u) >> (32 - HIST_SLOTS_LOG2);
@@ -111,6 +109,23 @@ __global__ void __launch_bounds__(512) k_group_hist(const long long* __restrict_
     }
     if (cur == te) atomicAdd(&cnt[slot], 1u);
     else atomicAdd(&hist[e], 1u);
+  };
+  // 16-byte loads, four entities per thread per trip (two loads in flight); the unaligned head and the
+  // tail go one by one
+  const long long head = ((uintptr_t)entity & 8) ? 1 : 0;
+  const long long n4 = head + ((n - head) & ~3LL);
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long t = head + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; t < n4; t += stride) {
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(entity + t));
+    const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(entity + t + 2));
+    count(a.x);
+    count(a.y);
+    count(b.x);
+    count(b.y);
+  }
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < head) count(entity[threadIdx.x]);
+    if (n4 + threadIdx.x < n) count(entity[n4 + threadIdx.x]);
   }
   __syncthreads();
   for (int s = threadIdx.x; s < (1 << HIST_SLOTS_LOG2); s += blockDim.x)
@@ -222,8 +237,18 @@ struct Scatter1Args {
   long long cells;
   double qscale;
   unsigned long long* flags;
+  unsigned* wide_seen;  // set when an event took the direct path (the bank is then no longer all-zero)
   HashFamily hf;
 };
+
+// float increments: with a power-of-two quantum the scaling is exact in float, and an integral value below
+// 2^15 is the common case -- no FP64 on that path
+__device__ __forceinline__ bool quanta_fast(float v, float qscale_f, int& q) {
+  const float qf = v * qscale_f;
+  q = (int)qf;
+  return fabsf(qf) < (float)Q_NARROW && (float)q == qf;
+}
+__device__ __forceinline__ bool quanta_fast(double, float, int&) { return false; }
 
 template <typename T, int D>
 __global__ void __launch_bounds__(G_THREADS, 2) k_group_scatter1(const Scatter1Args<T> p) {
@@ -232,6 +257,8 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_group_scatter1(const Scatter1A
   const int tid = threadIdx.x;
   unsigned bad = 0;
   unsigned long long maxabs = 0;
+  bool wide = false;
+  const float qscale_f = (float)p.qscale;
   const long long ntiles = (p.n + G_TILE - 1) / G_TILE;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long base = tile * G_TILE;
@@ -249,7 +276,15 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_group_scatter1(const Scatter1A
         const long long k = __ldg(p.key + idx);
         const T v = __ldg(p.inc + idx);
         if (e >= 0 && e < p.E) {  // bad entities were counted by P0
-          const long long q = inc_to_quanta(v, p.qscale, bad, maxabs);
+          int qi;
+          long long q;
+          if (quanta_fast(v, qscale_f, qi)) {
+            q = qi;
+            const unsigned aq = (unsigned)(qi < 0 ? -qi : qi);
+            maxabs = aq > maxabs ? aq : maxabs;
+          } else {
+            q = inc_to_quanta(v, p.qscale, bad, maxabs);
+          }
           if (q != 0) {
             if ((unsigned long long)k < (1ull << 32) && q > -Q_NARROW && q < Q_NARROW) {
               ok[i] = true;
@@ -258,6 +293,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_group_scatter1(const Scatter1A
               rank[i] = atomicAdd(&sm.hist[(unsigned)e >> p.shift], 1u);
             } else {
               scatter_event<D>(p.counters + (size_t)e * p.cells, p.hf, k, q);
+              wide = true;
             }
           }
         }
@@ -286,6 +322,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_group_scatter1(const Scatter1A
     }
     __syncthreads();
   }
+  if (wide) *p.wide_seen = 1u;
   publish_flags(p.flags, bad, 0u, maxabs);
 }
 
@@ -380,7 +417,9 @@ struct GroupedArgs {
   double qscale;
   unsigned long long* flags;
   unsigned* ticket;
+  const unsigned* wide_seen;  // may be null
   int tile_ok;  // d * W int32 cells fit the shared-memory tile
+  int virgin;   // the bank held only zeros when the call started: exclusive tiles are stored, not added
   HashFamily hf;
 };
 
@@ -427,13 +466,14 @@ __global__ void __launch_bounds__(U_THREADS, 2) k_update_grouped(const Src src, 
   int* tile = reinterpret_cast<int*>(smem_raw);
   __shared__ long long s_first;            // first entity of the window
   __shared__ unsigned s_next, s_work;      // next entity batch (relative), current window
-  __shared__ int s_dense_n;
+  __shared__ int s_dense_n, s_wide;
   __shared__ unsigned s_dense[U_DENSE_MAX];  // entities (relative to s_first) that take the tile path
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned bad = 0;
   unsigned long long maxabs = 0;
   const long long total = (long long)p.seg[p.E];
   const long long nwin = (total + U_WINDOW - 1) / U_WINDOW;
+  const bool store_only = p.virgin && (p.wide_seen == nullptr || *p.wide_seen == 0u);
   for (;;) {
     __syncthreads();
     if (tid == 0) s_work = atomicAdd(p.ticket, 1u);
@@ -521,31 +561,62 @@ __global__ void __launch_bounds__(U_THREADS, 2) k_update_grouped(const Src src, 
       int4* t4 = reinterpret_cast<int4*>(tile);
       const int c4 = (int)((p.cells + 3) >> 2);
       for (int c = tid; c < c4; c += U_THREADS) t4[c] = make_int4(0, 0, 0, 0);
+      if (tid == 0) s_wide = 0;
       __syncthreads();
       long long* ctr = p.counters + (size_t)e * p.cells;
+      bool wide = false;
 #pragma unroll 4
       for (long long r = r0 + tid; r < r1; r += U_THREADS) {
         long long key, q;
         bool narrow;
         if (fetch(src, r, p.qscale, bad, maxabs, key, q, narrow)) {
-          if (narrow) tile_add<D>(tile, p.hf, (uint32_t)key, (int)q);
-          else scatter_event<D>(ctr, p.hf, key, q);
+          if (narrow) {
+            tile_add<D>(tile, p.hf, (uint32_t)key, (int)q);
+          } else {
+            scatter_event<D>(ctr, p.hf, key, q);
+            wide = true;
+          }
         }
       }
+      if (wide) s_wide = 1;
       __syncthreads();
-      if (exclusive && (p.cells & 3) == 0) {
-        // this CTA is the only writer of the entity during the kernel: plain 32-byte RMW per touched sector
+      // Only this CTA touches the entity during the kernel when all of its records sit in this window --
+      // unless some of them just went straight to the counters with RED (a non-atomic read-modify-write
+      // could then lose them).  Then: touched 32-byte sectors are stored (virgin bank) or read, added and
+      // stored; otherwise every non-zero cell is added with RED.ADD.64.
+      if (exclusive && (p.cells & 3) == 0 && !s_wide) {
         longlong2* g2 = reinterpret_cast<longlong2*>(ctr);
-        for (int c = tid; c < c4; c += U_THREADS) {
-          const int4 v = t4[c];
-          if (v.x | v.y | v.z | v.w) {
-            longlong2 a = g2[2 * c], b2 = g2[2 * c + 1];
-            a.x += v.x;
-            a.y += v.y;
-            b2.x += v.z;
-            b2.y += v.w;
-            g2[2 * c] = a;
-            g2[2 * c + 1] = b2;
+        if (store_only) {
+          for (int c = tid; c < c4; c += U_THREADS) {
+            const int4 v = t4[c];
+            if (v.x | v.y | v.z | v.w) {
+              g2[2 * c] = make_longlong2(v.x, v.y);
+              g2[2 * c + 1] = make_longlong2(v.z, v.w);
+            }
+          }
+        } else {
+          for (int c = tid; c < c4; c += 2 * U_THREADS) {
+            const int c1 = c + U_THREADS;
+            const int4 v0 = t4[c];
+            const int4 v1 = c1 < c4 ? t4[c1] : make_int4(0, 0, 0, 0);
+            const bool n0 = (v0.x | v0.y | v0.z | v0.w) != 0, n1 = (v1.x | v1.y | v1.z | v1.w) != 0;
+            longlong2 a0, b0, a1, b1;
+            if (n0) {
+              a0 = g2[2 * c];
+              b0 = g2[2 * c + 1];
+            }
+            if (n1) {
+              a1 = g2[2 * c1];
+              b1 = g2[2 * c1 + 1];
+            }
+            if (n0) {
+              g2[2 * c] = make_longlong2(a0.x + v0.x, a0.y + v0.y);
+              g2[2 * c + 1] = make_longlong2(b0.x + v0.z, b0.y + v0.w);
+            }
+            if (n1) {
+              g2[2 * c1] = make_longlong2(a1.x + v1.x, a1.y + v1.y);
+              g2[2 * c1 + 1] = make_longlong2(b1.x + v1.z, b1.y + v1.w);
+            }
           }
         }
       } else {
@@ -591,7 +662,8 @@ int ws_get(mb200_ctx* ctx, size_t slot, size_t bytes, void** out) {
 }
 
 template <typename Src, typename IdxT>
-int launch_grouped(mb200_bank* bk, const Src& src, const IdxT* seg, const IdxT* end, unsigned* ticket) {
+int launch_grouped(mb200_bank* bk, const Src& src, const IdxT* seg, const IdxT* end, unsigned* ticket,
+                   const unsigned* wide_seen) {
   mb200_ctx* ctx = bk->ctx;
   GroupedArgs<IdxT> ga;
   ga.seg = seg;
@@ -602,6 +674,8 @@ int launch_grouped(mb200_bank* bk, const Src& src, const IdxT* seg, const IdxT* 
   ga.qscale = ldexp(1.0, bk->frac_bits);
   ga.flags = bk->flags;
   ga.ticket = ticket;
+  ga.wide_seen = wide_seen;
+  ga.virgin = bk->virgin ? 1 : 0;
   ga.hf = bk->hf;
   size_t tile_bytes = (((size_t)ga.cells * 4) + 15) & ~(size_t)15;
   // two CTAs per SM while the tile allows it
@@ -622,6 +696,7 @@ int launch_grouped(mb200_bank* bk, const Src& src, const IdxT* seg, const IdxT* 
 #undef LAUNCH_U
   ctx->launches++;
   MB_CUDA(ctx, cudaGetLastError());
+  bk->virgin = false;
   return MB200_OK;
 }
 
@@ -693,6 +768,7 @@ int mb200_group_update(mb200_bank* bk, const long long* entity, const long long*
     a1.cells = (long long)bk->d * bk->W;
     a1.qscale = ldexp(1.0, bk->frac_bits);
     a1.flags = bk->flags;
+    a1.wide_seen = ticket + 1;
     a1.hf = bk->hf;
     if (two_level) {
       k_init_coarse<<<(nb1 + 1 + 255) / 256, 256, 0, ctx->stream>>>(seg, E, shift, nb1, cur1, base1);
@@ -737,7 +813,7 @@ int mb200_group_update(mb200_bank* bk, const long long* entity, const long long*
     }
     NarrowSrc src{kq2};
     ProfScope prof_update(ctx, MB200_K_UPDATE);
-    MB_CHECK((launch_grouped<NarrowSrc, unsigned>(bk, src, seg, cur2, ticket)));
+    MB_CHECK((launch_grouped<NarrowSrc, unsigned>(bk, src, seg, cur2, ticket, ticket + 1)));
   }
   bk->events_total += (double)n;
   return MB200_OK;
@@ -788,7 +864,7 @@ extern "C" int mb200_bank_update_grouped(mb200_bank* bk, const int64_t* row_ptr,
       return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_update_grouped: row_ptr is not a non-decreasing sequence from 0 to n");
     WideSrc<float> src{d_key, d_inc};
     ProfScope prof(ctx, MB200_K_UPDATE);
-    MB_CHECK((launch_grouped<WideSrc<float>, long long>(bk, src, d_ptr, d_ptr + 1, ticket)));
+    MB_CHECK((launch_grouped<WideSrc<float>, long long>(bk, src, d_ptr, d_ptr + 1, ticket, nullptr)));
   }
   bk->events_total += (double)n;
   if (mem == MB200_MEM_HOST) MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -394,6 +394,7 @@ static int launch_update(mb200_bank* bk, const long long* entity, const long lon
   ctx->launches++;
   MB_CUDA(ctx, cudaGetLastError());
   bk->events_total += (double)n;
+  bk->virgin = false;
   return MB200_OK;
 }
 
@@ -628,12 +629,14 @@ int mb200_bank_clear(mb200_bank* bk) {
   MB_CUDA(ctx, cudaMemsetAsync(bk->counters, 0, (size_t)bk->E * bk->d * bk->W * sizeof(long long), ctx->stream));
   MB_CUDA(ctx, cudaMemsetAsync(bk->flags, 0, FLAG_WORDS * sizeof(unsigned long long), ctx->stream));
   bk->events_total = 0;
+  bk->virgin = true;
   return MB200_OK;
 }
 
 int mb200_bank_counters(mb200_bank* bk, void** device_ptr, int64_t* cells) {
   if (!bk || !device_ptr) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_counters: NULL argument");
   *device_ptr = bk->counters;
+  bk->virgin = false;  // the caller may write through the pointer (e.g. an all-reduce in place)
   if (cells) *cells = bk->E * (int64_t)bk->d * bk->W;
   return MB200_OK;
 }

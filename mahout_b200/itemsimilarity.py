@@ -95,7 +95,7 @@ class ItemSimilarityJob:
                 pairs = sim.most_similar_item_pairs(idx, s, cnt, prep.item_id)
                 if args.similarityMatrixOutput:
                     from . import seqfile
-                    seqfile.write_similarity_matrix(args.similarityMatrixOutput, idx, s, cnt, prep.num_items)
+                    seqfile.write_similarity_matrix(args.similarityMatrixOutput, idx, s, cnt, prep.index_values)
             prep.close()
             with open(args.output, "w") as out:
                 for a, b, v in pairs:

@@ -183,17 +183,35 @@ def read_sequence_file(path: str):
     return out
 
 
-def write_similarity_matrix(path: str, idx, sim, cnt, num_columns: int | None = None):
-    """rows of the top-k similarity matrix (idx [N,k], sim [N,k], cnt [N]) as RowSimilarityJob writes them:
-    key = row index, value = RandomAccessSparseVector(numberOfColumns) of the kept similarities.  Rows
-    without similarities are not written (the reducer never sees them)."""
+INT_MAX = 2147483647
+
+
+def write_similarity_matrix(path: str, idx, sim, cnt, index_values=None, num_columns: int | None = None):
+    """rows of the top-k similarity matrix (idx [N,k], sim [N,k], cnt [N]) as RowSimilarityJob writes them.
+
+    `index_values[r]` is the idToIndex value of dense row r (Prefs.index_values): the reference keys the rows
+    of the item-item matrix by TasteHadoopUtils.idToIndex(itemID) (ToItemVectorsMapper.java:41-53 builds the
+    item vectors under that index), the vector indices are the same index space, and every vector has
+    cardinality Integer.MAX_VALUE (RandomAccessSparseVector(Integer.MAX_VALUE, ...), kept by
+    Vectors.topKElements: `new RandomAccessSparseVector(original.size(), k)`, Vectors.java:74).  Phase 2
+    (MostSimilarItemPairsMapper) and RecommenderJob resolve these indexes through the itemIDIndex map.
+    Without `index_values` the dense row numbers are written with cardinality `num_columns` (a plain
+    RowSimilarityJob over an already dense matrix, --numberOfColumns).  Rows without similarities are not
+    written (the reducer never sees them)."""
     idx, sim, cnt = np.asarray(idx), np.asarray(sim), np.asarray(cnt)
-    n_cols = int(num_columns if num_columns is not None else idx.shape[0])
+    if index_values is not None:
+        index_values = np.asarray(index_values, np.int64)
+        n_cols = INT_MAX
+    else:
+        n_cols = int(num_columns if num_columns is not None else idx.shape[0])
     with SequenceFileWriter(path) as w:
         for r in range(idx.shape[0]):
             c = int(cnt[r])
             if c:
-                w.append(r, vector_writable(n_cols, idx[r, :c], sim[r, :c]))
+                if index_values is not None:
+                    w.append(int(index_values[r]), vector_writable(n_cols, index_values[idx[r, :c]], sim[r, :c]))
+                else:
+                    w.append(r, vector_writable(n_cols, idx[r, :c], sim[r, :c]))
 
 
 def read_similarity_matrix(path: str):

@@ -56,3 +56,27 @@ def test_sequence_file_round_trip_with_sync_escapes(tmp_path):
     assert sorted(back) == [r for r in range(N) if cnt[r]]
     for r, (i, v) in back.items():
         assert i.tolist() == idx[r, :cnt[r]].tolist() and v.tolist() == sim[r, :cnt[r]].tolist()
+
+
+def test_similarity_matrix_is_keyed_by_id_to_index(tmp_path):
+    """What phase 2 / RecommenderJob read: keys and vector indices are TasteHadoopUtils.idToIndex(itemID), the
+    cardinality is Integer.MAX_VALUE; decoding through the oracle's idToIndex map gives back the item IDs."""
+    import oracle as orc
+    item_id = np.array([10, 2 ** 31 + 5, 77, 2 ** 40 + 3, 123456789012], np.int64)     # dense row -> itemID
+    index_values = np.array([orc.id_to_index(int(t)) for t in item_id], np.int64)
+    order = np.argsort(index_values)                                                   # rows ascend by index
+    item_id, index_values = item_id[order], index_values[order]
+    idx = np.array([[1, 2], [0, -1], [4, 3], [2, -1], [-1, -1]], np.int64)
+    sim = np.array([[0.9, 0.5], [0.9, 0.0], [0.7, 0.6], [0.6, 0.0], [0.0, 0.0]])
+    cnt = np.array([2, 1, 2, 1, 0], np.int32)
+    path = str(tmp_path / "part-r-00000")
+    sf.write_similarity_matrix(path, idx, sim, cnt, index_values)
+    index_to_id = {int(i): int(t) for i, t in zip(index_values, item_id)}
+    rows = sf.read_sequence_file(path)
+    assert [k for k, _ in rows] == [int(index_values[r]) for r in range(4)]
+    for r, (key, value) in enumerate(rows):
+        size, i, v, _ = sf.parse_vector_writable(value)
+        assert size == 2147483647
+        assert index_to_id[key] == int(item_id[r])
+        assert [index_to_id[int(c)] for c in i] == [int(item_id[c]) for c in idx[r, :cnt[r]]]
+        assert v.tolist() == sim[r, :cnt[r]].tolist()
