@@ -244,6 +244,9 @@ int mb200_bank_cosine_topk(mb200_bank* bank, int32_t k, double threshold, int ex
 int64_t mb200_row_ld(int32_t width);
 int64_t mb200_valid_words(int64_t rows);
 int mb200_bank_normalize(mb200_bank* bank, int dtype, void* rows16, uint32_t* valid);
+/* after mb200_bank_normalize: did K2 see a negative counter (or a row norm >= 2^36 quanta)?  Synchronises.
+ * Sticky until mb200_bank_clear.  Feed the OR over all banks of a job into mb200_cosine_args.mixed_sign. */
+int mb200_bank_sign_info(mb200_bank* bank, int32_t* mixed_sign);
 
 typedef struct mb200_cosine_args {
   /* A side: the entities this GPU answers for */
@@ -287,6 +290,12 @@ typedef struct mb200_cosine_args {
    * counter that does not fit is stored as INT_MIN and sends the row to the exact full-row path,
    * which reads b_counter_blocks */
   const int32_t* const* b_counter_blocks32;
+  /* non-zero when any counter of the A or B side may be negative (negative increments, rating_shift) or a
+   * row norm reaches 2^36 quanta -- mb200_bank_sign_info of every bank involved, OR-ed.  The tensor-core
+   * values then carry an absolute instead of a relative error bound, and RESCORED / CERTIFIED widen their
+   * admission threshold, certification bound and undecided band accordingly.  mb200_bank_cosine_topk
+   * sets it by itself. */
+  int32_t mixed_sign;
 } mb200_cosine_args;
 
 int mb200_cosine_topk(mb200_ctx* ctx, const mb200_cosine_args* args);

@@ -52,7 +52,7 @@ class CosineArgs(C.Structure):
         ("a_counters", C.c_void_p), ("b_counters", C.c_void_p),
         ("out_idx", C.c_void_p), ("out_sim", C.c_void_p), ("out_cnt", C.c_void_p),
         ("dense_out", C.c_void_p), ("dense_ld", C.c_int64),
-        ("b_counter_blocks", C.c_void_p), ("b_counter_blocks32", C.c_void_p),
+        ("b_counter_blocks", C.c_void_p), ("b_counter_blocks32", C.c_void_p), ("mixed_sign", C.c_int32),
     ]
 
 
@@ -111,6 +111,7 @@ _PROTOS = {
     "mb200_row_ld": (i64, [i32]),
     "mb200_valid_words": (i64, [i64]),
     "mb200_bank_normalize": (C.c_int, [vp, C.c_int, vp, vp]),
+    "mb200_bank_sign_info": (C.c_int, [vp, C.POINTER(i32)]),
     "mb200_cosine_topk": (C.c_int, [vp, C.POINTER(CosineArgs)]),
     "mb200_events_parse": (C.c_int, [vp, vp, i64, C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(vp)]),
     "mb200_events_create": (C.c_int, [vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp)]),

@@ -20,7 +20,9 @@ struct HashFamily {
 };
 
 // device-side status words (one set per bank)
-enum { FLAG_INEXACT = 0, FLAG_MAXABS = 1, FLAG_BAD_ENTITY = 2, FLAG_RANGE = 3, FLAG_WORDS = 4 };
+enum { FLAG_INEXACT = 0, FLAG_MAXABS = 1, FLAG_BAD_ENTITY = 2, FLAG_RANGE = 3,
+       FLAG_MIXED = 4,  // K2 saw a negative counter or a row norm >= 2^36 quanta (see mb200_bank_sign_info)
+       FLAG_WORDS = 5 };
 
 struct ProfSpan {
   int kernel_id;

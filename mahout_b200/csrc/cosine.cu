@@ -91,7 +91,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__ counters, long long E,
                                                    int d, int W, int ld, float scale,
                                                    OutT* __restrict__ out, uint32_t* __restrict__ valid,
-                                                   long long vw) {
+                                                   long long vw, unsigned long long* __restrict__ flags) {
   __shared__ double red[8];
   const long long bid = blockIdx.x;
   const long long e = bid / d;
@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__
   const bool in_regs = (W & 1) == 0 && W <= 256 * NORM_VPT;
   long long v[NORM_VPT];
   double ss = 0.0;
+  bool neg = false;
   if (in_regs) {
     const longlong2* row2 = reinterpret_cast<const longlong2*>(row);
     const int pairs = W >> 1;
@@ -111,14 +112,18 @@ __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__
       if (j < pairs) x = __ldg(row2 + j);
       v[2 * t] = x.x;
       v[2 * t + 1] = x.y;
+      neg |= x.x < 0 || x.y < 0;
       ss += (double)x.x * (double)x.x + (double)x.y * (double)x.y;
     }
   } else {
     for (int j = threadIdx.x; j < W; j += blockDim.x) {
-      const double x = (double)row[j];
+      const long long xi = row[j];
+      neg |= xi < 0;
+      const double x = (double)xi;
       ss += x * x;
     }
   }
+  if (neg) flags[FLAG_MIXED] = 1ull;
   for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
@@ -126,6 +131,9 @@ __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__
 #pragma unroll
   for (int w = 0; w < 8; w++) tot += red[w];
   const double nrm = sqrt(tot);
+  // a counter of 1 quantum must stay non-zero in the 16-bit row (x / ||x|| * 2^12 > 2^-24): "tensor value 0
+  // <=> exact similarity 0" is what lets non-negative data drop zero products unseen
+  if (threadIdx.x == 0 && nrm >= 0x1.0p36) flags[FLAG_MIXED] = 1ull;
   const double inv = nrm > 0.0 ? (double)scale / nrm : 0.0;
   if (in_regs) {
     // ld is even and the row base is 4-byte aligned: two 16-bit outputs per store
@@ -766,6 +774,8 @@ struct RescoreParams {
   const float* cand_val;       // CERTIFIED: tensor values of the candidates
   float inv_scale2;
   float eps_rel;               // relative error bound of the tensor-core values
+  float eps_abs;               // absolute error bound (similarity units); = eps_rel for mixed-sign counters
+  int mixed;                   // counters may be negative (mb200_cosine_args.mixed_sign)
   int32_t k;
   double threshold;
   long long* out_idx;
@@ -875,7 +885,8 @@ __device__ __forceinline__ void rescore_finish_t(const RescoreParams& p, long lo
     const float b = p.cand_bound[r];
     int flag = bad_flag;
     if (b > -INFINITY && !certified_elsewhere) {
-      const double ub = (double)(b * p.inv_scale2) * (1.0 + (double)p.eps_rel) + (double)p.eps_rel * 1e-3;
+      const double bs = (double)(b * p.inv_scale2);
+      const double ub = bs + fabs(bs) * (double)p.eps_rel + (double)p.eps_abs;
       if (!(kth > ub)) flag = 1;
     }
     p.row_flag[r] = flag;
@@ -1024,15 +1035,19 @@ __global__ void __launch_bounds__(256) k_certify(const RescoreParams p) {
   const int k = p.k;
   const float vk = n > 0 ? val[min(k, n) - 1] : 0.0f;                 // k-th (or last) tensor value
   const float vk1 = n > k ? val[k] : -INFINITY;                       // (k+1)-th
-  const float band_hi = vk1 / (1.0f - e2), band_lo = vk / (1.0f + e2);
-  const float thr = (float)(p.threshold / (double)p.inv_scale2);      // threshold in the scaled domain
+  // with mixed-sign counters the error of a tensor value is absolute (eps * sum|x_i y_i| <= eps): ea2 widens
+  // every band by it, and the positivity cut (sim > Double.MIN_VALUE) becomes a threshold to certify too
+  const float ea2 = p.mixed ? 2.0f * p.eps_abs / p.inv_scale2 : 0.0f;
+  const float band_hi = vk1 + fabsf(vk1) * (e2 / (1.0f - e2)) + ea2;
+  const float band_lo = vk - fabsf(vk) * (e2 / (1.0f + e2)) - ea2;
+  const float thr = (float)((p.threshold > 0.0 ? p.threshold : 0.0) / (double)p.inv_scale2);   // scaled domain
   for (int c = tid; c < CAP; c += blockDim.x) {
     s_min[c] = JAVA_MAX_DOUBLE;
     if (c < n) {
       const float v = val[c];
       s_fin[c] = (double)(v * p.inv_scale2);
       const bool near_cut = (c < k && v <= band_hi) || (c >= k && v >= band_lo);
-      const bool near_thr = p.threshold > 0.0 && fabsf(v - thr) <= e2 * thr + 1e-30f;
+      const bool near_thr = (p.threshold > 0.0 || p.mixed) && fabsf(v - thr) <= e2 * thr + ea2 + 1e-30f;
       if (near_cut || near_thr) s_sel[atomicAdd(&s_nsel, 1)] = c;
     }
   }
@@ -1612,13 +1627,25 @@ static int normalize_locked(mb200_bank* bk, int dtype, void* rows16, uint32_t* v
     ProfScope prof(ctx, MB200_K_NORMALIZE);
     if (dtype == MB200_DTYPE_F16)
       k_normalize<__half><<<(unsigned)blocks, 256, 0, ctx->stream>>>(bk->counters, bk->E, bk->d, bk->W, ld, F16_SCALE,
-                                                                     (__half*)rows16, valid, vw);
+                                                                     (__half*)rows16, valid, vw, bk->flags);
     else
       k_normalize<__nv_bfloat16><<<(unsigned)blocks, 256, 0, ctx->stream>>>(bk->counters, bk->E, bk->d, bk->W, ld, 1.0f,
-                                                                            (__nv_bfloat16*)rows16, valid, vw);
+                                                                            (__nv_bfloat16*)rows16, valid, vw, bk->flags);
   }
   ctx->launches++;
   MB_CUDA(ctx, cudaGetLastError());
+  return MB200_OK;
+}
+
+int mb200_bank_sign_info(mb200_bank* bk, int32_t* mixed_sign) {
+  if (!bk || !mixed_sign) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_sign_info: NULL argument");
+  mb200_ctx* ctx = bk->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  unsigned long long mixed = 0;
+  MB_CUDA(ctx, cudaMemcpyAsync(&mixed, bk->flags + FLAG_MIXED, sizeof(mixed), cudaMemcpyDeviceToHost, ctx->stream));
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *mixed_sign = mixed ? 1 : 0;
   return MB200_OK;
 }
 
@@ -1715,7 +1742,11 @@ static int job_begin_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t w
   j->ld = (int)mb200_row_ld(a->width);
   const float scale = a->dtype == MB200_DTYPE_F16 ? F16_SCALE : 1.0f;
   j->scale2 = scale * scale;
-  j->eps_rel = a->dtype == MB200_DTYPE_F16 ? 0x1.0p-10f : 0x1.0p-6f;
+  // error bound of a tensor-core similarity: two operand roundings (2 * 2^-11 for F16's 11-bit significand,
+  // 2 * 2^-8 for BF16 -- the budget below keeps the factor 4 of the first release) plus the FP32 accumulation:
+  // products of 16-bit operands are exact in FP32, one rounding/truncation (<= 2^-23 relative to the running
+  // sum of |terms|) per K = 16 MMA step, ld / 16 steps, doubled for the alignment inside a step
+  j->eps_rel = (a->dtype == MB200_DTYPE_F16 ? 0x1.0p-10f : 0x1.0p-6f) + (float)(j->ld / 16 + 16) * 0x1.0p-22f;
   j->ws_state = ws_base;
   j->ws_base = j->ws_next = ws_base + 3;
   const size_t rows_pad = (size_t)j->num_m * BM;
@@ -1973,8 +2004,11 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   {
     const double thr = a->threshold > 0.0 ? a->threshold : 0.0;
     const double slack = j->rescored ? (1.0 - (double)j->eps_rel) : (1.0 - 1e-6);
-    p.thr_init = (float)(thr * slack * (double)j->scale2);
-    if (thr > 0.0) p.thr_init = nextafterf(p.thr_init, -INFINITY);
+    // mixed-sign counters: a pair whose exact similarity clears the threshold (or is merely positive) may show
+    // a tensor value up to eps lower
+    const double abs_slack = (j->rescored && a->mixed_sign) ? (double)j->eps_rel : 0.0;
+    p.thr_init = (float)((thr * slack - abs_slack) * (double)j->scale2);
+    if (thr > 0.0 || abs_slack > 0.0) p.thr_init = nextafterf(p.thr_init, -INFINITY);
   }
   p.ksel = j->ksel;
   p.lists = (uint2*)d_lists.p;
@@ -2112,6 +2146,8 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       rp.cand_bound = mp.cand_bound;
       rp.inv_scale2 = mp.inv_scale2;
       rp.eps_rel = j->eps_rel;
+      rp.mixed = a->mixed_sign ? 1 : 0;
+      rp.eps_abs = a->mixed_sign ? j->eps_rel : j->eps_rel * 1e-3f;
       rp.k = a->k;
       rp.threshold = mp.threshold;
       rp.out_idx = (long long*)fin->out_idx;
@@ -2293,6 +2329,12 @@ int mb200_bank_cosine_topk(mb200_bank* bk, int32_t k, double threshold, int excl
   a.threshold = threshold;
   a.exclude_self = exclude_self;
   a.a_counters = a.b_counters = (const int64_t*)bk->counters;
+  if (precision != MB200_PRECISION_TENSOR) {
+    unsigned long long mixed = 0;
+    MB_CUDA(ctx, cudaMemcpyAsync(&mixed, bk->flags + FLAG_MIXED, sizeof(mixed), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    a.mixed_sign = mixed ? 1 : 0;
+  }
   if (mem == MB200_MEM_HOST) {
     MB_CHECK(o_idx.alloc(ws, (size_t)bk->E * k * 8));
     MB_CHECK(o_sim.alloc(ws, (size_t)bk->E * k * 8));

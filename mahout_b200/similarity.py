@@ -173,19 +173,33 @@ class GpuShardBackend:
     def counters(self):
         return self.bank.counters_tensor()
 
+    def mixed_sign(self, precision, group=None) -> bool:
+        """OR over all ranks of mb200_bank_sign_info (after K2); only the exact-set precisions need it"""
+        if precision == "tensor":
+            return False
+        m = self.bank.sign_info()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            import torch
+            t = torch.tensor([int(m)], dtype=torch.int32, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            m = bool(t.item())
+        return m
+
     def cosine(self, plan, a_rows, a_valid, b_rows, b_valid, k, threshold, dtype, precision,
-               a_counters=None, b_counters=None):
+               a_counters=None, b_counters=None, mixed_sign=False):
         idx, sim, cnt = sk.cosine_topk_blocks(
             self.ctx, a_rows, a_valid, b_rows, b_valid, self.bank.d, self.bank.w, k,
             a_id=(plan.G, plan.rank), b_id=(plan.G, 1) if plan.G > 1 else (1, plan.rows_per_shard),
             threshold=threshold, exclude_self=True, dtype=dtype, precision=precision,
-            a_counters=a_counters, b_counters=b_counters)
+            a_counters=a_counters, b_counters=b_counters, mixed_sign=mixed_sign)
         return idx, sim, cnt
 
-    def begin(self, plan, a_rows, a_valid, k, threshold, dtype, precision):
+    def begin(self, plan, a_rows, a_valid, k, threshold, dtype, precision, mixed_sign=False):
         """incremental form of `cosine` (mb200_cosine_begin / push / finish)"""
         return sk.CosineJob(self.ctx, a_rows, a_valid, self.bank.d, self.bank.w, k, a_id=(plan.G, plan.rank),
-                            threshold=threshold, exclude_self=True, dtype=dtype, precision=precision)
+                            threshold=threshold, exclude_self=True, dtype=dtype, precision=precision,
+                            mixed_sign=mixed_sign)
 
     def close(self):
         self.bank.close()
@@ -230,7 +244,7 @@ def route_events(plan, row, user, pref, group=None):
 
 
 def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precision, group=None,
-                     chunk_rows: int = 2048, a_counters=None):
+                     chunk_rows: int = 2048, a_counters=None, mixed_sign: bool = False):
     """C1 overlapped with K3: the all-gather of the normalised rows runs in row chunks on
     a communication stream, two chunks ahead of the compute stream, and every gathered chunk
     [G, d, rows_c, ld] is pushed into one incremental cosine job as soon as it has landed.  Only two
@@ -248,7 +262,7 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
     vw_of = lambda n: (n + 255) // 256 * 8                                  # mb200_valid_words
     bufs = [torch.empty(G * d * rows_max * ld, dtype=a_rows.dtype, device=a_rows.device) for _ in range(nbuf)]
     vbufs = [torch.empty(G * d * vw_of(rows_max), dtype=a_valid.dtype, device=a_valid.device) for _ in range(nbuf)]
-    job = backend.begin(plan, a_rows, a_valid, k, threshold, dtype, precision)
+    job = backend.begin(plan, a_rows, a_valid, k, threshold, dtype, precision, **({"mixed_sign": True} if mixed_sign else {}))
     if cuda:
         ctx = backend.ctx
         prev = ctx.stream_ptr
@@ -451,7 +465,8 @@ class PeerRows:
 
 
 def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype: str = "f16",
-                        precision: str = "tensor", a_counters=None, b_counters=None, out=None, counter_blocks=None):
+                        precision: str = "tensor", a_counters=None, b_counters=None, out=None, counter_blocks=None,
+                        mixed_sign: bool = False):
     """C1 fused into K3: `peers.rows` / `peers.valid` hold this rank's normalised rows (K2 output).  One
     stream-ordered barrier makes every rank's rows final, the copy engines then pull the shards over
     NVLink while K3 -- launched immediately, once, over all blocks -- waits block by block on the arrival
@@ -462,7 +477,8 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
         peers.refresh_narrow()
     peers.barrier()
     ready = peers.pull()
-    job = backend.begin(plan, peers.rows, peers.valid, k, threshold, dtype, precision)
+    job = backend.begin(plan, peers.rows, peers.valid, k, threshold, dtype, precision,
+                        **({"mixed_sign": True} if mixed_sign else {}))
     try:
         job.push(peers.staging_rows, peers.staging_valid, id_mul=G, id_add=1, ready=ready, first_block=plan.rank)
         if precision != "tensor":
@@ -501,12 +517,12 @@ def _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_res
                 return None
             N.check(N.lib().mb200_bank_normalize(backend.bank.handle, sk._DTYPES[dtype], C.c_void_p(peers.rows.data_ptr()),
                                                  C.c_void_p(peers.valid.data_ptr())), ctx.handle)
-            kw = {}
+            kw = dict(mixed_sign=backend.mixed_sign(precision, group))
             if precision == "certified":
-                kw = dict(a_counters=backend.counters(), counter_blocks=peers.map_counters(backend.bank))
+                kw.update(a_counters=backend.counters(), counter_blocks=peers.map_counters(backend.bank))
             elif precision != "tensor":
                 a_cnt = backend.counters()
-                kw = dict(a_counters=a_cnt, b_counters=_all_gather(a_cnt, world, group))
+                kw.update(a_counters=a_cnt, b_counters=_all_gather(a_cnt, world, group))
             idx, sim, cnt = fused_gather_cosine(backend, plan, peers, k, threshold, dtype, precision, **kw)
             if gather_result:
                 parts = [_all_gather(t, world, group).cpu().numpy() for t in (idx, sim, cnt)]      # C3
@@ -566,10 +582,11 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
         # peer mappings are not available on this box (CUDA IPC refused): NCCL all-gather, then K3
     a_rows, a_valid = backend.normalized(dtype)
     a_cnt = backend.counters() if precision != "tensor" else None
+    mixed = backend.mixed_sign(precision, group) if hasattr(backend, "mixed_sign") else False
     if world > 1 and chunk_rows > 0:
         # C1 in row chunks, overlapped with K3 through the incremental cosine job
         idx, sim, cnt = pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precision, group,
-                                         chunk_rows, a_cnt)
+                                         chunk_rows, a_cnt, mixed)
     else:
         if world > 1:
             b_rows = _all_gather(a_rows, world, group)          # C1
@@ -580,7 +597,7 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
         if precision != "tensor":
             b_cnt = _all_gather(a_cnt, world, group) if world > 1 else a_cnt
         idx, sim, cnt = backend.cosine(plan, a_rows, a_valid, b_rows, b_valid, k, threshold, dtype, precision,
-                                       a_cnt, b_cnt)
+                                       a_cnt, b_cnt, **({"mixed_sign": True} if mixed else {}))
     if not gather_result:
         backend.close()
         return idx, sim, cnt

@@ -384,6 +384,13 @@ class SketchBank:
         self.ctx.sync()
         return rows, valid
 
+    def sign_info(self) -> bool:
+        """after normalize(): did K2 see a negative counter (or a row norm >= 2^36 quanta)?  The exact-set
+        precisions then work with absolute error bounds (mb200_cosine_args.mixed_sign)."""
+        m = C.c_int32()
+        N.check(N.lib().mb200_bank_sign_info(self.handle, C.byref(m)), self.ctx.handle)
+        return bool(m.value)
+
     def counters_tensor(self):
         """The raw int64 fixed-point counters [E, d, w] as a torch view (plumbing: collectives)."""
         p, n = self.counters_ptr()
@@ -402,7 +409,7 @@ _PRECISIONS = {"tensor": N.PRECISION_TENSOR, "rescored": N.PRECISION_RESCORED, "
 def cosine_topk_blocks(ctx: Context, a_rows, a_valid, b_rows, b_valid, depth: int, width: int, k: int,
                        a_id=(1, 0), b_id=(1, 0), threshold: float | None = None, exclude_self: bool = True,
                        dtype: str = "f16", precision: str = "tensor", a_counters=None, b_counters=None,
-                       block_n: int = 0, want_dense: bool = False, out=None):
+                       block_n: int = 0, want_dense: bool = False, out=None, mixed_sign: bool = False):
     """mb200_cosine_topk over device tensors: A rows [d, a_count, ld] against b_blocks gathered blocks
     B [blocks, d, b_count, ld].  Returns torch device tensors (idx, sim, cnt[, dense])."""
     import torch
@@ -425,6 +432,7 @@ def cosine_topk_blocks(ctx: Context, a_rows, a_valid, b_rows, b_valid, depth: in
     args.a_counters = a_counters.data_ptr() if a_counters is not None else None
     args.b_counters = b_counters.data_ptr() if b_counters is not None else None
     args.out_idx, args.out_sim, args.out_cnt = idx.data_ptr(), sim.data_ptr(), cnt.data_ptr()
+    args.mixed_sign = int(bool(mixed_sign))
     dense = None
     if want_dense:
         bn = block_n or 256
@@ -444,7 +452,7 @@ class CosineJob:
 
     def __init__(self, ctx: Context, a_rows, a_valid, depth: int, width: int, k: int, a_id=(1, 0),
                  threshold: float | None = None, exclude_self: bool = True, dtype: str = "f16",
-                 precision: str = "tensor", block_n: int = 0):
+                 precision: str = "tensor", block_n: int = 0, mixed_sign: bool = False):
         self.ctx, self.k, self.a_count = ctx, int(k), int(a_rows.shape[1])
         self._keep = [a_rows, a_valid]              # the job borrows these until finish
         args = N.CosineArgs()
@@ -452,6 +460,7 @@ class CosineJob:
         args.a_id_mul, args.a_id_off = a_id
         args.depth, args.width, args.dtype, args.precision = depth, width, _DTYPES[dtype], _PRECISIONS[precision]
         args.k, args.threshold, args.exclude_self, args.block_n = k, (threshold or 0.0), int(exclude_self), block_n
+        args.mixed_sign = int(bool(mixed_sign))
         self._args = args
         h = C.c_void_p()
         N.check(N.lib().mb200_cosine_begin(ctx.handle, C.byref(args), C.byref(h)), ctx.handle)

@@ -352,3 +352,35 @@ def test_rescore_kernel_variants_bit_equal(mb, ctx, variant, monkeypatch):
     assert (cnt == ocnt).all() and (idx == oidx).all()
     assert sim.tobytes() == osim.tobytes()
     bank.close()
+
+
+@pytest.mark.parametrize("precision", ["rescored", "certified"])
+@pytest.mark.parametrize("E,d,w,k", [(400, 4, 512, 20), (300, 1, 256, 50)])
+def test_mixed_sign_counters_exact_sets(mb, ctx, E, d, w, k, precision):
+    """Negative increments (mb200_bank_update accepts them; ingest's rating_shift produces them) give
+    mixed-sign counters: the tensor-core error is then absolute, similarities cluster around zero and many rows
+    have fewer than k positive ones.  The exact-set precisions must still return the oracle's sets."""
+    rng = np.random.Generator(np.random.PCG64(E + k))
+    n = 50 * E
+    item = rng.integers(0, E, n).astype(np.int64)
+    user = rng.integers(1, 2000, n).astype(np.int64)
+    pref = (rng.integers(-10, 11, n) * 0.5).astype(np.float32)
+    bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+    bank.update(item, user, pref)
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((E, d, w))
+    orc.bank_update(ref, d, w, a, b, item, user, pref)
+    assert (ref < 0).any()
+    idx, sim, cnt = bank.cosine_topk(k, precision=precision)
+    assert bank.sign_info()
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    assert (cnt == ocnt).all()
+    if precision == "rescored":
+        assert (idx == oidx).all() and sim.tobytes() == osim.tobytes()
+    else:
+        for r in range(E):
+            assert set(idx[r, :cnt[r]].tolist()) == set(oidx[r, :ocnt[r]].tolist()), r
+        m = oidx >= 0
+        # values are the tensor-core ones where the set was decided without re-scoring: absolute tolerance
+        assert np.abs(np.sort(sim, axis=1) - np.sort(osim, axis=1))[m.any(axis=1)].max() <= 2e-3
+    bank.close()

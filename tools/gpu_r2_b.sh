@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 GPU session B: grouped K1 after the store-only flush / big sub-batch; ncu --set full of the four kernels
 mkdir -p gpurun_out/r2b
-timeout 900 python -m pytest tests/test_sketch_gpu.py -x -q -m gpu -k "grouped or update" > gpurun_out/r2b/pytest_sketch.log 2>&1
+timeout 900 python -m pytest tests/test_sketch_gpu.py tests/test_cosine_gpu.py -x -q -m gpu > gpurun_out/r2b/pytest_sketch.log 2>&1
 echo "pytest_sketch rc=$?" | tee -a gpurun_out/r2b/summary.txt
 tail -3 gpurun_out/r2b/pytest_sketch.log
 for cfg in "26744 2e7 1 grouped" "125000 2.5e8 1 grouped" "125000 2.5e8 1 csr" "125000 1e9 1 grouped" "125000 1e9 1 csr" "125000 1e9 1 direct"; do
