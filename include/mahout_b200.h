@@ -185,7 +185,8 @@ int mb200_bank_cross_cosine(mb200_bank* bank_a, const int64_t* ea, mb200_bank* b
  * mb200_events_parse = ToEntityPrefsMapper.map (ToEntityPrefsMapper.java:56-76) over a whole text
  * buffer: lines `userID,itemID[,pref[,...]]` split on tab or comma; Long.parseLong / Float.parseFloat
  * (+ rating_shift); pref = 1.0 when absent or boolean_data; transpose swaps the first two columns.
- * Blank lines are skipped; a malformed line fails the call with MB200_ERR_BAD_ARG and a message
+ * Blank lines are skipped (a deliberate leniency for trailing newlines: the reference's mapper would
+ * throw NumberFormatException from Long.parseLong("")); a malformed line fails the call with MB200_ERR_BAD_ARG and a message
  * naming the Java exception and the byte offset.  Events keep the order of the lines. */
 typedef struct mb200_events mb200_events;
 typedef struct mb200_prefs mb200_prefs;

@@ -284,6 +284,12 @@ __device__ __noinline__ uint32_t warp_select_list(uint2* list, int n, int ksel, 
 // K3: Sketch . Sketch^T on tcgen05 with fused min-over-depth and candidate selection
 // ------------------------------------------------------------------------------------------------
 // TMEM columns: ACC_STAGES accumulators of BN FP32 columns, then (HAS_MIN) the running min.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 template <int BN, int ACC_STAGES, bool HAS_MIN>
 __global__ void __launch_bounds__(COS_THREADS, 1)
 k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -351,7 +357,9 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
               const long long t_wait = clock64();
               while (*flag != p.epoch) {
                 __nanosleep(256);
-                if (clock64() - t_wait > 8000000000LL) {  // ~4 s: report instead of hanging the GPU
+                // ~4 s: report instead of hanging the GPU.  The sweep then runs on incomplete data, but the abort
+                // word makes mb200_cosine_finish fail with MB200_ERR_CUDA before any result is handed out
+                if (clock64() - t_wait > 8000000000LL) {
                   atomicExch(p.abort_flag, 1u);
                   break;
                 }
@@ -462,7 +470,9 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           uint32_t cm[CHUNKS];
           const uint32_t* bv = p.b_valid + ((size_t)g * p.depth + dep) * p.b_vw + (l0 >> 5);
           // (if the block has already landed they can be fetched ahead as well)
-          const bool early = p.ready == nullptr || *((const volatile uint32_t*)p.ready + g) == p.epoch;
+          // acquire at system scope: the validity words of the block (written by a peer's DMA, published by the
+          // copy stream's flag write) must not be read ahead of the flag
+          const bool early = p.ready == nullptr || ld_acquire_sys(p.ready + g) == p.epoch;
           if (early) {
 #pragma unroll
             for (int c = 0; c < CHUNKS; c++) cm[c] = p.ready == nullptr ? __ldg(bv + c) : __ldcv(bv + c);

@@ -447,6 +447,7 @@ __global__ void __launch_bounds__(256) k_id_to_index(const long long* __restrict
 struct PrepArgs {
   const long long* user;
   const long long* item;
+  const float* pref;
   long long n;
   unsigned long long mask;
   unsigned long long* ukeys;      // user table
@@ -479,7 +480,10 @@ __global__ void __launch_bounds__(256) k_prep_insert(const PrepArgs a) {
 
 __global__ void __launch_bounds__(256) k_prep_mark(const PrepArgs a) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += (long long)gridDim.x * blockDim.x) {
-    const bool last = a.ppos[a.pslot[t]] == (unsigned long long)t + 1ull;
+    // userVector.set(index, 0.0) REMOVES the element (RandomAccessSparseVector.setQuick, :125-132): a pair whose
+    // last preference is 0.0 -- e.g. rating + ratingShift == 0 -- neither counts toward minPrefsPerUser
+    // (getNumNondefaultElements, ToUserVectorsReducer.java:75) nor reaches the item vectors
+    const bool last = a.ppos[a.pslot[t]] == (unsigned long long)t + 1ull && a.pref[t] != 0.0f;
     a.keep[t] = last ? 1 : 0;
     if (last) atomicAdd(a.ucount + a.uslot[t], 1);
   }
@@ -861,6 +865,7 @@ int mb200_events_prepare(mb200_events* ev, int32_t min_prefs_per_user, mb200_pre
   memset(&a, 0, sizeof(a));
   a.user = ev->user;
   a.item = ev->item;
+  a.pref = ev->pref;
   a.n = n;
   a.mask = mask;
   a.min_prefs = min_prefs_per_user;

@@ -93,6 +93,9 @@ class PreferenceMatrix:
         uniq_idx, inv = np.unique(idx, return_inverse=True)
         min_id = np.full(uniq_idx.shape[0], np.iinfo(np.int64).max, np.int64)
         np.minimum.at(min_id, inv, item)
+        # set(index, 0.0) removes the element (RandomAccessSparseVector.setQuick, math/.../RandomAccessSparseVector.java:125-132):
+        # a pair whose last preference is 0.0 does not count toward minPrefsPerUser and is not in the vector
+        last &= p != 0.0
         u, i, p = u[last], i[last], p[last]
         # ToUserVectorsReducer: users with fewer than minPrefsPerUser preferences are dropped
         uu, cnt = np.unique(u, return_counts=True)

@@ -134,6 +134,24 @@ def test_prepare_small_reference_cases(ing):
     _check_prepare(ing, [-1, -1, -2 ** 63, 5, -1], [3, 4, 3, 3, 3], [1.0, 2.0, 3.0, 4.0, 5.0], 2)
 
 
+def test_prepare_zero_preferences_are_removed(ing):
+    """userVector.set(index, 0.0) removes the element (RandomAccessSparseVector.setQuick): a pair whose LAST
+    preference is 0.0 (rating + ratingShift == 0) neither counts toward minPrefsPerUser nor survives; an earlier
+    0.0 overwritten by a later value does not matter."""
+    user = [1, 1, 1, 2, 2, 2, 3, 3]
+    item = [5, 7, 5, 5, 9, 7, 7, 7]
+    pref = [1.0, 2.0, 0.0, 3.0, 0.0, 1.0, 0.0, 4.0]     # user 1 ends with 1 element, user 2 with 2, user 3 with 1
+    for mp in (1, 2):
+        _check_prepare(ing, user, item, pref, mp)
+    rng = np.random.Generator(np.random.PCG64(15))
+    n = 50_000
+    u = rng.integers(1, 2000, n)
+    i = rng.integers(1, 500, n).astype(np.int64)
+    p = (rng.integers(-2, 9, n) * 0.5).astype(np.float32)      # ~9 % zeros, some negatives
+    _check_prepare(ing, u, i, p, 1)
+    _check_prepare(ing, u, i, p, 20)
+
+
 def test_prepare_random_with_duplicates_and_collisions(ing):
     rng = np.random.Generator(np.random.PCG64(5))
     n = 200_000

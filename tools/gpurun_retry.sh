@@ -1,0 +1,10 @@
+#!/bin/bash
+# usage: tools/gpurun_retry.sh LOGFILE [gpurun args...] -- command ; retries while the pod has no free slot (exit code 3)
+log=$1; shift
+for attempt in $(seq 1 30); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  rc=$?
+  if [ $rc -ne 3 ] && ! grep -q "status=transient" "$log"; then exit $rc; fi
+  sleep 90
+done
+exit 3
