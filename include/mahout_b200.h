@@ -38,6 +38,7 @@ extern "C" {
 #define MB200_MEM_HOST 0
 #define MB200_MEM_DEVICE 1
 
+#define MB200_MAX_BLOCKS 64 /* shards / gathered blocks per job */
 #define MB200_MAX_DEPTH 32 /* CountMinSketchConfig searches depths 1..24 (CountMinSketchConfig.java:28-29) */
 
 /* element type of the normalised sketch rows fed to the tensor cores */
@@ -177,6 +178,24 @@ int mb200_bank_pair_cosine(mb200_bank* bank, const int64_t* ea, const int64_t* e
  * depths differ (Preconditions.checkArgument, DoubleCountMinSketch.java:117-118). */
 int mb200_bank_cross_cosine(mb200_bank* bank_a, const int64_t* ea, mb200_bank* bank_b,
                             const int64_t* eb, int64_t n, double* out, int mem);
+
+/* ---- sharded ingest: events travel to the GPU that owns their row ------------------------------ */
+/* Item-hash sharding: owner(row) = row mod shards, local row = row div shards.  Every GPU
+ * holds an arbitrary slice of the event stream in DEVICE memory.
+ *   mb200_route_count    how many of these events belong to each shard (HOST counts[shards]; synchronises).
+ *                        The callers exchange the shards x shards count matrix (a few hundred bytes, their
+ *                        collective) so that every source knows where its region starts in every destination.
+ *   mb200_route_scatter  one kernel partitions the events by owner in shared memory and writes every owner's
+ *                        run straight into that GPU's receive columns: dst_row / dst_key / dst_inc are HOST
+ *                        arrays of `shards` DEVICE pointers (the local columns, or a peer's mapped with
+ *                        mb200_peer_alloc / mb200_peer_open), dst_offset[s] the first slot of THIS source in
+ *                        destination s.  The row written is the local row.  Asynchronous on the context's
+ *                        stream; the destinations may be read after a cross-GPU barrier behind it.
+ * The order of the events inside a destination is unspecified (sketch updates commute). */
+int mb200_route_count(mb200_ctx* ctx, const int64_t* row, int64_t n, int32_t shards, int64_t* counts);
+int mb200_route_scatter(mb200_ctx* ctx, const int64_t* row, const int64_t* key, const float* inc, int64_t n,
+                        int32_t shards, void* const* dst_row, void* const* dst_key, void* const* dst_inc,
+                        const int64_t* dst_offset);
 
 /* ---- ingest: text preference data -> device-resident events -> preference matrix ------------ */
 /* The step in front of the sketch path (PreparePreferenceMatrixJob.java:54-114), so that the events
@@ -342,7 +361,6 @@ typedef struct mb200_cosine_piece {
  *   mb200_peer_alloc   cudaMalloc + a 64-byte IPC handle to send to the other ranks
  *   mb200_peer_open    map a peer's buffer from its handle (once; mappings persist)
  *   mb200_gather_wait  block until the queued pulls are complete */
-#define MB200_MAX_BLOCKS 64
 int mb200_peer_alloc(mb200_ctx* ctx, int64_t bytes, void** ptr, void* ipc_handle_64_bytes);
 int mb200_peer_open(mb200_ctx* ctx, const void* ipc_handle_64_bytes, void** ptr);
 int mb200_peer_close(mb200_ctx* ctx, void* ptr);

@@ -126,6 +126,8 @@ _PROTOS = {
     "mb200_prefs_user_columns": (C.c_int, [vp, C.POINTER(vp)]),
     "mb200_prefs_tables": (C.c_int, [vp, vp, vp]),
     "mb200_prefs_destroy": (C.c_int, [vp]),
+    "mb200_route_count": (C.c_int, [vp, vp, i64, i32, vp]),
+    "mb200_route_scatter": (C.c_int, [vp, vp, vp, vp, i64, i32, vp, vp, vp, vp]),
     "mb200_peer_alloc": (C.c_int, [vp, i64, C.POINTER(vp), vp]),
     "mb200_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "mb200_peer_close": (C.c_int, [vp, vp]),

@@ -215,10 +215,127 @@ def _all_gather(t, world, group):
     return flat.view((world,) + tuple(t.shape))
 
 
+class EventRouter:
+    """The exchange step of the sharded ingest on the GPUs (csrc/route.cu): every rank owns receive columns
+    (row, key, inc) of `capacity` events in peer-accessible memory, mapped by all the others (CUDA IPC over
+    NVLink).  `route` = count by owner, exchange of the G x G count matrix (the only collective: G int64 per
+    rank), one kernel that partitions this rank's events by owner in shared memory and stores every run
+    straight into its owner's columns, one stream-ordered barrier.  Collective; set up once, reused."""
+
+    def __init__(self, ctx, plan, capacity: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        from .ingest import _view
+        self.ctx, self.plan, self.group, self.capacity = ctx, plan, group, int(max(capacity, 1))
+        G = plan.G
+        dev = f"cuda:{ctx.device}"
+        self._own, handles = [], b""
+        for width in (8, 8, 4):
+            p, h = C.c_void_p(), (C.c_char * 64)()
+            N.check(N.lib().mb200_peer_alloc(ctx.handle, self.capacity * width, C.byref(p), C.cast(h, C.c_void_p)), ctx.handle)
+            self._own.append(p)
+            handles += bytes(h)
+        self.recv_row = _view(self._own[0].value, self.capacity, ctx.device, "<i8")
+        self.recv_key = _view(self._own[1].value, self.capacity, ctx.device, "<i8")
+        self.recv_inc = _view(self._own[2].value, self.capacity, ctx.device, "<f4")
+        mine = torch.frombuffer(bytearray(handles), dtype=torch.uint8).to(dev)
+        allh = torch.empty(G * 192, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy().tobytes()
+        self._opened = []
+        self.dst = [(C.c_void_p * G)() for _ in range(3)]
+        for g in range(G):
+            for j in range(3):
+                if g == plan.rank:
+                    self.dst[j][g] = self._own[j].value
+                    continue
+                q = C.c_void_p()
+                hb = (C.c_char * 64).from_buffer_copy(allh[g * 192 + j * 64:g * 192 + (j + 1) * 64])
+                N.check(N.lib().mb200_peer_open(ctx.handle, C.cast(hb, C.c_void_p), C.byref(q)), ctx.handle)
+                self._opened.append(q)
+                self.dst[j][g] = q.value
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def counts(self, row):
+        """events of `row` per owner (host int64 [G]) and the all-gathered G x G matrix M[src][dst]"""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        G = self.plan.G
+        c = np.zeros(G, np.int64)
+        N.check(N.lib().mb200_route_count(self.ctx.handle, C.c_void_p(row.data_ptr()), row.numel(), G,
+                                          c.ctypes.data_as(C.c_void_p)), self.ctx.handle)
+        mine = torch.from_numpy(c).to(row.device)
+        allc = torch.empty(G * G, dtype=torch.int64, device=row.device)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        return c, allc.cpu().numpy().reshape(G, G)
+
+    def route(self, row, user, pref, matrix=None):
+        """-> this rank's (local_row, user, pref): views of the receive columns, valid until the next route()"""
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _native as N
+        G, me = self.plan.G, self.plan.rank
+        row, user, pref = row.contiguous(), user.contiguous(), pref.contiguous()
+        if matrix is None:
+            _, matrix = self.counts(row)
+        total = int(matrix[:, me].sum())
+        if int(matrix.sum(axis=0).max()) > self.capacity:
+            raise ValueError(f"EventRouter: a shard receives {int(matrix.sum(axis=0).max())} events, capacity {self.capacity}")
+        off = matrix[:me].sum(axis=0).astype(np.int64) if me > 0 else np.zeros(G, np.int64)
+        off = np.ascontiguousarray(off)
+        # the all-gather of the counts already ordered every rank's previous use of its columns before this
+        N.check(N.lib().mb200_route_scatter(
+            self.ctx.handle, C.c_void_p(row.data_ptr()), C.c_void_p(user.data_ptr()), C.c_void_p(pref.data_ptr()),
+            row.numel(), G, C.cast(self.dst[0], C.c_void_p), C.cast(self.dst[1], C.c_void_p),
+            C.cast(self.dst[2], C.c_void_p), off.ctypes.data_as(C.c_void_p)), self.ctx.handle)
+        dist.all_reduce(self.token, group=self.group)          # every source has delivered
+        return self.recv_row[:total], self.recv_key[:total], self.recv_inc[:total]
+
+    def close(self):
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        if getattr(self, "_own", None) is None:
+            return
+        torch.cuda.synchronize(self.ctx.device)
+        dist.all_reduce(self.token, group=self.group)          # nobody is still writing into my columns
+        torch.cuda.synchronize(self.ctx.device)
+        self.recv_row = self.recv_key = self.recv_inc = None
+        for q in self._opened:
+            N.lib().mb200_peer_close(self.ctx.handle, q)
+        for p in self._own:
+            N.lib().mb200_peer_free(self.ctx.handle, p)
+        self._own = None
+
+
+def route_events_device(ctx, plan, row, user, pref, group=None, router: EventRouter | None = None):
+    """route_events on the GPUs through an EventRouter (created, sized by the exchanged counts, when none is
+    passed).  The context's stream must be the current torch stream (the NCCL barrier is ordered with the
+    scatter kernel through it).  Returns (local_row, user, pref, router): the tensors alias the router's
+    receive columns."""
+    import torch
+    dev = torch.device(f"cuda:{ctx.device}")
+    row = torch.as_tensor(row).to(dev)
+    user, pref = torch.as_tensor(user).to(dev), torch.as_tensor(pref).to(dev)
+    matrix = None
+    if router is None:
+        # size the receive columns by what the largest shard receives
+        probe = EventRouter.__new__(EventRouter)
+        probe.ctx, probe.plan, probe.group = ctx, plan, group
+        _, matrix = EventRouter.counts(probe, row.contiguous())
+        router = EventRouter(ctx, plan, int(matrix.sum(axis=0).max()), group)
+    lrow, luser, lpref = router.route(row, user, pref, matrix)
+    return lrow, luser, lpref, router
+
+
 def route_events(plan, row, user, pref, group=None):
-    """The exchange step of a sharded ingest: every rank holds an arbitrary slice of the
-    event stream; events travel to the owner of their item (owner = row % G) with one all-to-all of the
-    20-byte events -- NCCL over NVLink for CUDA tensors, gloo for CPU tensors.  Returns this rank's
+    """The exchange step of a sharded ingest for HOST tensors (gloo; the CPU-side tests of the
+    sharding logic): events travel to the owner of their item (owner = row % G) with one all-to-all of the
+    20-byte events.  On GPUs the product path is `route_events_device` (csrc/route.cu).  Returns this rank's
     (local_row, user, pref) as torch tensors on the inputs' device; order within a source is kept."""
     import torch
     import torch.distributed as dist
@@ -566,13 +683,32 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
         t = [torch.as_tensor(np.asarray(x, dt)) for x, dt in ((row, np.int64), (user, np.int64), (pref, np.float32))]
         if dev is not None:
             t = [x.to(dev) for x in t]
-        lrow, luser, lpref = route_events(plan, *t, group=group)
+        router = None
+        if dev is not None and isinstance(backend, GpuShardBackend):
+            # on the GPUs: partition + peer scatter in one kernel (csrc/route.cu), on the context's stream
+            ctx = backend.ctx
+            cur = torch.cuda.current_stream(torch.device(dev))
+            prev = ctx.stream_ptr
+            if prev is None:
+                ctx.set_stream(cur.cuda_stream)
+            try:
+                lrow, luser, lpref, router = route_events_device(ctx, plan, *t, group=group)
+                backend.build(plan, lrow, luser, lpref, width, depth, seed, frac_bits)
+                torch.cuda.synchronize(torch.device(dev))
+            finally:
+                if prev is None:
+                    ctx.set_stream(None)
+            router.close()
+            lrow = None
+        else:
+            lrow, luser, lpref = route_events(plan, *t, group=group)
         if dev is None:
             lrow, luser, lpref = lrow.numpy(), luser.numpy(), lpref.numpy()
     else:
         row, user, pref = np.asarray(row, np.int64), np.asarray(user, np.int64), np.asarray(pref, np.float32)
         lrow, luser, lpref = plan.my_events(row, user, pref)
-    backend.build(plan, lrow, luser, lpref, width, depth, seed, frac_bits)
+    if lrow is not None:
+        backend.build(plan, lrow, luser, lpref, width, depth, seed, frac_bits)
     if fused is None:
         fused = world > 1 and chunk_rows == 0 and isinstance(backend, GpuShardBackend)
     if fused and world > 1:
