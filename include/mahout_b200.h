@@ -155,6 +155,12 @@ int mb200_bank_update(mb200_bank* bank, const int64_t* entity, const int64_t* ke
                       const float* inc, int64_t n, int mem);
 int mb200_bank_update_f64(mb200_bank* bank, const int64_t* entity, const int64_t* key,
                           const double* inc, int64_t n, int mem);
+/* The same update in the narrow wire format, for callers whose IDs fit 32 bits and whose increments are small
+ * multiples of the bank's quantum (MovieLens-style data: int IDs, half-star ratings): u32 entity / key and ONE
+ * BYTE per increment holding the number of quanta, increment = quanta[t] * 2^-frac_bits.  5 bytes per event over
+ * PCIe for a single sketch (9 with entities) instead of 12 (20).  Same counters, bit for bit. */
+int mb200_bank_update_u8(mb200_bank* bank, const uint32_t* entity, const uint32_t* key, const uint8_t* quanta,
+                         int64_t n, int mem);
 /* The same update for events that are already grouped by entity -- the shape the reference itself works
  * on: CosineCM.exportProfile walks ONE entity's PreferenceArray into ONE sketch (CosineCM.java:41-58).
  * row_ptr [entities + 1] (CSR: the events of entity e are [row_ptr[e], row_ptr[e+1]), row_ptr[0] = 0,
@@ -166,6 +172,9 @@ int mb200_bank_check(mb200_bank* bank);
 
 /* counters of entities [e0, e1) as the reference's doubles, out[(e-e0)][i][j] */
 int mb200_bank_read(mb200_bank* bank, int64_t e0, int64_t e1, double* out, int mem);
+/* the same counters as int32 quanta (counter = out * 2^-frac_bits): half the bytes of mb200_bank_read on the way
+ * back to the host; MB200_ERR_RANGE if a counter does not fit 31 bits */
+int mb200_bank_read_i32(mb200_bank* bank, int64_t e0, int64_t e1, int32_t* out, int mem);
 /* DoubleCountMinSketch.get(key): min_i C[e][i][h_i(key)] (DoubleCountMinSketch.java:94-103) */
 int mb200_bank_query(mb200_bank* bank, const int64_t* entity, const int64_t* key, int64_t n,
                      double* out, int mem);

@@ -102,6 +102,8 @@ _PROTOS = {
     "mb200_bank_update": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
     "mb200_bank_update_f64": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
     "mb200_bank_update_grouped": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
+    "mb200_bank_update_u8": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
+    "mb200_bank_read_i32": (C.c_int, [vp, i64, i64, vp, C.c_int]),
     "mb200_bank_check": (C.c_int, [vp]),
     "mb200_bank_read": (C.c_int, [vp, i64, i64, vp, C.c_int]),
     "mb200_bank_query": (C.c_int, [vp, vp, vp, i64, vp, C.c_int]),
@@ -141,6 +143,7 @@ _PROTOS = {
     "mb200_cosine_last_fallback_rows": (C.c_int, [vp, C.POINTER(i64)]),
     # bench / test support (mahout_b200/csrc/synth.h)
     "mb200_synth_events": (C.c_int, [vp, C.c_uint64, i64, i64, i64, vp, i64, vp, vp, vp, vp]),
+    "mb200_bench_red64": (C.c_int, [vp, i64, i64, C.POINTER(f64), C.POINTER(f64)]),
 }
 
 _lib = None

@@ -89,6 +89,7 @@ struct mb200_bank {
 int mb200_fail(mb200_ctx* ctx, int code, const char* fmt, ...);
 // group.cu: bank-mode K1 through device-side grouping (called with ctx->mu held)
 bool mb200_group_applicable(const mb200_bank* bk, int64_t n);
+int mb200_group_ws(mb200_ctx* ctx, size_t slot, size_t bytes, void** out);  // grow-only slot of ctx->ws_group
 template <typename T>
 int mb200_group_update(mb200_bank* bk, const long long* entity, const long long* key, const T* inc, int64_t n);
 extern "C" void mb200_job_release(struct mb200_cosine_job* job);  // cosine.cu (internal)

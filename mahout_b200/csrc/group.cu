@@ -32,15 +32,22 @@
 
 namespace {
 
-constexpr int G_THREADS = 512;
+constexpr int G_THREADS = 256;               // four CTAs per SM: four tiles in four different phases
 constexpr int G_ITEMS = 8;
 constexpr int G_TILE = G_THREADS * G_ITEMS;  // records per partition tile
-constexpr int G_NB = 2048;                   // buckets per partition level
+constexpr int G_NB = 4 * G_THREADS;          // buckets per partition level
 constexpr int U_WINDOW = 32768;              // grouped records per update work item
 constexpr int U_TILE_MIN = 128;              // records of one entity in a window that pay for a tile
 constexpr int Q_NARROW = 1 << 15;            // |quanta| below this: 32 Ki of them cannot overflow an int32
 constexpr int HIST_SLOTS_LOG2 = 12;
 constexpr long long SUB_BATCH = 1LL << 30;   // events grouped per pass (u32 record offsets; workspace: 20 B/event)
+
+// bulk prefetch of a contiguous range into L2 (one instruction, no registers): the partition kernels issue it
+// for the tile AFTER the one they are about to load, so that tile's loads find their lines in L2
+__device__ __forceinline__ void l2_prefetch(const void* p, long long bytes) {
+  if (bytes >= 16 && (((uintptr_t)p) & 15) == 0)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((unsigned)(bytes & ~15LL)) : "memory");
+}
 
 // ---- block-wide exclusive scan of nb <= 4 * G_THREADS shared-memory words ---------------------------
 // in[] -> out[] (exclusive), returns the total to every thread.  wsum: G_THREADS / 32 + 1 words.
@@ -113,19 +120,23 @@ __global__ void __launch_bounds__(512) k_group_hist(const long long* __restrict_
   // 16-byte loads, four entities per thread per trip (two loads in flight); the unaligned head and the
   // tail go one by one
   const long long head = ((uintptr_t)entity & 8) ? 1 : 0;
-  const long long n4 = head + ((n - head) & ~3LL);
-  const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  for (long long t = head + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; t < n4; t += stride) {
-    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(entity + t));
-    const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(entity + t + 2));
+  const long long n8 = head + ((n - head) & ~7LL);
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long t = head + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; t < n8; t += stride) {
+    const longlong2* src = reinterpret_cast<const longlong2*>(entity + t);
+    const longlong2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
     count(a.x);
     count(a.y);
     count(b.x);
     count(b.y);
+    count(c.x);
+    count(c.y);
+    count(d.x);
+    count(d.y);
   }
   if (blockIdx.x == 0) {
     if (threadIdx.x < head) count(entity[threadIdx.x]);
-    if (n4 + threadIdx.x < n) count(entity[n4 + threadIdx.x]);
+    if (n8 + threadIdx.x < n) count(entity[n8 + threadIdx.x]);
   }
   __syncthreads();
   for (int s = threadIdx.x; s < (1 << HIST_SLOTS_LOG2); s += blockDim.x)
@@ -219,7 +230,6 @@ struct ScatterSmem {
   uint2 st_kq[G_TILE];
   unsigned st_ent[G_TILE];
   unsigned wsum[G_THREADS / 32 + 1];
-  unsigned bcast[4];
 };
 
 template <typename T>
@@ -248,20 +258,71 @@ __device__ __forceinline__ bool quanta_fast(float v, float qscale_f, int& q) {
   q = (int)qf;
   return fabsf(qf) < (float)Q_NARROW && (float)q == qf;
 }
-__device__ __forceinline__ bool quanta_fast(double, float, int&) { return false; }
+__device__ __forceinline__ bool quanta_fast(double v, float qscale_f, int& q) {
+  const double qd = v * (double)qscale_f;
+  q = (int)qd;
+  return fabs(qd) < (double)Q_NARROW && (double)q == qd;
+}
+
+// An event the fast conversion rejects (not an integral number of quanta below 2^15): rare, kept out of line so
+// that the FP64 conversion and the 128-bit hash arithmetic do not inflate the registers of the partition loop.
+// Publishes its own status words.  Returns the quanta when the event still fits the narrow record, else applies
+// it with the direct d x RED.ADD.64 path and returns 0.
+template <typename T, int D>
+__device__ __noinline__ long long slow_event(const Scatter1Args<T>* p, long long e, long long k, T v) {
+  unsigned bad = 0;
+  unsigned long long maxabs = 0;
+  const long long q = inc_to_quanta(v, p->qscale, bad, maxabs);
+  if (bad) atomicAdd(&p->flags[FLAG_INEXACT], 1ull);
+  if (maxabs) atomicMax(&p->flags[FLAG_MAXABS], maxabs);
+  if (q == 0) return 0;
+  if ((unsigned long long)k < (1ull << 32) && q > -Q_NARROW && q < Q_NARROW) return q;
+  scatter_event<D>(p->counters + (size_t)e * p->cells, p->hf, k, q);
+  *p->wide_seen = 1u;
+  return 0;
+}
+
+// a narrow-quanta event whose key does not fit 32 bits
+template <typename T, int D>
+__device__ __noinline__ void wide_key_event(const Scatter1Args<T>* p, long long e, long long k, long long q) {
+  scatter_event<D>(p->counters + (size_t)e * p->cells, p->hf, k, q);
+  *p->wide_seen = 1u;
+}
 
 template <typename T, int D>
-__global__ void __launch_bounds__(G_THREADS, 2) k_group_scatter1(const Scatter1Args<T> p) {
+__global__ void __launch_bounds__(G_THREADS, 4) k_group_scatter1(const __grid_constant__ Scatter1Args<T> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
   const int tid = threadIdx.x;
-  unsigned bad = 0;
-  unsigned long long maxabs = 0;
-  bool wide = false;
+  unsigned maxabs = 0;
   const float qscale_f = (float)p.qscale;
   const long long ntiles = (p.n + G_TILE - 1) / G_TILE;
+  auto prefetch_tile = [&](long long tile) {
+    if (tid == 0 && tile < ntiles) {
+      const long long base = tile * G_TILE;
+      const long long m = (p.n - base) < G_TILE ? (p.n - base) : G_TILE;
+      l2_prefetch(p.entity + base, m * 8);
+      l2_prefetch(p.key + base, m * 8);
+      l2_prefetch(p.inc + base, m * (long long)sizeof(T));
+    }
+  };
+  prefetch_tile(blockIdx.x);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // the kernel is bound by the latency of its loads, not by their bytes: the next tile is pulled into L2 now
+    prefetch_tile(tile + gridDim.x);
     const long long base = tile * G_TILE;
+    long long raw_e[G_ITEMS], raw_k[G_ITEMS];
+    T raw_v[G_ITEMS];
+#pragma unroll
+    for (int i = 0; i < G_ITEMS; i++) {
+      const long long idx = base + (long long)i * G_THREADS + tid;
+      raw_e[i] = -1;
+      if (idx < p.n) {
+        raw_e[i] = __ldg(p.entity + idx);
+        raw_k[i] = __ldg(p.key + idx);
+        raw_v[i] = __ldg(p.inc + idx);
+      }
+    }
     for (int b = tid; b < p.nb; b += G_THREADS) sm.hist[b] = 0;
     __syncthreads();
     unsigned ent[G_ITEMS], rank[G_ITEMS];
@@ -269,33 +330,26 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_group_scatter1(const Scatter1A
     bool ok[G_ITEMS];
 #pragma unroll
     for (int i = 0; i < G_ITEMS; i++) {
-      const long long idx = base + (long long)i * G_THREADS + tid;
       ok[i] = false;
-      if (idx < p.n) {
-        const long long e = __ldg(p.entity + idx);
-        const long long k = __ldg(p.key + idx);
-        const T v = __ldg(p.inc + idx);
-        if (e >= 0 && e < p.E) {  // bad entities were counted by P0
-          int qi;
-          long long q;
-          if (quanta_fast(v, qscale_f, qi)) {
-            q = qi;
-            const unsigned aq = (unsigned)(qi < 0 ? -qi : qi);
-            maxabs = aq > maxabs ? aq : maxabs;
-          } else {
-            q = inc_to_quanta(v, p.qscale, bad, maxabs);
+      const long long e = raw_e[i];
+      if (e >= 0 && e < p.E) {  // bad entities were counted by P0
+        const long long k = raw_k[i];
+        int q;
+        if (quanta_fast(raw_v[i], qscale_f, q)) {
+          const unsigned aq = (unsigned)(q < 0 ? -q : q);
+          maxabs = aq > maxabs ? aq : maxabs;
+          if (q != 0 && (unsigned long long)k >= (1ull << 32)) {
+            wide_key_event<T, D>(&p, e, k, q);
+            q = 0;
           }
-          if (q != 0) {
-            if ((unsigned long long)k < (1ull << 32) && q > -Q_NARROW && q < Q_NARROW) {
-              ok[i] = true;
-              ent[i] = (unsigned)e;
-              kq[i] = make_uint2((unsigned)k, (unsigned)(int)q);
-              rank[i] = atomicAdd(&sm.hist[(unsigned)e >> p.shift], 1u);
-            } else {
-              scatter_event<D>(p.counters + (size_t)e * p.cells, p.hf, k, q);
-              wide = true;
-            }
-          }
+        } else {
+          q = (int)slow_event<T, D>(&p, e, k, raw_v[i]);
+        }
+        if (q != 0) {
+          ok[i] = true;
+          ent[i] = (unsigned)e;
+          kq[i] = make_uint2((unsigned)k, (unsigned)q);
+          rank[i] = atomicAdd(&sm.hist[(unsigned)e >> p.shift], 1u);
         }
       }
     }
@@ -322,8 +376,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_group_scatter1(const Scatter1A
     }
     __syncthreads();
   }
-  if (wide) *p.wide_seen = 1u;
-  publish_flags(p.flags, bad, 0u, maxabs);
+  publish_flags(p.flags, 0u, 0u, (unsigned long long)maxabs);
 }
 
 struct Scatter2Args {
@@ -338,39 +391,63 @@ struct Scatter2Args {
   uint2* out_kq;
 };
 
-__global__ void __launch_bounds__(G_THREADS, 2) k_group_scatter2(const Scatter2Args p) {
+__global__ void __launch_bounds__(G_THREADS, 4) k_group_scatter2(const Scatter2Args p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const unsigned ntiles = p.tile_ptr[p.nb1];
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    if (tid == 0) {
-      // coarse bucket of this tile: last b with tile_ptr[b] <= tile
-      int lo = 0, hi = p.nb1;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (p.tile_ptr[mid] <= tile) lo = mid;
-        else hi = mid;
-      }
-      sm.bcast[0] = (unsigned)lo;
+  const int R = 1 << p.shift;
+  // where a tile lives: coarse bucket = last b with tile_ptr[b] <= tile (every thread searches: 10 L2 hits)
+  auto locate = [&](unsigned tile, unsigned& bkt, unsigned& first, unsigned& last) {
+    int lo = 0, hi = p.nb1;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(p.tile_ptr + mid) <= tile) lo = mid;
+      else hi = mid;
     }
-    const int R = 1 << p.shift;
+    bkt = (unsigned)lo;
+    first = __ldg(p.base1 + lo) + (tile - __ldg(p.tile_ptr + lo)) * G_TILE;
+    last = p.end1[lo];
+  };
+  unsigned bkt = 0, first = 0, last = 0;
+  auto prefetch_tile = [&](unsigned tile) {
+    if (tid == 0 && tile < ntiles) {
+      unsigned b2, f2, l2;
+      locate(tile, b2, f2, l2);
+      const long long m = (long long)(l2 - f2) < G_TILE ? (long long)(l2 - f2) : G_TILE;
+      // record offsets inside a bucket are arbitrary: round the range out to 16-byte boundaries
+      const unsigned f16 = f2 & ~3u;
+      l2_prefetch(p.in_ent + f16, (m + (f2 - f16)) * 4);
+      l2_prefetch(p.in_kq + (f2 & ~1u), (m + (f2 & 1u)) * 8);
+    }
+  };
+  prefetch_tile(blockIdx.x);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    prefetch_tile(tile + gridDim.x);
+    locate(tile, bkt, first, last);
+    unsigned raw_e[G_ITEMS];
+    uint2 raw_kq[G_ITEMS];
+#pragma unroll
+    for (int i = 0; i < G_ITEMS; i++) {
+      const unsigned idx = first + i * G_THREADS + tid;
+      raw_e[i] = 0xFFFFFFFFu;
+      if (idx < last) {
+        raw_e[i] = __ldg(p.in_ent + idx);
+        raw_kq[i] = __ldg(p.in_kq + idx);
+      }
+    }
     for (int b = tid; b < R; b += G_THREADS) sm.hist[b] = 0;
     __syncthreads();
-    const unsigned bkt = sm.bcast[0];
     const unsigned ebase = bkt << p.shift;
-    const unsigned first = p.base1[bkt] + (tile - p.tile_ptr[bkt]) * G_TILE;
-    const unsigned last = p.end1[bkt];
     unsigned ent[G_ITEMS], rank[G_ITEMS];
     uint2 kq[G_ITEMS];
     bool ok[G_ITEMS];
 #pragma unroll
     for (int i = 0; i < G_ITEMS; i++) {
-      const unsigned idx = first + i * G_THREADS + tid;
-      ok[i] = idx < last;
+      ok[i] = raw_e[i] != 0xFFFFFFFFu;
       if (ok[i]) {
-        ent[i] = __ldg(p.in_ent + idx) - ebase;
-        kq[i] = __ldg(p.in_kq + idx);
+        ent[i] = raw_e[i] - ebase;
+        kq[i] = raw_kq[i];
         rank[i] = atomicAdd(&sm.hist[ent[i]], 1u);
       }
     }
@@ -422,6 +499,18 @@ struct GroupedArgs {
   int virgin;   // the bank held only zeros when the call started: exclusive tiles are stored, not added
   HashFamily hf;
 };
+
+// pull the records of a window into L2 ahead of the entity walk
+__device__ __forceinline__ void prefetch_window(const NarrowSrc& s, long long w0, long long w1) {
+  const long long a = w0 & ~1LL;
+  l2_prefetch(s.kq + a, (w1 - a) * 8);   // rounded DOWN to 16 bytes: never past the end
+}
+template <typename T>
+__device__ __forceinline__ void prefetch_window(const WideSrc<T>& s, long long w0, long long w1) {
+  const long long a = w0 & ~3LL;
+  l2_prefetch(s.key + a, (w1 - a) * 8);
+  l2_prefetch(s.inc + a, (w1 - a) * (long long)sizeof(T));
+}
 
 __device__ __forceinline__ uint32_t col_small(const HashFamily& hf, int i, uint32_t k) {
   const uint64_t s = cmh_mul_add_mod_small(hf.a[i], k, hf.b[i]);
@@ -481,6 +570,7 @@ __global__ void __launch_bounds__(U_THREADS, 2) k_update_grouped(const Src src, 
     const long long win = s_work;
     if (win >= nwin) break;
     const long long w0 = win * U_WINDOW, w1 = (w0 + U_WINDOW) < total ? (w0 + U_WINDOW) : total;
+    if (tid == 32) prefetch_window(src, w0, w1);
     if (tid == 0) {
       // last entity whose segment starts at or before w0
       long long lo = 0, hi = p.E;  // seg[lo] <= w0 always (seg[0] = 0)
@@ -702,6 +792,8 @@ int launch_grouped(mb200_bank* bk, const Src& src, const IdxT* seg, const IdxT* 
 
 }  // namespace
 
+int mb200_group_ws(mb200_ctx* ctx, size_t slot, size_t bytes, void** out) { return ws_get(ctx, slot, bytes, out); }
+
 // ---- host orchestration (called with the context's mutex held) ------------------------------------------
 bool mb200_group_applicable(const mb200_bank* bk, int64_t n) {
   // worth it once the events outnumber the fixed cost of the extra passes; the two partition levels cover
@@ -782,7 +874,7 @@ int mb200_group_update(mb200_bank* bk, const long long* entity, const long long*
     }
     {
       long long want = ceil_div64(m, G_TILE);
-      const int grid = (int)(want < (long long)ctx->num_sms * 2 ? want : (long long)ctx->num_sms * 2);
+      const int grid = (int)(want < (long long)ctx->num_sms * 4 ? want : (long long)ctx->num_sms * 4);
 #define LAUNCH_S1(DD)                                                                                              \
   do {                                                                                                             \
     MB_CUDA(ctx, cudaFuncSetAttribute(k_group_scatter1<T, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -806,7 +898,7 @@ int mb200_group_update(mb200_bank* bk, const long long* entity, const long long*
       a2.cursor = cur2;
       a2.out_kq = kq2;
       MB_CUDA(ctx, cudaFuncSetAttribute(k_group_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_group_scatter2<<<ctx->num_sms * 2, G_THREADS, smem, ctx->stream>>>(a2);
+      k_group_scatter2<<<ctx->num_sms * 4, G_THREADS, smem, ctx->stream>>>(a2);
     }
     ctx->launches += two_level ? 6 : 3;
     MB_CUDA(ctx, cudaGetLastError());

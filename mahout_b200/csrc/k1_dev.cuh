@@ -9,11 +9,13 @@
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
-template <typename T>
+// T: increment type (float / double preference values, or uint8_t quanta of the narrow wire format);
+// K: key / entity type (long long, or uint32_t in the narrow wire format)
+template <typename T, typename K = long long>
 struct UpdateArgs {
   long long* counters;
-  const long long* entity;  // may be null
-  const long long* key;
+  const K* entity;  // may be null
+  const K* key;
   const T* inc;
   long long n;
   long long E;
@@ -36,6 +38,12 @@ __device__ __forceinline__ long long inc_to_quanta(T inc, double qscale, unsigne
   unsigned long long aq = q < 0 ? (unsigned long long)(-q) : (unsigned long long)q;
   maxabs = aq > maxabs ? aq : maxabs;
   return q;
+}
+
+// narrow wire format: the byte IS the number of quanta -- nothing to round, nothing to reject
+__device__ __forceinline__ long long inc_to_quanta(unsigned char inc, double, unsigned int&, unsigned long long& maxabs) {
+  maxabs = (unsigned long long)inc > maxabs ? (unsigned long long)inc : maxabs;
+  return (long long)inc;
 }
 
 // the d scattered RMWs of one event: RED.ADD.64 into HBM/L2-resident counter rows

@@ -20,9 +20,33 @@ struct Quad {
   T inc[4];
 };
 
-template <typename T, bool HAS_ENTITY, bool VEC>
-__device__ __forceinline__ void load_quad(const UpdateArgs<T>& p, long long base, Quad<T>& q) {
-  if (VEC) {
+template <typename T, bool HAS_ENTITY, bool VEC, typename K>
+__device__ __forceinline__ void load_quad(const UpdateArgs<T, K>& p, long long base, Quad<T>& q) {
+  if constexpr (sizeof(K) == 4) {
+    // narrow wire format: four u32 keys in one 16-byte load, four u8 quanta in one 4-byte load
+    if (VEC) {
+      const uint4 k = __ldg(reinterpret_cast<const uint4*>(p.key + base));
+      q.key[0] = k.x; q.key[1] = k.y; q.key[2] = k.z; q.key[3] = k.w;
+      if (HAS_ENTITY) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4*>(p.entity + base));
+        q.ent[0] = e.x; q.ent[1] = e.y; q.ent[2] = e.z; q.ent[3] = e.w;
+      }
+      if constexpr (sizeof(T) == 1) {
+        const uchar4 c = __ldg(reinterpret_cast<const uchar4*>(p.inc + base));
+        q.inc[0] = c.x; q.inc[1] = c.y; q.inc[2] = c.z; q.inc[3] = c.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) q.inc[j] = p.inc[base + j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        q.key[j] = p.key[base + j];
+        if (HAS_ENTITY) q.ent[j] = p.entity[base + j];
+        q.inc[j] = p.inc[base + j];
+      }
+    }
+  } else if (VEC) {
     const longlong2* k2 = reinterpret_cast<const longlong2*>(p.key + base);
     longlong2 k01 = __ldg(k2), k23 = __ldg(k2 + 1);
     q.key[0] = k01.x; q.key[1] = k01.y; q.key[2] = k23.x; q.key[3] = k23.y;
@@ -31,13 +55,16 @@ __device__ __forceinline__ void load_quad(const UpdateArgs<T>& p, long long base
       longlong2 e01 = __ldg(e2), e23 = __ldg(e2 + 1);
       q.ent[0] = e01.x; q.ent[1] = e01.y; q.ent[2] = e23.x; q.ent[3] = e23.y;
     }
-    if (sizeof(T) == 4) {
+    if constexpr (sizeof(T) == 4) {
       float4 v = __ldg(reinterpret_cast<const float4*>(p.inc + base));
       q.inc[0] = (T)v.x; q.inc[1] = (T)v.y; q.inc[2] = (T)v.z; q.inc[3] = (T)v.w;
-    } else {
+    } else if constexpr (sizeof(T) == 8) {
       const double2* d2 = reinterpret_cast<const double2*>(p.inc + base);
       double2 a = __ldg(d2), b = __ldg(d2 + 1);
       q.inc[0] = (T)a.x; q.inc[1] = (T)a.y; q.inc[2] = (T)b.x; q.inc[3] = (T)b.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) q.inc[j] = p.inc[base + j];
     }
   } else {
 #pragma unroll
@@ -53,8 +80,8 @@ __device__ __forceinline__ void load_quad(const UpdateArgs<T>& p, long long base
 // K1 (bank mode): every event goes straight to its entity's counter rows.
 // Coalesced 16-byte event loads, 4 events per thread per trip, d RED.ADD.64 per event.
 // ------------------------------------------------------------------------------------------
-template <typename T, bool HAS_ENTITY, bool VEC, int D>
-__global__ void __launch_bounds__(256) k_update_bank(const UpdateArgs<T> p) {
+template <typename T, bool HAS_ENTITY, bool VEC, int D, typename K = long long>
+__global__ void __launch_bounds__(256) k_update_bank(const UpdateArgs<T, K> p) {
   unsigned int bad = 0, bad_entity = 0;
   unsigned long long maxabs = 0;
   const size_t cells = (size_t)p.hf.d * p.hf.w;
@@ -63,7 +90,7 @@ __global__ void __launch_bounds__(256) k_update_bank(const UpdateArgs<T> p) {
   for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < n4;
        base += stride) {
     Quad<T> ev;
-    load_quad<T, HAS_ENTITY, VEC>(p, base, ev);
+    load_quad<T, HAS_ENTITY, VEC, K>(p, base, ev);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       long long q = inc_to_quanta(ev.inc[j], p.qscale, bad, maxabs);
@@ -127,8 +154,8 @@ __device__ __forceinline__ bool cache_absorb(unsigned long long* tag, unsigned i
 // shared memory and drained 32 at a time, every lane busy.
 static constexpr int MISS_Q = 64;  // entries per warp (a trip adds at most 32)
 
-template <typename T, bool VEC, int D>
-__global__ void __launch_bounds__(512, 2) k_update_single(const UpdateArgs<T> p) {
+template <typename T, bool VEC, int D, typename K = long long>
+__global__ void __launch_bounds__(512, 2) k_update_single(const UpdateArgs<T, K> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S = 1 << p.slots_log2;
   unsigned long long* tag = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -155,7 +182,7 @@ __global__ void __launch_bounds__(512, 2) k_update_single(const UpdateArgs<T> p)
     const long long base = wbase + (long long)lane * 4;
     const bool live = base < n4;
     Quad<T> ev;
-    if (live) load_quad<T, false, VEC>(p, base, ev);
+    if (live) load_quad<T, false, VEC, K>(p, base, ev);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       bool miss = false;
@@ -341,12 +368,41 @@ static int check_flags(mb200_bank* bk) {
   return MB200_OK;
 }
 
-template <typename T>
-static int launch_update(mb200_bank* bk, const long long* entity, const long long* key, const T* inc,
-                         int64_t n) {
+// narrow wire format, bank mode: widen to the (int64, int64, float) columns on the device (HBM-cheap next to
+// the PCIe bytes saved), then the ordinary path
+__global__ void __launch_bounds__(256) k_widen_events(const uint32_t* __restrict__ entity, const uint32_t* __restrict__ key,
+                                                      const unsigned char* __restrict__ quanta, long long n,
+                                                      float inv_q, long long* __restrict__ out_entity,
+                                                      long long* __restrict__ out_key, float* __restrict__ out_inc) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    out_entity[t] = entity[t];
+    out_key[t] = key[t];
+    out_inc[t] = (float)quanta[t] * inv_q;
+  }
+}
+
+template <typename T, typename K = long long>
+static int launch_update(mb200_bank* bk, const K* entity, const K* key, const T* inc, int64_t n) {
   mb200_ctx* ctx = bk->ctx;
   if (n <= 0) return MB200_OK;
-  UpdateArgs<T> p;
+  if constexpr (sizeof(K) == 4) {
+    if (bk->E > 1) {
+      if (!entity) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_update_u8: entity is NULL but the bank has %lld entities", (long long)bk->E);
+      if (bk->frac_bits > 24) return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_bank_update_u8: bank mode needs frac_bits <= 24");
+      void *we, *wk, *wi;
+      MB_CHECK(mb200_group_ws(ctx, 16, (size_t)n * 8, &we));
+      MB_CHECK(mb200_group_ws(ctx, 17, (size_t)n * 8, &wk));
+      MB_CHECK(mb200_group_ws(ctx, 18, (size_t)n * 4, &wi));
+      long long want = ceil_div64(n, 256);
+      const int grid = (int)(want < (long long)ctx->num_sms * 16 ? want : (long long)ctx->num_sms * 16);
+      k_widen_events<<<grid, 256, 0, ctx->stream>>>((const uint32_t*)entity, (const uint32_t*)key, (const unsigned char*)inc, n,
+                                                   (float)ldexp(1.0, -bk->frac_bits), (long long*)we, (long long*)wk, (float*)wi);
+      ctx->launches++;
+      MB_CUDA(ctx, cudaGetLastError());
+      return launch_update<float, long long>(bk, (const long long*)we, (const long long*)wk, (const float*)wi, n);
+    }
+  }
+  UpdateArgs<T, K> p;
   p.counters = bk->counters;
   p.entity = entity;
   p.key = key;
@@ -357,9 +413,12 @@ static int launch_update(mb200_bank* bk, const long long* entity, const long lon
   p.flags = bk->flags;
   p.hf = bk->hf;
   p.slots_log2 = 12;
-  const bool vec = (((uintptr_t)key | (uintptr_t)inc | (uintptr_t)entity) & 15) == 0;
+  const bool vec = sizeof(K) == 4 ? ((((uintptr_t)key | (uintptr_t)entity) & 15) == 0 && ((uintptr_t)inc & 3) == 0)
+                                  : ((((uintptr_t)key | (uintptr_t)inc | (uintptr_t)entity) & 15) == 0);
   const bool d4 = bk->d == 4;
-  if (bk->E > 1 && entity && mb200_group_applicable(bk, n)) return mb200_group_update<T>(bk, entity, key, inc, n);
+  if constexpr (sizeof(K) == 8 && sizeof(T) != 1) {
+    if (bk->E > 1 && entity && mb200_group_applicable(bk, n)) return mb200_group_update<T>(bk, entity, key, inc, n);
+  }
   ProfScope prof(ctx, MB200_K_UPDATE);
   if (bk->E == 1) {
     // single-sketch mode: the entity column (if any) is not needed
@@ -369,9 +428,9 @@ static int launch_update(mb200_bank* bk, const long long* entity, const long lon
     int grid = (int)(want < (long long)ctx->num_sms * 2 ? want : (long long)ctx->num_sms * 2);
 #define LAUNCH_SINGLE(VEC, D)                                                                       \
   do {                                                                                              \
-    MB_CUDA(ctx, cudaFuncSetAttribute(k_update_single<T, VEC, D>,                                   \
+    MB_CUDA(ctx, cudaFuncSetAttribute(k_update_single<T, VEC, D, K>,                                \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    k_update_single<T, VEC, D><<<grid, threads, smem, ctx->stream>>>(p);                            \
+    k_update_single<T, VEC, D, K><<<grid, threads, smem, ctx->stream>>>(p);                         \
   } while (0)
     if (vec && d4) LAUNCH_SINGLE(true, 4);
     else if (vec) LAUNCH_SINGLE(true, 0);
@@ -384,12 +443,14 @@ static int launch_update(mb200_bank* bk, const long long* entity, const long lon
     long long cap = (long long)ctx->num_sms * 16;
     int grid = (int)(want < cap ? want : cap);
     if (!entity) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_update: entity is NULL but the bank has %lld entities", (long long)bk->E);
+    if constexpr (sizeof(K) == 8) {
 #define LAUNCH_BANK(VEC, D) k_update_bank<T, true, VEC, D><<<grid, threads, 0, ctx->stream>>>(p)
-    if (vec && d4) LAUNCH_BANK(true, 4);
-    else if (vec) LAUNCH_BANK(true, 0);
-    else if (d4) LAUNCH_BANK(false, 4);
-    else LAUNCH_BANK(false, 0);
+      if (vec && d4) LAUNCH_BANK(true, 4);
+      else if (vec) LAUNCH_BANK(true, 0);
+      else if (d4) LAUNCH_BANK(false, 4);
+      else LAUNCH_BANK(false, 0);
 #undef LAUNCH_BANK
+    }
   }
   ctx->launches++;
   MB_CUDA(ctx, cudaGetLastError());
@@ -411,18 +472,17 @@ static int ensure_stage(mb200_ctx* ctx, size_t bytes) {
 }
 
 // host-resident events: chunked, double-buffered H2D on the copy stream overlapped with K1
-template <typename T>
-static int update_from_host(mb200_bank* bk, const int64_t* entity, const int64_t* key, const T* inc,
-                            int64_t n) {
+template <typename T, typename K = long long>
+static int update_from_host(mb200_bank* bk, const K* entity, const K* key, const T* inc, int64_t n) {
   mb200_ctx* ctx = bk->ctx;
   const int64_t chunk = 1 << 23;  // 8 Mi events
   const bool has_e = entity != nullptr && bk->E > 1;
-  const size_t per_event = 8 + sizeof(T) + (has_e ? 8 : 0);
+  const size_t per_event = sizeof(K) + sizeof(T) + (has_e ? sizeof(K) : 0);
   const int64_t c_events = n < chunk ? n : chunk;
   // each array starts 256-byte aligned inside the staging buffer
   const size_t off_key = 0;
-  const size_t off_ent = ((size_t)c_events * 8 + 255) & ~(size_t)255;
-  const size_t off_inc = off_ent + (has_e ? (((size_t)c_events * 8 + 255) & ~(size_t)255) : 0);
+  const size_t off_ent = ((size_t)c_events * sizeof(K) + 255) & ~(size_t)255;
+  const size_t off_inc = off_ent + (has_e ? (((size_t)c_events * sizeof(K) + 255) & ~(size_t)255) : 0);
   const size_t need = off_inc + (((size_t)c_events * sizeof(T) + 255) & ~(size_t)255);
   (void)per_event;
   MB_CHECK(ensure_stage(ctx, need));
@@ -431,17 +491,17 @@ static int update_from_host(mb200_bank* bk, const int64_t* entity, const int64_t
     const int64_t m = (n - off) < chunk ? (n - off) : chunk;
     char* base = (char*)ctx->stage[buf];
     MB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[buf], 0));
-    MB_CUDA(ctx, cudaMemcpyAsync(base + off_key, key + off, (size_t)m * 8, cudaMemcpyHostToDevice,
+    MB_CUDA(ctx, cudaMemcpyAsync(base + off_key, key + off, (size_t)m * sizeof(K), cudaMemcpyHostToDevice,
                                  ctx->copy_stream));
     if (has_e)
-      MB_CUDA(ctx, cudaMemcpyAsync(base + off_ent, entity + off, (size_t)m * 8,
+      MB_CUDA(ctx, cudaMemcpyAsync(base + off_ent, entity + off, (size_t)m * sizeof(K),
                                    cudaMemcpyHostToDevice, ctx->copy_stream));
     MB_CUDA(ctx, cudaMemcpyAsync(base + off_inc, inc + off, (size_t)m * sizeof(T),
                                  cudaMemcpyHostToDevice, ctx->copy_stream));
     MB_CUDA(ctx, cudaEventRecord(ctx->stage_full[buf], ctx->copy_stream));
     MB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stage_full[buf], 0));
-    MB_CHECK(launch_update<T>(bk, has_e ? (const long long*)(base + off_ent) : nullptr,
-                              (const long long*)(base + off_key), (const T*)(base + off_inc), m));
+    MB_CHECK((launch_update<T, K>(bk, has_e ? (const K*)(base + off_ent) : nullptr, (const K*)(base + off_key),
+                                  (const T*)(base + off_inc), m)));
     MB_CUDA(ctx, cudaEventRecord(ctx->stage_free[buf], ctx->stream));
   }
   // the caller's buffers are only borrowed for the call
@@ -449,8 +509,8 @@ static int update_from_host(mb200_bank* bk, const int64_t* entity, const int64_t
   return MB200_OK;
 }
 
-template <typename T>
-static int bank_update_impl(mb200_bank* bk, const int64_t* entity, const int64_t* key, const T* inc,
+template <typename T, typename KIn = int64_t, typename K = long long>
+static int bank_update_impl(mb200_bank* bk, const KIn* entity, const KIn* key, const T* inc,
                             int64_t n, int mem) {
   if (!bk) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_update: bank is NULL");
   mb200_ctx* ctx = bk->ctx;
@@ -462,8 +522,8 @@ static int bank_update_impl(mb200_bank* bk, const int64_t* entity, const int64_t
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_update: entity is NULL but the bank has %lld entities", (long long)bk->E);
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (mem == MB200_MEM_DEVICE)
-    return launch_update<T>(bk, (const long long*)entity, (const long long*)key, inc, n);
-  if (mem == MB200_MEM_HOST) return update_from_host<T>(bk, entity, key, inc, n);
+    return launch_update<T, K>(bk, (const K*)entity, (const K*)key, inc, n);
+  if (mem == MB200_MEM_HOST) return update_from_host<T, K>(bk, (const K*)entity, (const K*)key, inc, n);
   return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_update: mem must be MB200_MEM_HOST or MB200_MEM_DEVICE");
 }
 
@@ -660,6 +720,11 @@ int mb200_bank_update_f64(mb200_bank* bk, const int64_t* entity, const int64_t* 
   return bank_update_impl<double>(bk, entity, key, inc, n, mem);
 }
 
+int mb200_bank_update_u8(mb200_bank* bk, const uint32_t* entity, const uint32_t* key, const uint8_t* quanta,
+                         int64_t n, int mem) {
+  return bank_update_impl<unsigned char, uint32_t, uint32_t>(bk, entity, key, (const unsigned char*)quanta, n, mem);
+}
+
 int mb200_bank_check(mb200_bank* bk) {
   if (!bk) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_check: bank is NULL");
   std::lock_guard<std::mutex> g(bk->ctx->mu);
@@ -686,6 +751,42 @@ int mb200_bank_read(mb200_bank* bk, int64_t e0, int64_t e1, double* out, int mem
     long long want = ceil_div64(cells, 256);
     int grid = (int)(want < (long long)ctx->num_sms * 32 ? want : (long long)ctx->num_sms * 32);
     k_read<<<grid, 256, 0, ctx->stream>>>(bk->counters + e * cells_per, cells, inv_q, (double*)ob.dev, bk->flags);
+    ctx->launches++;
+    MB_CUDA(ctx, cudaGetLastError());
+    MB_CHECK(ob.release());
+  }
+  return check_flags(bk);
+}
+
+__global__ void k_read_i32(const long long* __restrict__ counters, long long n, int* __restrict__ out,
+                           unsigned long long* flags) {
+  unsigned int range = 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long c = counters[t];
+    if (c > 2147483647LL || c < -2147483647LL) range++;
+    out[t] = (int)c;
+  }
+  range = __reduce_add_sync(0xffffffffu, range);
+  if ((threadIdx.x & 31) == 0 && range) atomicAdd(&flags[FLAG_RANGE], (unsigned long long)range);
+}
+
+int mb200_bank_read_i32(mb200_bank* bk, int64_t e0, int64_t e1, int32_t* out, int mem) {
+  if (!bk) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_read_i32: bank is NULL");
+  mb200_ctx* ctx = bk->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (e0 < 0 || e1 > bk->E || e0 > e1 || (e1 > e0 && !out))
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_read_i32: bad entity range [%lld,%lld) of %lld", (long long)e0, (long long)e1, (long long)bk->E);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t cells_per = (int64_t)bk->d * bk->W;
+  int64_t step = mem == MB200_MEM_HOST ? ((64LL << 20) / cells_per > 0 ? (64LL << 20) / cells_per : 1) : (e1 - e0);
+  for (int64_t e = e0; e < e1; e += step) {
+    int64_t m = (e1 - e) < step ? (e1 - e) : step;
+    int64_t cells = m * cells_per;
+    OutBuf ob(ctx, out + (e - e0) * cells_per, (size_t)cells * 4, mem, 2);
+    MB_CHECK(ob.acquire());
+    long long want = ceil_div64(cells, 256);
+    int grid = (int)(want < (long long)ctx->num_sms * 32 ? want : (long long)ctx->num_sms * 32);
+    k_read_i32<<<grid, 256, 0, ctx->stream>>>(bk->counters + e * cells_per, cells, (int*)ob.dev, bk->flags);
     ctx->launches++;
     MB_CUDA(ctx, cudaGetLastError());
     MB_CHECK(ob.release());

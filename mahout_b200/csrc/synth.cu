@@ -56,3 +56,49 @@ extern "C" int mb200_synth_events(mb200_ctx* ctx, uint64_t seed, int64_t first, 
   MB_CUDA(ctx, cudaGetLastError());
   return MB200_OK;
 }
+
+// ---- L2 atomic peak (bench support): RED.ADD.64 to uniformly random cells of an L2-resident array -------------
+// What K1's miss path and bank-mode sparse path are bounded by once the counters sit in L2.  Every thread issues
+// `per_thread` fire-and-forget 64-bit reductions at addresses from a counter-based generator (no loads).
+__global__ void __launch_bounds__(512) k_red64_peak(unsigned long long* __restrict__ cells, unsigned long long mask,
+                                                    int per_thread, unsigned long long seed) {
+  unsigned long long x = seed + ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull;
+#pragma unroll 4
+  for (int i = 0; i < per_thread; i++) {
+    x += 0x9E3779B97F4A7C15ull;
+    const unsigned long long z = splitmix_fin(x);
+    atomicAdd(cells + (z & mask), 1ull);
+  }
+}
+
+extern "C" int mb200_bench_red64(mb200_ctx* ctx, int64_t cells_log2, int64_t updates, double* ms_out,
+                                 double* updates_done) {
+  if (!ctx || !ms_out || cells_log2 < 4 || cells_log2 > 32 || updates <= 0)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bench_red64: bad arguments");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  unsigned long long* cells = nullptr;
+  const size_t n = (size_t)1 << cells_log2;
+  MB_CUDA(ctx, cudaMalloc(&cells, n * 8));
+  MB_CUDA(ctx, cudaMemsetAsync(cells, 0, n * 8, ctx->stream));
+  const int grid = ctx->num_sms * 4, threads = 512;
+  const int per_thread = (int)ceil_div64(updates, (int64_t)grid * threads);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_red64_peak<<<grid, threads, 0, ctx->stream>>>(cells, n - 1, per_thread, 1);  // warm-up
+  cudaEventRecord(e0, ctx->stream);
+  k_red64_peak<<<grid, threads, 0, ctx->stream>>>(cells, n - 1, per_thread, 2);
+  cudaEventRecord(e1, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(cells);
+  ctx->launches += 2;
+  if (e != cudaSuccess) return mb200_fail(ctx, MB200_ERR_CUDA, "mb200_bench_red64: %s", cudaGetErrorString(e));
+  *ms_out = ms;
+  if (updates_done) *updates_done = (double)grid * threads * per_thread;
+  return MB200_OK;
+}

@@ -28,6 +28,10 @@ int mb200_synth_events(mb200_ctx* ctx, uint64_t seed, int64_t first, int64_t n, 
                        const double* cdf, int64_t items, const int64_t* perm, int64_t* out_user,
                        int64_t* out_item, float* out_pref);
 
+/* L2 atomic peak: `updates` RED.ADD.64 to uniformly random cells of a 2^cells_log2-word array (22 = 32 MiB,
+ * L2-resident on B200); one warm-up launch, one timed.  The denominator bench.py quotes K1's reductions/s against. */
+int mb200_bench_red64(mb200_ctx* ctx, int64_t cells_log2, int64_t updates, double* ms_out, double* updates_done);
+
 #ifdef __cplusplus
 }
 #endif

@@ -307,6 +307,25 @@ class SketchBank:
         fn = N.lib().mb200_bank_update_f64 if f64 else N.lib().mb200_bank_update
         N.check(fn(self.handle, e.ptr, k.ptr, v.ptr, k.n, mem), self.ctx.handle)
 
+    def update_u8(self, entity, key, quanta):
+        """The update in the narrow wire format: uint32 entity / key, one byte of quanta per event
+        (increment = quanta * 2^-frac_bits).  Same counters as update(), bit for bit."""
+        k = _Arg(key, np.uint32, "int32")
+        e = _Arg(entity, np.uint32, "int32", allow_none=True)
+        v = _Arg(quanta, np.uint8, "uint8")
+        if v.n != k.n or (e.ptr is not None and e.n != k.n):
+            raise ValueError("entity, key and quanta must have the same length")
+        mem = _same_mem(k, e, v)
+        N.check(N.lib().mb200_bank_update_u8(self.handle, e.ptr, k.ptr, v.ptr, k.n, mem), self.ctx.handle)
+
+    def read_i32(self, e0: int = 0, e1: int | None = None, device: bool = False):
+        """counters of entities [e0, e1) as int32 quanta, shape [e1-e0, d, w]"""
+        e1 = self.E if e1 is None else e1
+        mem = N.MEM_DEVICE if device else N.MEM_HOST
+        out, optr = _out((e1 - e0, self.d, self.w), np.int32, "int32", mem, self.ctx.device)
+        N.check(N.lib().mb200_bank_read_i32(self.handle, e0, e1, optr, mem), self.ctx.handle)
+        return out
+
     def update_grouped(self, row_ptr, key, inc):
         """The update for events already grouped by entity (CSR: entity e owns [row_ptr[e], row_ptr[e+1])) --
         one PreferenceArray per entity, as CosineCM.exportProfile walks them (CosineCM.java:41-58)."""

@@ -75,3 +75,11 @@ def events_device(ctx, seed: int, first: int, n: int, users: int, cdf_dev, perm_
         C.c_void_p(pref.data_ptr()) if pref is not None else None), ctx.handle)
     ctx.sync()
     return user, item, pref
+
+
+def red64_peak(ctx, cells_log2: int = 22, updates: int = 1 << 31) -> float:
+    """measured RED.ADD.64 rate (reductions / s) into a 2^cells_log2-word array (default 32 MiB: L2-resident, the
+    shape of config 2's sketch) -- the denominator for K1's reductions per second"""
+    ms, done = C.c_double(), C.c_double()
+    N.check(N.lib().mb200_bench_red64(ctx.handle, cells_log2, updates, C.byref(ms), C.byref(done)), ctx.handle)
+    return done.value / (ms.value * 1e-3)

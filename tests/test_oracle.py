@@ -263,3 +263,40 @@ def test_golden_fixture():
     assert idx.tolist() == g["topk_idx"]
     assert cnt.tolist() == g["topk_cnt"]
     assert np.allclose(sim, np.array(g["topk_sim"]), rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("E,d,w,k,neg", [(150, 4, 256, 10, False), (90, 1, 64, 100, False), (120, 3, 100, 7, True)])
+def test_fast_oracle_equals_loop_oracle_bit_for_bit(E, d, w, k, neg):
+    """oracle/fast.py (blocked FP64 products over integer quanta; the checker of bench.py's config-4 / config-5
+    parity legs) against the loop-for-loop C oracle: indices, counts and similarities bit-equal -- including tie
+    groups (boolean-style data), empty rows (NaN) and column blocks smaller than k."""
+    from oracle import fast
+    rng = np.random.Generator(np.random.PCG64(E + k))
+    n = 30 * E
+    ent = rng.integers(0, E - 2, n).astype(np.int64)            # the last two entities stay empty
+    key = rng.integers(0, 40 if k == 100 else 5000, n).astype(np.int64)   # few keys -> many exact ties
+    inc = (rng.integers(-6 if neg else 1, 11, n) * 0.5).astype(np.float32)
+    if k == 100:
+        inc[:] = 1.0
+    a, b = orc.hash_params(42, d)
+    bank = np.zeros((E, d, w))
+    orc.bank_update(bank, d, w, a, b, ent, key, inc)
+    want_i, want_s, want_c = orc.bank_cosine_topk(bank, k)
+    q = np.rint(bank * 2).astype(np.int32)                       # quanta at frac_bits = 1
+    rows = np.arange(E)
+    for block in (8192, 37):
+        gi, gs, gc = fast.bank_rows_topk(q, rows, k, block=block)
+        assert (gc == want_c).all()
+        assert (gi == want_i).all()
+        assert gs.tobytes() == want_s.tobytes()
+    # columns split over "ranks", partial top-k lists merged: the distributed form bench.py uses
+    parts = []
+    for g in range(3):
+        cols = np.arange(g, E, 3)
+        parts.append(fast.rows_vs_columns_topk(q[rows], rows, q[cols], cols, k, block=50))
+    gi, gs, gc = fast.merge_partials(parts, k)
+    assert (gi == want_i).all() and gs.tobytes() == want_s.tobytes() and (gc == want_c).all()
+    thr = float(np.median(want_s[want_s > 0]))
+    ti, ts, tc = orc.bank_cosine_topk(bank, k, threshold=thr)
+    gi, gs, gc = fast.bank_rows_topk(q, rows, k, threshold=thr, block=64)
+    assert (gi == ti).all() and gs.tobytes() == ts.tobytes() and (gc == tc).all()

@@ -197,6 +197,41 @@ def test_grouped_csr_update_and_errors(mb, ctx):
         ctx.set_option(N.OPT_GROUP_MIN_EVENTS, 1 << 16)
 
 
+@pytest.mark.parametrize("E", [1, 700])
+def test_narrow_wire_format_bit_exact(mb, ctx, E):
+    """mb200_bank_update_u8 (u32 keys, one byte of quanta per event) == the (int64, float) update, host and device,
+    aligned and not; mb200_bank_read_i32 gives the same counters as quanta."""
+    import torch
+    rng = np.random.Generator(np.random.PCG64(31 + E))
+    n, d, w = 200003, 4, 4096
+    key = np.minimum(rng.zipf(1.1, n), 2 ** 32 - 1).astype(np.uint32)
+    key[:5] = [0, 1, 2 ** 32 - 1, 2 ** 31, 7]
+    ent = rng.integers(0, E, n).astype(np.uint32)
+    quanta = rng.integers(0, 256, n).astype(np.uint8)
+    a, b = orc.hash_params(42, d)
+    want = np.zeros((E, d, w))
+    orc.bank_update(want, d, w, a, b, ent.astype(np.int64) if E > 1 else None, key.astype(np.int64),
+                    (quanta * 0.5).astype(np.float32))
+    for where in ("host", "device", "device_unaligned"):
+        bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+        if where == "host":
+            bank.update_u8(ent if E > 1 else None, key, quanta)
+        else:
+            o = 1 if where.endswith("unaligned") else 0
+            tk = torch.from_numpy(key.view(np.int32)).cuda()[o:]
+            te = torch.from_numpy(ent.view(np.int32)).cuda()[o:] if E > 1 else None
+            tq = torch.from_numpy(quanta).cuda()[o:]
+            bank.update_u8(te, tk, tq)
+            if o:
+                bank.update_u8(te[:0] if E > 1 else None, tk[:0], tq[:0])
+                bank.update_u8(torch.from_numpy(ent.view(np.int32)).cuda()[:1] if E > 1 else None,
+                               torch.from_numpy(key.view(np.int32)).cuda()[:1], torch.from_numpy(quanta).cuda()[:1])
+        bank.check()
+        assert bank.read().tobytes() == want.tobytes(), where
+        assert (bank.read_i32() == np.rint(want * 2).astype(np.int32)).all()
+        bank.close()
+
+
 def test_update_unaligned_and_tail(mb, ctx):
     """odd offsets defeat the 16-byte vector loads; n % 4 != 0 exercises the tail."""
     import torch
