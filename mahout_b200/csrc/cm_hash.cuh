@@ -59,20 +59,23 @@ CMH_FN uint64_t cmh_mul_add_mod(uint64_t a, uint64_t k, uint64_t b) {
 }
 
 // (a*k + b) mod p for a, b in [0, p) and a key residue below 2^32 -- item and user IDs in practice.
-// a*k < 2^95 is assembled from two 32x32->64 products; with 2^64 == 50 (mod p) the part above
-// 2^64 (< 2^31) folds into one small product: a third of the instructions of the general path.
+// a*k < 2^95 is assembled from two 32x32->64 products and split at bit 63: a*k = xh * 2^63 + xl with
+// xh < 2^32, so a*k == xl + 25 * xh (mod p), a value below 2^63 + 2^37.  "r >= p" is "bit 63 of r + 25", and
+// r - p is then (r + 25) with that bit cleared: two such steps (before and after adding b) give the canonical
+// residue in about half the instructions of the general path.
 CMH_FN uint64_t cmh_mul_add_mod_small(uint64_t a, uint32_t k, uint64_t b) {
   const uint64_t p0 = (a & 0xFFFFFFFFull) * (uint64_t)k;
-  const uint64_t p1 = (a >> 32) * (uint64_t)k;         // a < 2^63: p1 < 2^63
-  uint64_t s = p0 + (p1 << 32);                        // low 64 bits of a*k
-  const uint64_t hi = (p1 >> 32) + (s < p0 ? 1ull : 0ull);
-  uint64_t t = hi * 50ull + b;                         // < 2^37 + p < 2^64
-  if (s >= CMH_P) s -= CMH_P;
-  if (s >= CMH_P) s -= CMH_P;                          // 2^64 - 1 < 2p + 50
-  if (t >= CMH_P) t -= CMH_P;
-  s += t;                                              // < 2p
-  if (s >= CMH_P) s -= CMH_P;
-  return s;
+  const uint64_t p1 = (a >> 32) * (uint64_t)k;          // a < 2^63: p1 < 2^63
+  const uint64_t lo = p0 + (p1 << 32);                  // low 64 bits of a*k
+  const uint32_t hi = (uint32_t)(p1 >> 32) + (lo < p0 ? 1u : 0u);   // bits 64..94
+  const uint32_t xh = (hi << 1) | (uint32_t)(lo >> 63); // (a*k) >> 63
+  uint64_t r = (lo & CMH_M63) + (uint64_t)xh * 25ull;   // < 2^63 + 2^37
+  uint64_t t = r + 25ull;
+  if (t >> 63) r = t & CMH_M63;                         // r < p
+  r += b;                                               // < 2p = 2^64 - 50
+  t = r + 25ull;
+  if (t >> 63) r = t & CMH_M63;
+  return r;
 }
 
 // column of key residue `kr` in a row of width w; wmask = w-1 if w is a power of two else 0

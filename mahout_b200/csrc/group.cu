@@ -222,6 +222,39 @@ __global__ void __launch_bounds__(G_THREADS) k_scan_tiles(const unsigned* __rest
   if (threadIdx.x == 0) tile_ptr[nb] = total;
 }
 
+// one descriptor per P2 tile (coarse bucket, first record, end of the bucket's records) and per U window (first
+// entity): the binary searches run here, thousands at a time, instead of as a chain of dependent loads at the head
+// of every tile / window
+__global__ void k_tile_desc(const unsigned* __restrict__ tile_ptr, const unsigned* __restrict__ base1,
+                            const unsigned* __restrict__ end1, int nb1, uint4* __restrict__ desc) {
+  const unsigned ntiles = tile_ptr[nb1];
+  for (unsigned tile = blockIdx.x * blockDim.x + threadIdx.x; tile < ntiles; tile += gridDim.x * blockDim.x) {
+    int lo = 0, hi = nb1;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tile_ptr[mid] <= tile) lo = mid;
+      else hi = mid;
+    }
+    desc[tile] = make_uint4((unsigned)lo, base1[lo] + (tile - tile_ptr[lo]) * G_TILE, end1[lo], 0u);
+  }
+}
+
+template <typename IdxT>
+__global__ void k_window_desc(const IdxT* __restrict__ seg, long long E, unsigned* __restrict__ win_first) {
+  const long long total = (long long)seg[E];
+  const long long nwin = (total + U_WINDOW - 1) / U_WINDOW;
+  for (long long win = (long long)blockIdx.x * blockDim.x + threadIdx.x; win < nwin; win += (long long)gridDim.x * blockDim.x) {
+    const long long w0 = win * U_WINDOW;
+    long long lo = 0, hi = E;  // last entity whose segment starts at or before w0 (seg[0] = 0)
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if ((long long)seg[mid] <= w0) lo = mid;
+      else hi = mid;
+    }
+    win_first[win] = (unsigned)lo;
+  }
+}
+
 // ---- P1 / P2: tile partition through shared memory ---------------------------------------------------
 struct ScatterSmem {
   unsigned hist[G_NB];
@@ -248,6 +281,7 @@ struct Scatter1Args {
   double qscale;
   unsigned long long* flags;
   unsigned* wide_seen;  // set when an event took the direct path (the bank is then no longer all-zero)
+  int prefetch;         // MB200_OPT_GROUP_PREFETCH
   HashFamily hf;
 };
 
@@ -298,7 +332,7 @@ __global__ void __launch_bounds__(G_THREADS, 4) k_group_scatter1(const __grid_co
   const float qscale_f = (float)p.qscale;
   const long long ntiles = (p.n + G_TILE - 1) / G_TILE;
   auto prefetch_tile = [&](long long tile) {
-    if (tid == 0 && tile < ntiles) {
+    if (tid == 0 && tile < ntiles && p.prefetch) {
       const long long base = tile * G_TILE;
       const long long m = (p.n - base) < G_TILE ? (p.n - base) : G_TILE;
       l2_prefetch(p.entity + base, m * 8);
@@ -385,7 +419,8 @@ struct Scatter2Args {
   const unsigned* base1;     // [nb1 + 1] start of every coarse bucket
   const unsigned* end1;      // [nb1] fill end of every coarse bucket (P1's cursors)
   const unsigned* tile_ptr;  // [nb1 + 1]
-  int nb1, shift;
+  const uint4* desc;         // [tiles] (bucket, first record, end of the bucket's records)
+  int nb1, shift, prefetch;
   long long E;
   unsigned* cursor;  // [E] running fill position of every entity
   uint2* out_kq;
@@ -397,21 +432,15 @@ __global__ void __launch_bounds__(G_THREADS, 4) k_group_scatter2(const Scatter2A
   const int tid = threadIdx.x;
   const unsigned ntiles = p.tile_ptr[p.nb1];
   const int R = 1 << p.shift;
-  // where a tile lives: coarse bucket = last b with tile_ptr[b] <= tile (every thread searches: 10 L2 hits)
   auto locate = [&](unsigned tile, unsigned& bkt, unsigned& first, unsigned& last) {
-    int lo = 0, hi = p.nb1;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(p.tile_ptr + mid) <= tile) lo = mid;
-      else hi = mid;
-    }
-    bkt = (unsigned)lo;
-    first = __ldg(p.base1 + lo) + (tile - __ldg(p.tile_ptr + lo)) * G_TILE;
-    last = p.end1[lo];
+    const uint4 dsc = __ldg(p.desc + tile);
+    bkt = dsc.x;
+    first = dsc.y;
+    last = dsc.z;
   };
   unsigned bkt = 0, first = 0, last = 0;
   auto prefetch_tile = [&](unsigned tile) {
-    if (tid == 0 && tile < ntiles) {
+    if (tid == 0 && tile < ntiles && p.prefetch) {
       unsigned b2, f2, l2;
       locate(tile, b2, f2, l2);
       const long long m = (long long)(l2 - f2) < G_TILE ? (long long)(l2 - f2) : G_TILE;
@@ -494,6 +523,7 @@ struct GroupedArgs {
   double qscale;
   unsigned long long* flags;
   unsigned* ticket;
+  const unsigned* win_first;  // [windows] first entity of every window (k_window_desc)
   const unsigned* wide_seen;  // may be null
   int tile_ok;  // d * W int32 cells fit the shared-memory tile
   int virgin;   // the bank held only zeros when the call started: exclusive tiles are stored, not added
@@ -572,14 +602,7 @@ __global__ void __launch_bounds__(U_THREADS, 2) k_update_grouped(const Src src, 
     const long long w0 = win * U_WINDOW, w1 = (w0 + U_WINDOW) < total ? (w0 + U_WINDOW) : total;
     if (tid == 32) prefetch_window(src, w0, w1);
     if (tid == 0) {
-      // last entity whose segment starts at or before w0
-      long long lo = 0, hi = p.E;  // seg[lo] <= w0 always (seg[0] = 0)
-      while (hi - lo > 1) {
-        const long long mid = (lo + hi) >> 1;
-        if ((long long)p.seg[mid] <= w0) lo = mid;
-        else hi = mid;
-      }
-      s_first = lo;
+      s_first = p.win_first[win];
       s_next = 0;
       s_dense_n = 0;
     }
@@ -753,7 +776,7 @@ int ws_get(mb200_ctx* ctx, size_t slot, size_t bytes, void** out) {
 
 template <typename Src, typename IdxT>
 int launch_grouped(mb200_bank* bk, const Src& src, const IdxT* seg, const IdxT* end, unsigned* ticket,
-                   const unsigned* wide_seen) {
+                   const unsigned* wide_seen, long long max_records) {
   mb200_ctx* ctx = bk->ctx;
   GroupedArgs<IdxT> ga;
   ga.seg = seg;
@@ -765,6 +788,15 @@ int launch_grouped(mb200_bank* bk, const Src& src, const IdxT* seg, const IdxT* 
   ga.flags = bk->flags;
   ga.ticket = ticket;
   ga.wide_seen = wide_seen;
+  {
+    void* wf;
+    const long long max_win = max_records / U_WINDOW + 2;
+    MB_CHECK(ws_get(ctx, 9, (size_t)max_win * 4, &wf));
+    ga.win_first = (const unsigned*)wf;
+    const int g = (int)(max_win / 256 + 1 < 1024 ? max_win / 256 + 1 : 1024);
+    k_window_desc<IdxT><<<g, 256, 0, ctx->stream>>>(seg, bk->E, (unsigned*)wf);
+    ctx->launches++;
+  }
   ga.virgin = bk->virgin ? 1 : 0;
   ga.hf = bk->hf;
   size_t tile_bytes = (((size_t)ga.cells * 4) + 15) & ~(size_t)15;
@@ -861,6 +893,7 @@ int mb200_group_update(mb200_bank* bk, const long long* entity, const long long*
     a1.qscale = ldexp(1.0, bk->frac_bits);
     a1.flags = bk->flags;
     a1.wide_seen = ticket + 1;
+    a1.prefetch = ctx->group_prefetch;
     a1.hf = bk->hf;
     if (two_level) {
       k_init_coarse<<<(nb1 + 1 + 255) / 256, 256, 0, ctx->stream>>>(seg, E, shift, nb1, cur1, base1);
@@ -892,7 +925,16 @@ int mb200_group_update(mb200_bank* bk, const long long* entity, const long long*
       a2.base1 = base1;
       a2.end1 = cur1;
       a2.tile_ptr = tile_ptr;
+      {
+        void* dp;
+        const long long max_tiles = m / G_TILE + nb1 + 2;
+        MB_CHECK(ws_get(ctx, 10, (size_t)max_tiles * sizeof(uint4), &dp));
+        a2.desc = (const uint4*)dp;
+        const int g = (int)(max_tiles / 256 + 1 < 2048 ? max_tiles / 256 + 1 : 2048);
+        k_tile_desc<<<g, 256, 0, ctx->stream>>>(tile_ptr, base1, cur1, nb1, (uint4*)dp);
+      }
       a2.nb1 = nb1;
+      a2.prefetch = ctx->group_prefetch;
       a2.shift = shift;
       a2.E = E;
       a2.cursor = cur2;
@@ -900,12 +942,12 @@ int mb200_group_update(mb200_bank* bk, const long long* entity, const long long*
       MB_CUDA(ctx, cudaFuncSetAttribute(k_group_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_group_scatter2<<<ctx->num_sms * 4, G_THREADS, smem, ctx->stream>>>(a2);
     }
-    ctx->launches += two_level ? 6 : 3;
+    ctx->launches += two_level ? 7 : 3;
     MB_CUDA(ctx, cudaGetLastError());
     }
     NarrowSrc src{kq2};
     ProfScope prof_update(ctx, MB200_K_UPDATE);
-    MB_CHECK((launch_grouped<NarrowSrc, unsigned>(bk, src, seg, cur2, ticket, ticket + 1)));
+    MB_CHECK((launch_grouped<NarrowSrc, unsigned>(bk, src, seg, cur2, ticket, ticket + 1, m)));
   }
   bk->events_total += (double)n;
   return MB200_OK;
@@ -956,7 +998,7 @@ extern "C" int mb200_bank_update_grouped(mb200_bank* bk, const int64_t* row_ptr,
       return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_update_grouped: row_ptr is not a non-decreasing sequence from 0 to n");
     WideSrc<float> src{d_key, d_inc};
     ProfScope prof(ctx, MB200_K_UPDATE);
-    MB_CHECK((launch_grouped<WideSrc<float>, long long>(bk, src, d_ptr, d_ptr + 1, ticket, nullptr)));
+    MB_CHECK((launch_grouped<WideSrc<float>, long long>(bk, src, d_ptr, d_ptr + 1, ticket, nullptr, n)));
   }
   bk->events_total += (double)n;
   if (mem == MB200_MEM_HOST) MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

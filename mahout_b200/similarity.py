@@ -361,7 +361,8 @@ def route_events(plan, row, user, pref, group=None):
 
 
 def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precision, group=None,
-                     chunk_rows: int = 2048, a_counters=None, mixed_sign: bool = False):
+                     chunk_rows: int = 2048, a_counters=None, mixed_sign: bool = False, counter_blocks=None,
+                     counter_blocks32=None):
     """C1 overlapped with K3: the all-gather of the normalised rows runs in row chunks on
     a communication stream, two chunks ahead of the compute stream, and every gathered chunk
     [G, d, rows_c, ld] is pushed into one incremental cosine job as soon as it has landed.  Only two
@@ -421,7 +422,13 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
             else:
                 gather()
                 job.push(out.clone(), vout.clone(), id_mul=G, id_add=1, id_base=c0 * G)
-        if precision != "tensor":
+        if precision != "tensor" and counter_blocks is not None:
+            # the undecided candidates are read from their owners' banks through peer mappings
+            # (PeerRows.map_counters): no counter is ever gathered -- what makes exact sets possible when the
+            # bank of all shards (config 5: 10^7 x 4096 x 8 B) could not exist on one GPU
+            res = job.finish(a_counters=a_counters, b_id=(G, 1), counter_blocks=counter_blocks,
+                             b_count=plan.rows_per_shard, counter_blocks32=counter_blocks32)
+        elif precision != "tensor":
             # the exact re-score reads the counters of arbitrary peers: gathered whole, behind the rows
             if cuda:
                 with torch.cuda.stream(comm):

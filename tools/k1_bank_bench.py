@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--mode", default="grouped", choices=["grouped", "direct", "csr"])
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--parity-events", type=float, default=2e6)
+    ap.add_argument("--no-prefetch", action="store_true")
     args = ap.parse_args()
 
     import torch
@@ -53,6 +54,8 @@ def main():
     cdf = torch.from_numpy(synth.zipf_cdf(E, args.zipf)).to(dev)
     perm = torch.from_numpy(synth.rank_permutation(E, 3) - 1).to(dev)
     ctx.set_option(N.OPT_GROUP_MIN_EVENTS, (1 << 62) if args.mode == "direct" else 0)
+    if args.no_prefetch:
+        ctx.set_option(N.OPT_GROUP_PREFETCH, 0)
     bank = mb.SketchBank(E, w, d, 42, 1, ctx)
 
     def slice_events(c):
@@ -115,7 +118,7 @@ def main():
         pb.close()
     model = 20 + 16 * d
     line = {
-        "tool": "k1_bank_bench", "mode": args.mode, "items": E, "depth": d, "width": w, "zipf_s": args.zipf,
+        "tool": "k1_bank_bench", "mode": args.mode, "prefetch": not args.no_prefetch, "items": E, "depth": d, "width": w, "zipf_s": args.zipf,
         "events_per_call": n, "calls": args.calls, "events": total, "bank_GB": E * d * w * 8 / 1e9,
         "ms_total": ms, "events_per_s": total / (ms * 1e-3),
         "ms_group_stage": g_ms, "ms_update_kernel": u_ms, "launch_spans": [int(g_n), int(u_n)],
