@@ -34,7 +34,14 @@ SEED = 20240002           # 20240001 + config number (config 2 -> 
 SKETCH_SEED = 42
 DEPTH, WIDTH = 4, 1 << 20
 ITEMS, USERS, ZIPF_S = 10_000_000, 1_000_000, 1.1
-ALGO_BYTES_PER_EVENT = 20 + DEPTH * 16   # 20 B event + d x (8 B read + 8 B write)
+# SURVEY.md 8d's algorithmic model: event read + d x (8 B read + 8 B write) per FP64 counter RMW.  The single-sketch
+# kernel reads 12 B per event (8 B key + 4 B preference; no entity column), a bank-mode event is 20 B.
+ALGO_BYTES_PER_EVENT = 12 + DEPTH * 16
+BANK_BYTES_PER_EVENT = 20 + DEPTH * 16
+# ncu --set full of k_update_single on this workload (profiles/r2_k_update_single_ncu.txt): DRAM bytes and L2
+# reductions per event -- the physical side of the roofline object
+K1_DRAM_BYTES_PER_EVENT = 12.2
+K1_REDS_PER_EVENT = 1.5
 C3_USERS, C3_ITEMS, C3_EVENTS, C3_WIDTH, C3_DEPTH, C3_K = 138_493, 26_744, 20_000_000, 4096, 4, 50
 C3_SEED = 20240003
 C3_CHUNKS = 4              # all-gather chunks per step of the pipelined multi-GPU cosine form
@@ -165,7 +172,10 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference Java cannot run (no JVM in image): oracle/ C port of HashFunction.hash + "
-                "DoubleCountMinSketch.update, OpenMP over event slices with private sketches",
+                "DoubleCountMinSketch.update, OpenMP over event slices with private sketches.  Each step times a "
+                f"PREFIX of {per_step} events of the config-2 stream, not the 1e9 of the GPU arm: a rate measured on a "
+                "bounded sample of the same workload (same generator, seed, sketch shape)",
+        "sample_is_prefix_of_config": True,
     }
     if not args.no_cosine:
         line["cosine"] = _reference_cosine(threads)
@@ -303,23 +313,53 @@ def run_ours(args):
         N.check(N.lib().mb200_bank_read(ebank.handle, 0, 1, C.c_void_p(hout.data_ptr()), N.MEM_HOST),
                 ctx.handle)
 
-    for _ in range(2):
-        e2e_step()
+    # the narrow wire format of the same events (mb200_bank_update_u8): u32 key + one byte of quanta = 5 B/event
+    # over PCIe instead of 12, and the sketch read back as int32 quanta (16 MiB instead of 32)
+    hk32 = torch.empty(e2e_n, dtype=torch.int32).pin_memory()
+    hq8 = torch.empty(e2e_n, dtype=torch.uint8).pin_memory()
+    hk32.copy_(item[:e2e_n].to(torch.int32))
+    hq8.copy_((pref[:e2e_n] * 2).to(torch.uint8))
+    hout32 = torch.empty(DEPTH * WIDTH, dtype=torch.int32).pin_memory()
+    hk32_np, hq8_np = hk32.numpy(), hq8.numpy()
+
+    def e2e_step_narrow():
+        N.check(N.lib().mb200_bank_update_u8(ebank.handle, None, C.c_void_p(hk32_np.ctypes.data),
+                                             C.c_void_p(hq8_np.ctypes.data), e2e_n, N.MEM_HOST), ctx.handle)
+        N.check(N.lib().mb200_bank_read_i32(ebank.handle, 0, 1, C.c_void_p(hout32.data_ptr()), N.MEM_HOST),
+                ctx.handle)
+
     e2e_steps = max(2, min(args.steps, 5))
-    e2e_reps = []
-    for _ in range(3):                      # the host side of a shared box is noisy: best of 3 repetitions
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e_reps.append(e2e_s)
+
+    def time_e2e(fn):
+        for _ in range(2):
+            fn()
+        reps = []
+        for _ in range(3):                      # the host side of a shared box is noisy: best of 3 repetitions
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                fn()
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            reps.append(dt)
+        return reps
+
+    e2e_reps = time_e2e(e2e_step)
     e2e_s = min(e2e_reps)
+    ebank.clear()
+    narrow_reps = time_e2e(e2e_step_narrow)
+    narrow_s = min(narrow_reps)
+    # both formats feed the same counters
+    ebank.clear()
+    e2e_step_narrow()
+    narrow_q = hout32.clone()
+    ebank.clear()
+    e2e_step()
+    narrow_equal = bool(torch.equal(narrow_q.to(torch.float64) * 0.5, hout))
     # what the link itself delivers for the same bytes (explains the e2e number; not part of it)
     dkey = torch.empty(e2e_n, dtype=torch.int64, device=dev)
     dkey.copy_(hk, non_blocking=True)
@@ -330,6 +370,8 @@ def run_ours(args):
     h2d_gbps = 8 * e2e_n / (time.perf_counter() - t0) / 1e9
     del dkey
     e2e_value = world * e2e_n * e2e_steps / e2e_s
+    narrow_value = world * e2e_n * e2e_steps / narrow_s
+    red_peak = synth.red64_peak(ctx, 22, 1 << 30)           # measured L2 RED.ADD.64 rate into a 32 MiB array
 
     if numa_bound:
         os.sched_setaffinity(0, orig_affinity)        # the CPU baseline below uses every core again
@@ -349,9 +391,14 @@ def run_ours(args):
         got = pbank.read()
         parity = {"sketch_bit_exact": bool(got.tobytes() == cpu_bank.tobytes()), "events_checked": sample}
         pbank.close()
+        s1 = int(min(sample, max(1 << 22, rate / max(threads, 1) * 2.0)))
+        cpu1_rate, cpu1_dt, _ = _cpu_update_rate(item[:s1].cpu().numpy(), pref[:s1].cpu().numpy(), 1)
         cpu = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {sample} events of rank 0's stream, {cpu_dt:.1f} s; oracle/ C port "
-                         "(the Java reference cannot run: no JVM in the image)"}
+                         "(the Java reference cannot run: no JVM in the image)",
+               # the reference is single-threaded per sketch (and serial under LocalJobRunner): SURVEY.md 8d
+               "single_thread": {"value": cpu1_rate, "unit": UNIT, "cores": 1,
+                                 "sample": f"first {s1} events, {cpu1_dt:.1f} s"}}
 
     # free the sketch-stage buffers before the cosine stage
     bank.close()
@@ -361,39 +408,56 @@ def run_ours(args):
     cosine = None
     if not args.no_cosine:
         cosine = run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, args.steps, args.warmup)
+    big = run_big_stages(args, ctx, stream, world, rank, local, dev, peaks)
 
     if rank == 0:
         kern_s = (k_ms / max(k_n, 1)) * 1e-3
-        achieved = ALGO_BYTES_PER_EVENT * n / kern_s / 1e9
-        physical = 12 * n / kern_s / 1e9
+        model_gbps = ALGO_BYTES_PER_EVENT * n / kern_s / 1e9
+        dram_gbps = K1_DRAM_BYTES_PER_EVENT * n / kern_s / 1e9
+        reds = K1_REDS_PER_EVENT * n / kern_s
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64 fixed-point counters (== reference f64, exact)",
             "data": "synthetic", "config": _config(world, n),
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * e2e_n,
-                    "d2h_bytes_per_step": 8 * DEPTH * WIDTH,
-                    "sample": f"{e2e_n} events/step from pinned host memory through mb200_bank_update(MEM_HOST) "
-                              "+ mb200_bank_read of the whole sketch; best of 3 repetitions of "
-                              f"{e2e_steps} steps",
-                    "repetitions_s": e2e_reps, "pinned_h2d_GBps": h2d_gbps, "host_threads_bound_to_gpu_numa_node": numa_bound,
-                    "bound": "PCIe: 12 B/event over the host link"},
-            "roofline": {"bound": "hbm", "kernel": "k_update_single", "achieved": achieved, "peak": peaks["hbm"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm"],
-                         # ncu --set full (profiles/r1_k_update_single_v2_ncu.txt): 3.056 GB of DRAM traffic per
-                         # 2.5e8-event launch = 12.2 B/event; the counters (32 MiB) stay in L2
-                         "traffic": 12.2 * n,
-                         "peak_source": peaks["source"], "algorithmic_bytes_per_event": ALGO_BYTES_PER_EVENT,
+            # headline e2e: the library's narrow wire format (u32 keys, one byte of quanta per event) from pinned host
+            # memory + the sketch read back; the reference's own (long, float) layout is reported beside it
+            "e2e": {"value": narrow_value, "unit": UNIT, "h2d_bytes_per_step": 5 * e2e_n,
+                    "d2h_bytes_per_step": 4 * DEPTH * WIDTH,
+                    "sample": f"{e2e_n} events/step from pinned host memory through mb200_bank_update_u8(MEM_HOST) "
+                              "(u32 key + u8 quanta = 5 B/event) + mb200_bank_read_i32 of the whole sketch; best of 3 "
+                              f"repetitions of {e2e_steps} steps",
+                    "repetitions_s": narrow_reps, "counters_equal_wide_format": narrow_equal,
+                    "wide_format": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * e2e_n,
+                                    "d2h_bytes_per_step": 8 * DEPTH * WIDTH, "repetitions_s": e2e_reps,
+                                    "sample": "the same events as int64 key + float32 preference (the reference's parsed "
+                                              "types) through mb200_bank_update(MEM_HOST) + mb200_bank_read (doubles)"},
+                    "pinned_h2d_GBps": h2d_gbps, "host_threads_bound_to_gpu_numa_node": numa_bound,
+                    "bound": "PCIe: bytes per event over the host link"},
+            # frac is PHYSICAL: DRAM bytes per event measured with ncu x events / kernel time, against the measured
+            # copy bandwidth.  The 32 MiB sketch is L2-resident, so the algorithmic model of SURVEY.md 8d (every
+            # counter RMW as 16 B of HBM traffic) describes traffic that never reaches DRAM; its figure is kept under
+            # "model" and may exceed 1.  What binds the kernel is the L2 reduction path: "l2_atomic".
+            "roofline": {"bound": "hbm", "kernel": "k_update_single", "achieved": dram_gbps, "peak": peaks["hbm"],
+                         "unit": "GB/s", "frac": dram_gbps / peaks["hbm"],
+                         "traffic": K1_DRAM_BYTES_PER_EVENT * n, "peak_source": peaks["source"],
                          "kernel_ms_per_launch": kern_s * 1e3, "launches_timed": int(k_n),
-                         "physical_event_read_GBps": physical,
-                         # frac follows SURVEY.md 8d's algorithmic model (84 B/event as if every counter RMW
-                         # went to HBM); the 32 MiB sketch is L2-resident and the hot-key cache absorbs most
-                         # updates, so the physical DRAM traffic is 12.2 B/event:
-                         "frac_physical_dram": 12.2 * n / kern_s / 1e9 / peaks["hbm"],
+                         "dram_bytes_per_event_ncu": K1_DRAM_BYTES_PER_EVENT,
+                         "model": {"algorithmic_bytes_per_event": ALGO_BYTES_PER_EVENT, "achieved": model_gbps,
+                                   "frac": model_gbps / peaks["hbm"],
+                                   "note": "12 B event + 4 x 16 B counter RMW as if every update went to HBM; the "
+                                           "counters are L2-resident and 2/3 of the events are absorbed in shared "
+                                           "memory, so this is not a physical bound"},
+                         "l2_atomic": {"peak_red64_per_s": red_peak, "reds_per_event_ncu": K1_REDS_PER_EVENT,
+                                       "achieved_red64_per_s": reds, "frac": reds / red_peak,
+                                       "peak_source": "mb200_bench_red64: RED.ADD.64 to uniformly random cells of a "
+                                                      "32 MiB array, measured in this run"},
                          "atomic_updates_per_s": DEPTH * n / kern_s},
             "cpu_baseline": cpu, "parity": parity, "cosine": cosine,
         }
+        if big:
+            line.update(big)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -436,19 +500,24 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
     from mahout_b200 import synth
     from mahout_b200.sketch import cosine_topk_blocks, last_fallback_rows
 
+    import bench_big as bb
+    env = bb.Env(ctx, stream, world, rank, local, dev, peaks)
     plan = sim.ShardPlan(C3_ITEMS, world, rank)
     cdf = torch.from_numpy(synth.zipf_cdf(C3_ITEMS, ZIPF_S)).to(dev)
     perm = torch.from_numpy(synth.rank_permutation(C3_ITEMS, 3) - 1).to(dev)     # item rows 0..N-1
-    user, item, pref = synth.events_device(ctx, C3_SEED, 0, C3_EVENTS, C3_USERS, cdf, perm)
-    mine = (item % world) == rank
-    lrow, luser, lpref = (item[mine] // world).contiguous(), user[mine].contiguous(), pref[mine].contiguous()
+    # sketch build: every rank holds 1/G of the stream; the events travel to the owners of their items (route.cu)
+    # and the owner groups them by item and updates its shard bank (group.cu)
+    n_slice = C3_EVENTS // world
     bank = mb.SketchBank(plan.rows_per_shard, C3_WIDTH, C3_DEPTH, SKETCH_SEED, 1, ctx)
+    build = bb.routed_build(env, plan, bank, C3_SEED, C3_EVENTS, C3_USERS, cdf, perm)
+    for _ in range(2):                                  # steady state: workspaces and the router's columns exist
+        bank.clear()
+        b2 = bb.routed_build(env, plan, bank, C3_SEED, C3_EVENTS, C3_USERS, cdf, perm)
+        if b2["route_ms"] + b2["k1_ms"] < build["route_ms"] + build["k1_ms"]:
+            build = b2
     ctx.set_profiling(True)
-    ctx.reset_profile()
-    bank.update(lrow, luser, lpref)
-    bank.check()
-    upd_ms, _ = ctx.kernel_time(N.K_UPDATE)
-    n_local = int(lrow.numel())
+    s_user, s_item, s_pref = synth.events_device(ctx, C3_SEED, rank * n_slice, n_slice, C3_USERS, cdf, perm)
+    n_local = int(n_slice)
 
     ld = int(N.lib().mb200_row_ld(C3_WIDTH))
     vw = int(N.lib().mb200_valid_words(plan.rows_per_shard))
@@ -616,14 +685,25 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
 
     # ---- end to end: this rank's events start in pinned HOST memory, its rows' top-k ends in host memory;
     # bank allocation + zero fill, H2D staging, K1, K2, (all-gathers), K3, K5 and the D2H are all inside
-    h_row, h_user, h_pref = (t.cpu().pin_memory() for t in (lrow, luser, lpref))
+    h_row, h_user, h_pref = (t.cpu().pin_memory() for t in (s_item, s_user, s_pref))
+    del s_user, s_item, s_pref
+    e2e_router = None
+    if world > 1:
+        probe = sim.EventRouter.__new__(sim.EventRouter)
+        probe.ctx, probe.plan, probe.group = ctx, plan, None
+        _, mat = sim.EventRouter.counts(probe, h_row.to(dev))
+        e2e_router = sim.EventRouter(ctx, plan, int(mat.sum(axis=0).max()))
 
     def e2e_step(precision):
         eb = mb.SketchBank(plan.rows_per_shard, C3_WIDTH, C3_DEPTH, SKETCH_SEED, 1, ctx)
         try:
-            eb.update(h_row.numpy(), h_user.numpy(), h_pref.numpy())
             if world == 1:
+                eb.update(h_row.numpy(), h_user.numpy(), h_pref.numpy())
                 return eb.cosine_topk(C3_K, None, True, "f16", precision)          # numpy (host) outputs
+            # this rank's slice of the stream: H2D, routed to the owners over NVLink, grouped K1 on the owner
+            d_ev = [t.to(dev, non_blocking=True) for t in (h_row, h_user, h_pref)]
+            lrow, luser, lpref, _ = sim.route_events_device(ctx, plan, *d_ev, router=e2e_router)
+            eb.update(lrow, luser, lpref)
             N.check(N.lib().mb200_bank_normalize(eb.handle, N.DTYPE_F16, C.c_void_p(a_rows.data_ptr()),
                                                  C.c_void_p(a_valid.data_ptr())), ctx.handle)
             dist.all_gather_into_tensor(b_rows.view(-1, plan.rows_per_shard, ld), a_rows)
@@ -728,10 +808,8 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                               "arrays (API default precision = rescored, bit-equal to the reference); best of 3"},
             "rescored": {"ms_per_step": rescored_ms, "K5_merge_rescore_ms": r5_ms, "fallback_rows": int(fallback),
                          "pairs_per_s": pairs / (rescored_ms * 1e-3)},
-            "sketch_build": {"events_per_s": n_local / (upd_ms * 1e-3) if upd_ms > 0 else None,
-                             "kernel": "k_update_bank", "events": n_local, "ms": upd_ms,
-                             "hbm_frac": (ALGO_BYTES_PER_EVENT * n_local / (upd_ms * 1e-3) / 1e9 / peaks["hbm"])
-                             if upd_ms > 0 else None},
+            "sketch_build": dict(build, kernel="k_group_* + k_update_grouped (bank mode)",
+                                 model_bytes_per_event=BANK_BYTES_PER_EVENT),
             "parity": {"rows_checked": rows_chk, "rescored_topk_and_sims_equal_oracle": exact_equal,
                        "certified_topk_sets_equal_oracle": cert_sets,
                        "tensor_max_rel_err": max_rel, "tensor_topk_overlap": overlap / max(tot, 1)},
@@ -739,8 +817,54 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                              "sample": f"{rows_chk} rows x all {C3_ITEMS} columns, {cpu_s:.1f} s; oracle/ C port of "
                                        "DoubleCountMinSketch.cosine + top-k"},
         }
+    if e2e_router is not None:
+        e2e_router.close()
     bank.close()
     return out
+
+
+def run_big_stages(args, ctx, stream, world, rank, local, dev, peaks):
+    """BASELINE.json configs[3] and configs[4] (bench_big.py): at 8 GPUs by default, at other N when asked for with
+    --big on (sizes then come from the --c4-* / --c5-* flags).  Returns {"config4": ..., "config5": ...} on rank 0."""
+    on = args.big == "on" or (args.big == "auto" and world == 8)
+    if not on:
+        return None
+    import torch
+    import bench_big as bb
+    env = bb.Env(ctx, stream, world, rank, local, dev, peaks)
+    out = {}
+    try:
+        c4 = []
+        for d, rows in ((1, args.c4_check_rows), (4, args.c4_check_rows_d4)):
+            if d == 4 and not args.c4_d4:
+                continue
+            c4.append(bb.big_cosine(
+                env, f"config4_d{d}", "configs[3]: 1M-item all-pairs sketch cosine (width 4096), fused top-100 epilogue, "
+                "item-hash sharded; sketch rows built from config-3-style Zipf(1.1) events routed to their owners",
+                int(args.c4_items), 5_000_000, args.c4_events, 1.1, d, 4096, 100, "fused", int(rows), 20240004))
+        out["config4"] = c4[0] if rank == 0 else None
+        if rank == 0 and len(c4) > 1:
+            out["config4"]["depth4"] = c4[1]
+    except Exception as ex:                      # a failed big stage must not lose the headline line
+        out["config4"] = {"error": repr(ex)[:400]}
+        torch.cuda.synchronize(dev)
+    try:
+        a = bb.skew_update(env, args.c5_events, 10_000_000, 1.5, DEPTH, WIDTH, max(1, min(args.steps, 3)), 1, 20240005)
+        b = bb.big_cosine(
+            env, "config5b_streamed_cosine", "configs[4]b (scaled): 10M-item cosine top-100 at "
+            f"{int(args.c5_items)} items, width 4096, depth 1, in the STREAMED form -- row chunks of every shard "
+            "gathered into two staging buffers while K3 consumes them; the gathered operand never exists",
+            int(args.c5_items), 5_000_000, args.c5_cos_events, 1.1, 1, 4096, 100, "pipelined", int(args.c5_check_rows),
+            20240006, chunk_rows=int(args.c5_chunk_rows), warmup=0)
+        if rank == 0:
+            out["config5"] = {"skew_update": a, "streamed_cosine": b,
+                              "scale_note": "configs[4] asks for 1e10 events and 1e7 items: the update leg runs at full size; "
+                                            "the cosine leg is scaled (2*N^2*W FLOP: 85 s at 1e7 items on 8 GPUs) -- "
+                                            "at 1e7 x 4096 the gathered FP16 operand would be 82 GB per depth row"}
+    except Exception as ex:
+        out["config5"] = {"error": repr(ex)[:400]}
+        torch.cuda.synchronize(dev)
+    return out if rank == 0 else None
 
 
 def main():
@@ -752,6 +876,18 @@ def main():
     ap.add_argument("--events", type=float, default=1e9, help="events per step per GPU")
     ap.add_argument("--e2e-events", type=float, default=float(1 << 27))
     ap.add_argument("--no-cosine", action="store_true", help="skip the secondary cosine-stage measurement")
+    ap.add_argument("--big", default="auto", choices=["auto", "on", "off"],
+                    help="configs[3] / configs[4] stages (auto: at 8 GPUs)")
+    ap.add_argument("--c4-items", type=float, default=1e6)
+    ap.add_argument("--c4-events", type=float, default=2e9)
+    ap.add_argument("--c4-check-rows", type=float, default=4096)
+    ap.add_argument("--c4-check-rows-d4", type=float, default=512)
+    ap.add_argument("--c4-d4", type=int, default=1, help="also run configs[3] at depth 4")
+    ap.add_argument("--c5-events", type=float, default=1e10)
+    ap.add_argument("--c5-items", type=float, default=4e6)
+    ap.add_argument("--c5-cos-events", type=float, default=8e9)
+    ap.add_argument("--c5-check-rows", type=float, default=1024)
+    ap.add_argument("--c5-chunk-rows", type=float, default=8192)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

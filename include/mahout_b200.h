@@ -69,7 +69,7 @@ int mb200_sync(mb200_ctx* ctx);
 #define MB200_OPT_GROUP_MIN_EVENTS 1 /* bank-mode updates of at least this many events are grouped by entity on
                                         the device first (default 65536; 0 = always; INT64_MAX = never) */
 #define MB200_OPT_GROUP_PREFETCH 2   /* the partition passes of that grouping pull their next tile into L2 with
-                                        cp.async.bulk.prefetch (default 1) */
+                                        cp.async.bulk.prefetch (default 0: measured neutral on B200, profiles/r2_k1_bank.md) */
 int mb200_set_option(mb200_ctx* ctx, int option, int64_t value);
 /* the cosine stage keeps its device workspaces (candidate lists, gathered rows of the single-GPU
  * convenience call) on the context between calls; this frees them */
