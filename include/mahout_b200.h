@@ -389,6 +389,50 @@ int mb200_cosine_abort(mb200_cosine_job* job);
  * exact full-row path during the last mb200_cosine_topk / mb200_bank_cosine_topk on ctx */
 int mb200_cosine_last_fallback_rows(mb200_ctx* ctx, int64_t* rows);
 
+/* ---- the whole item-similarity phase, on one GPU or on all GPUs of the box ------------------------------- */
+/* One process drives n_gpus GPUs: one mb200_ctx and one host worker thread per GPU, peer access between all of
+ * them (`mb200_create(int n_gpus, ...)`).  devices may be NULL (GPUs 0 .. n_gpus-1); n_gpus == 0
+ * takes every visible GPU.  This is what a JVM binds for `--numGpus`. */
+typedef struct mb200_multi mb200_multi;
+int mb200_create_multi(int32_t n_gpus, const int32_t* devices, mb200_multi** out);
+int mb200_multi_destroy(mb200_multi* m);
+int mb200_multi_gpus(mb200_multi* m, int32_t* n_gpus);
+int mb200_multi_ctx(mb200_multi* m, int32_t g, mb200_ctx** out); /* GPU g's context (owned by m) */
+const char* mb200_multi_last_error(mb200_multi* m);
+
+typedef struct mb200_job_params {
+  int32_t k;          /* --maxSimilaritiesPerItem (ItemSimilarityJob.java:88,105) */
+  double threshold;   /* --threshold; <= 0 = RowSimilarityJob.NO_THRESHOLD */
+  int32_t width, depth;
+  int64_t seed;       /* HashFunctionBuilder seed ... */
+  const int64_t* hash_a; /* ... or explicit parameters [depth] (both NULL = from seed); a = 1, b = 0 with width = */
+  const int64_t* hash_b; /*     number of users and dense user numbers as keys is the exact measure          */
+  int32_t frac_bits;
+  int32_t dtype;      /* MB200_DTYPE_* */
+  int32_t precision;  /* MB200_PRECISION_* */
+} mb200_job_params;
+
+typedef struct mb200_job_stats {
+  int32_t n_gpus;
+  int64_t events;              /* USED_OBSERVATIONS of RowSimilarityJob.Counters (RowSimilarityJob.java:84) */
+  int64_t rows;                /* ROWS */
+  int64_t similarities_kept;   /* entries written over all rows (<= rows * k) */
+  int64_t fallback_rows;       /* rows that took the exact full-row path */
+  int64_t events_busiest_gpu;  /* events received by the fullest shard */
+  double route_s, build_s, cosine_s; /* host wall clock of the three stages (GPU 0's worker) */
+} mb200_job_stats;
+
+/* Phase 1 of ItemSimilarityJob.run (ItemSimilarityJob.java:146-162) for prepared events in HOST memory: dense item
+ * rows [0, num_items), keys (user IDs, or dense user numbers for the exact measure), preferences.  Items are
+ * sharded by row mod n_gpus; events are routed to their owners over NVLink, every GPU builds its shard's
+ * sketches (K1), normalises (K2) and computes its block row of the similarity matrix against the rows pulled
+ * from its peers (K3, top-k fused) -- see csrc/job.cu.  out_idx / out_sim are [num_items][k] in global row
+ * order (unused slots -1 / 0), out_cnt [num_items]; stats may be NULL.  RESCORED pulls the peers' counters
+ * whole (n_gpus x the shard bank per GPU); CERTIFIED reads only the undecided candidates remotely. */
+int mb200_job_item_similarity(mb200_multi* m, const int64_t* row, const int64_t* key, const float* inc, int64_t n,
+                              int64_t num_items, const mb200_job_params* p, int64_t* out_idx, double* out_sim,
+                              int32_t* out_cnt, mb200_job_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,20 @@ class Stats(C.Structure):
                 ("cosine_job_active", C.c_int32), ("device_name", C.c_char * 64)]
 
 
+class JobParams(C.Structure):
+    """struct mb200_job_params (include/mahout_b200.h)."""
+    _fields_ = [("k", C.c_int32), ("threshold", C.c_double), ("width", C.c_int32), ("depth", C.c_int32),
+                ("seed", C.c_int64), ("hash_a", C.c_void_p), ("hash_b", C.c_void_p), ("frac_bits", C.c_int32),
+                ("dtype", C.c_int32), ("precision", C.c_int32)]
+
+
+class JobStats(C.Structure):
+    """struct mb200_job_stats (include/mahout_b200.h)."""
+    _fields_ = [("n_gpus", C.c_int32), ("events", C.c_int64), ("rows", C.c_int64), ("similarities_kept", C.c_int64),
+                ("fallback_rows", C.c_int64), ("events_busiest_gpu", C.c_int64), ("route_s", C.c_double),
+                ("build_s", C.c_double), ("cosine_s", C.c_double)]
+
+
 class CosinePiece(C.Structure):
     """struct mb200_cosine_piece (include/mahout_b200.h)."""
     _fields_ = [
@@ -141,6 +155,12 @@ _PROTOS = {
     "mb200_cosine_finish": (C.c_int, [vp, C.POINTER(CosineArgs)]),
     "mb200_cosine_abort": (C.c_int, [vp]),
     "mb200_cosine_last_fallback_rows": (C.c_int, [vp, C.POINTER(i64)]),
+    "mb200_create_multi": (C.c_int, [i32, vp, C.POINTER(vp)]),
+    "mb200_multi_destroy": (C.c_int, [vp]),
+    "mb200_multi_gpus": (C.c_int, [vp, C.POINTER(i32)]),
+    "mb200_multi_ctx": (C.c_int, [vp, i32, C.POINTER(vp)]),
+    "mb200_multi_last_error": (C.c_char_p, [vp]),
+    "mb200_job_item_similarity": (C.c_int, [vp, vp, vp, vp, i64, i64, C.POINTER(JobParams), vp, vp, vp, C.POINTER(JobStats)]),
     # bench / test support (mahout_b200/csrc/synth.h)
     "mb200_synth_events": (C.c_int, [vp, C.c_uint64, i64, i64, i64, vp, i64, vp, vp, vp, vp]),
     "mb200_bench_red64": (C.c_int, [vp, i64, i64, C.POINTER(f64), C.POINTER(f64)]),

@@ -18,7 +18,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmahout_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["runtime.cu", "sketch.cu", "group.cu", "route.cu", "synth.cu", "cosine.cu", "ingest.cu"]
+SOURCES = ["runtime.cu", "sketch.cu", "group.cu", "route.cu", "synth.cu", "cosine.cu", "ingest.cu", "job.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

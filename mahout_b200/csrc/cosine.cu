@@ -1473,6 +1473,95 @@ __global__ void __launch_bounds__(256) k_exact_rows(const RescoreParams p, const
   }
 }
 
+// The same full-row values at memory speed: one WARP per (flagged row, column), coalesced 16-byte loads of both
+// sketch rows, the three sums as exact integers.  While max|a| * max|b| * W < 2^52 every partial sum of the
+// reference's sequential FP64 loop is an exactly representable integer, so the integer sums converted to double ARE
+// that loop's results, whatever the order; a (column, depth) that fails the bound is recomputed by one lane with the
+// sequential FP64 loop of k_exact_rows.  A CTA takes EXACT_COLS columns of one flagged row; the A row (d x W x 8 B)
+// is read through L2 by every warp.
+#define EXACT_COLS 256
+__global__ void __launch_bounds__(256) k_exact_rows_fast(const RescoreParams p, const int32_t* flagged_rows,
+                                                         double* scratch, int64_t total_cols) {
+  const long long r = flagged_rows[blockIdx.x];
+  const long long* arow = p.a_counters + (size_t)r * p.d * p.W;
+  double* out = scratch + (size_t)blockIdx.x * total_cols;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long c0 = (long long)blockIdx.y * EXACT_COLS;
+  const long long c1 = (c0 + EXACT_COLS) < total_cols ? (c0 + EXACT_COLS) : total_cols;
+  const bool vec = (p.W & 1) == 0;
+  for (long long col = c0 + warp; col < c1; col += 8) {
+    const long long g = col / p.b_count, l = col % p.b_count;
+    double mn = JAVA_MAX_DOUBLE;
+    for (int i = 0; i < p.d; i++) {
+      const long long* a = arow + (size_t)i * p.W;
+      const long long* b = b_row(p, g, l, i);
+      long long aa = 0, bb = 0, ab = 0;
+      unsigned long long amax = 0, bmax = 0;
+      auto acc = [&](long long x, long long y) {
+        const unsigned long long ax = x < 0 ? (unsigned long long)(-x) : (unsigned long long)x;
+        const unsigned long long ay = y < 0 ? (unsigned long long)(-y) : (unsigned long long)y;
+        amax = ax > amax ? ax : amax;
+        bmax = ay > bmax ? ay : bmax;
+        aa += x * x;   // wraps only when the bound below fails, and then the value is not used
+        bb += y * y;
+        ab += x * y;
+      };
+      int j = 0;
+      if (vec && ((((uintptr_t)a | (uintptr_t)b) & 15) == 0)) {
+        const int pairs = p.W >> 1;
+        constexpr int UN = 4;
+        for (; j + 32 * UN <= pairs; j += 32 * UN) {
+          longlong2 xa[UN], xb[UN];
+#pragma unroll
+          for (int u = 0; u < UN; u++) {
+            xa[u] = __ldg(reinterpret_cast<const longlong2*>(a) + j + u * 32 + lane);
+            xb[u] = __ldg(reinterpret_cast<const longlong2*>(b) + j + u * 32 + lane);
+          }
+#pragma unroll
+          for (int u = 0; u < UN; u++) {
+            acc(xa[u].x, xb[u].x);
+            acc(xa[u].y, xb[u].y);
+          }
+        }
+        j *= 2;
+      }
+      for (int jj = j + lane; jj < p.W; jj += 32) acc(__ldg(a + jj), __ldg(b + jj));
+      for (int o = 16; o > 0; o >>= 1) {
+        aa += __shfl_xor_sync(0xffffffffu, aa, o);
+        bb += __shfl_xor_sync(0xffffffffu, bb, o);
+        ab += __shfl_xor_sync(0xffffffffu, ab, o);
+        const unsigned long long oa = __shfl_xor_sync(0xffffffffu, amax, o), ob = __shfl_xor_sync(0xffffffffu, bmax, o);
+        amax = oa > amax ? oa : amax;
+        bmax = ob > bmax ? ob : bmax;
+      }
+      double va, vb, vab;
+      const double big = (double)(amax > bmax ? amax : bmax);
+      if (big * big * (double)p.W < TWO53 * 0.5) {
+        va = (double)aa;
+        vb = (double)bb;
+        vab = (double)ab;
+      } else {
+        // beyond the exact range: the reference's own summation order decides the roundings
+        va = vb = vab = 0.0;
+        if (lane == 0) {
+          for (int jj = 0; jj < p.W; jj++) {
+            const double xa = (double)a[jj], xb = (double)b[jj];
+            va = __dadd_rn(va, __dmul_rn(xa, xa));
+            vb = __dadd_rn(vb, __dmul_rn(xb, xb));
+            vab = __dadd_rn(vab, __dmul_rn(xa, xb));
+          }
+        }
+      }
+      const double den = __dmul_rn(sqrt(va), sqrt(vb));
+      if (den != 0.0) {
+        const double cs = __ddiv_rn(vab, den);
+        mn = cs < mn ? cs : mn;
+      }
+    }
+    if (lane == 0) out[col] = mn == JAVA_MAX_DOUBLE ? nan("") : mn;
+  }
+}
+
 // top-k of one flagged row's exact similarities (scratch), one CTA per row: k rounds of arg-max
 __global__ void __launch_bounds__(256) k_exact_topk(const RescoreParams p, const int32_t* flagged_rows,
                                                     const double* scratch, int64_t total_cols,
@@ -2246,7 +2335,12 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
         MB_CHECK(d_scratch.alloc(ws, (size_t)batch * total_b * sizeof(double)));
         for (int off = 0; off < nflag; off += batch) {
           const int m = std::min(batch, nflag - off);
-          k_exact_rows<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, 1.0, 1.0, (double*)d_scratch.p, total_b);
+          if (getenv("MB200_EXACT_ROWS_SEQ") != nullptr) {  // the loop-for-loop form, kept for cross-checks
+            k_exact_rows<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, 1.0, 1.0, (double*)d_scratch.p, total_b);
+          } else {
+            dim3 grid((unsigned)m, (unsigned)((total_b + EXACT_COLS - 1) / EXACT_COLS));
+            k_exact_rows_fast<<<grid, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (double*)d_scratch.p, total_b);
+          }
           k_exact_topk<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (const double*)d_scratch.p, total_b,
                                                    a->exclude_self ? 1 : 0);
           ctx->launches += 2;

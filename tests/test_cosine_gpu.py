@@ -384,3 +384,40 @@ def test_mixed_sign_counters_exact_sets(mb, ctx, E, d, w, k, precision):
         # values are the tensor-core ones where the set was decided without re-scoring: absolute tolerance
         assert np.abs(np.sort(sim, axis=1) - np.sort(osim, axis=1))[m.any(axis=1)].max() <= 2e-3
     bank.close()
+
+
+@pytest.mark.parametrize("precision", ["rescored", "certified"])
+def test_boolean_data_tie_groups_take_the_exact_path(mb, ctx, precision, monkeypatch):
+    """--booleanData (every preference 1.0) with few users: many items have IDENTICAL sketches, so whole groups of
+    candidates tie exactly at the k-th value and the candidate lists cannot certify their rows -- they take the exact
+    full-row path (k_exact_rows_fast + k_exact_topk).  Ties are broken by index, as in the oracle; the memory-speed
+    integer form and the loop-for-loop FP64 form (MB200_EXACT_ROWS_SEQ) of that path must give the same answer."""
+    from mahout_b200.sketch import last_fallback_rows
+    rng = np.random.Generator(np.random.PCG64(12))
+    E, d, w, k = 900, 2, 256, 10
+    users = 40
+    item = np.repeat(np.arange(E - 5), 2).astype(np.int64)           # the last 5 items stay empty
+    user = rng.integers(1, users + 1, item.shape[0]).astype(np.int64)
+    pref = np.ones(item.shape[0], np.float32)
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((E, d, w))
+    orc.bank_update(ref, d, w, a, b, item, user, pref)
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    results = []
+    for seq in (False, True):
+        if seq:
+            monkeypatch.setenv("MB200_EXACT_ROWS_SEQ", "1")
+        else:
+            monkeypatch.delenv("MB200_EXACT_ROWS_SEQ", raising=False)
+        bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+        bank.update(item, user, pref)
+        idx, sim, cnt = bank.cosine_topk(k, precision=precision)
+        fb = last_fallback_rows(ctx)
+        bank.close()
+        assert fb > 0, "the tie groups were expected to defeat certification"
+        assert (cnt == ocnt).all()
+        assert (idx == oidx).all(), f"{(idx != oidx).sum()} index mismatches (fallback rows {fb})"
+        if precision == "rescored":
+            assert sim.tobytes() == osim.tobytes()
+        results.append((idx, sim))
+    assert (results[0][0] == results[1][0]).all() and results[0][1].tobytes() == results[1][1].tobytes()

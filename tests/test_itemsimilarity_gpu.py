@@ -235,3 +235,69 @@ def test_sharded_two_gpus_nccl():
     for r in range(777):
         for t in range(cnt[r]):
             assert abs(s[r, t] - dense[r, idx[r, t]]) <= 1e-3 * abs(dense[r, idx[r, t]])
+
+
+def _job_events(seed, n, U, I):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    item = (np.minimum(rng.zipf(1.2, n), I) - 1).astype(np.int64)
+    item = (item * 7919) % I
+    user = rng.integers(1, U, n).astype(np.int64)
+    pref = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
+    return item, user, pref
+
+
+@pytest.mark.parametrize("precision", ["rescored", "certified", "tensor"])
+def test_multi_gpu_job_behind_the_c_abi(precision):
+    """mb200_create_multi + mb200_job_item_similarity (csrc/job.cu): one process drives every visible GPU -- routing,
+    grouped K1, K2, fused pull-gather K3, top-k -- and must agree with the oracle: re-scored bit for bit, certified by
+    sets, tensor within tolerance; with 2+ GPUs also with the single-GPU result of the same call."""
+    import torch
+    import oracle as orc
+    from mahout_b200.multi import MultiGpu
+    I, d, w, k = 1500, 4, 1024, 20
+    item, user, pref = _job_events(5, 120000, 3000, I)
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((I, d, w))
+    orc.bank_update(ref, d, w, a, b, item, user, pref)
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    results = []
+    for g in sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()}):
+        with MultiGpu(g) as m:
+            idx, sim, cnt, st = m.item_similarity(item, user, pref, I, k=k, width=w, depth=d, precision=precision)
+        assert st["n_gpus"] == g and st["events"] == item.shape[0] and st["rows"] == I
+        assert st["similarities_kept"] == int(cnt.sum())
+        assert (cnt == ocnt).all(), g
+        if precision == "rescored":
+            assert (idx == oidx).all() and sim.tobytes() == osim.tobytes(), g
+        elif precision == "certified":
+            assert all(set(idx[r, :cnt[r]].tolist()) == set(oidx[r, :ocnt[r]].tolist()) for r in range(I)), g
+        else:
+            dense = orc.bank_cosine_dense(ref)
+            for r in range(0, I, 37):
+                for t in range(cnt[r]):
+                    assert abs(sim[r, t] - dense[r, idx[r, t]]) <= 1e-3 * abs(dense[r, idx[r, t]])
+        results.append((idx, sim, cnt))
+    for other in results[1:]:
+        if precision != "tensor":
+            assert (other[2] == results[0][2]).all()
+        if precision == "rescored":
+            assert (other[0] == results[0][0]).all() and other[1].tobytes() == results[0][1].tobytes()
+
+
+def test_multi_gpu_job_errors_surface():
+    from mahout_b200.multi import MultiGpu
+    import mahout_b200 as mb
+    with pytest.raises(ValueError):
+        MultiGpu(1000)
+    with MultiGpu(1) as m:
+        item, user, pref = _job_events(6, 5000, 100, 50)
+        with pytest.raises(ValueError):
+            m.item_similarity(item, user, pref, 50, k=0)
+        bad = item.copy()
+        bad[7] = 50                                               # a row outside [0, num_items)
+        with pytest.raises(ValueError):
+            m.item_similarity(bad, user, pref, 50, k=5, width=256, depth=2)
+        p = pref.copy()
+        p[3] = 0.3                                                # not a multiple of the quantum
+        with pytest.raises(mb.InexactError):
+            m.item_similarity(item, user, p, 50, k=5, width=256, depth=2)
