@@ -626,7 +626,7 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
             peers = None
     # certified precision (exact top-k sets, tensor-core values): the north star's contract.  N = 1: local
     # counters; N > 1: fused pull-gather + the peers' banks mapped over NVLink (no counter gather)
-    cert_ms, cidx, ccnt = None, None, None
+    cert_ms, cidx, ccnt, cert_kernels = None, None, None, None
     try:
         if world == 1:
             cstep = lambda: step("certified", a_cnt)
@@ -644,12 +644,18 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
             for _ in range(warmup):
                 cstep()
             barrier()
+            ctx.reset_profile()
+            t_c0 = time.perf_counter()
             e0.record(stream)
             for _ in range(steps):
                 cidx, cs, ccnt = cstep()
             e1.record(stream)
             barrier()
+            cert_wall_ms = (time.perf_counter() - t_c0) * 1e3 / steps
             cert_ms = e0.elapsed_time(e1) / steps
+            cert_kernels = {name: ctx.kernel_time(kid)[0] / steps for name, kid in
+                            (("K2_normalize", N.K_NORMALIZE), ("K3_cosine_topk", N.K_COSINE), ("K5_merge_certify", N.K_RESCORE))}
+            cert_kernels["host_wall_ms_per_step"] = cert_wall_ms
             if world > 1:
                 t = torch.tensor([cert_ms], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -777,6 +783,7 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
             "unit": "pairs/s", "precision_of_value": "certified" if cert_ms else "tensor",
             "ms_per_step": cert_ms or min(ms, piped_ms or ms, fused_ms or ms),
             "ms_per_step_certified": cert_ms, "certified_fallback_rows": cert_fallback,
+            "certified_kernels_ms_per_step": cert_kernels,
             "ms_per_step_tensor": min(ms, piped_ms or ms, fused_ms or ms), "ms_per_step_allgather_then_k3": ms,
             "ms_per_step_pipelined": piped_ms, "pipelined_equals_one_shot": piped_equal,
             "ms_per_step_fused_pull_gather": fused_ms, "fused_equals_one_shot": fused_equal,

@@ -245,6 +245,9 @@ int mb200_prefs_columns(mb200_prefs* p, int64_t** row, int64_t** user, float** p
 /* DEVICE column: a dense number 0..num_users-1 per surviving event's user -- the counter column of the
  * exact measure (bank of depth 1, width num_users, hash parameters a = 1, b = 0) */
 int mb200_prefs_user_columns(mb200_prefs* p, int64_t** ucol);
+/* copies of the surviving events to HOST arrays of n elements each (NULL = skip the column): what a host-side
+ * driver hands to mb200_job_item_similarity when the preparation ran on one GPU and the job runs on several */
+int mb200_prefs_read(mb200_prefs* p, int64_t* row, int64_t* user, int64_t* ucol, float* pref);
 /* HOST tables of num_items entries: row -> itemID written to the output, row -> index */
 int mb200_prefs_tables(mb200_prefs* p, int64_t* item_id, int32_t* index_values);
 int mb200_prefs_destroy(mb200_prefs* p);

@@ -140,6 +140,7 @@ _PROTOS = {
     "mb200_prefs_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "mb200_prefs_columns": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "mb200_prefs_user_columns": (C.c_int, [vp, C.POINTER(vp)]),
+    "mb200_prefs_read": (C.c_int, [vp, vp, vp, vp, vp]),
     "mb200_prefs_tables": (C.c_int, [vp, vp, vp]),
     "mb200_prefs_destroy": (C.c_int, [vp]),
     "mb200_route_count": (C.c_int, [vp, vp, i64, i32, vp]),

@@ -6,6 +6,8 @@
 //                    --maxPrefs/-mppu (500, accepted; no down-sampling takes place) --minPrefsPerUser/-mp (1)
 //                    --booleanData/-b --threshold/-tr --randomSeed --tempDir --startPhase --endPhase (:99-113)
 //                    + --sketchWidth --sketchDepth --sketchSeed --fracBits --precision --device
+//                    + --numGpus N (0 = every visible GPU): phase 1 runs as ONE mb200_job_item_similarity call over
+//                      N GPUs of this process (items sharded by row mod N, events routed over NVLink)
 //   phase 0          PreparePreferenceMatrixJob on the GPU (mb200_events_parse / mb200_events_prepare)
 //   phase 1          RowSimilarityJob: K1 -> K2 -> K3 -> K5 (mb200_bank_update / mb200_bank_cosine_topk);
 //                    -s SIMILARITY_COSINE is the exact measure (one counter column per user),
@@ -66,7 +68,7 @@ static std::string java_double(double v) {
 
 struct Args {
   std::string input, output, measure, precision = "rescored";
-  int max_sim = 100, min_prefs = 1, width = 4096, depth = 4, frac_bits = 1, device = 0;
+  int max_sim = 100, min_prefs = 1, width = 4096, depth = 4, frac_bits = 1, device = 0, num_gpus = -1;
   long long seed = 42;
   bool boolean_data = false, has_threshold = false;
   double threshold = 0.0;
@@ -102,6 +104,7 @@ static bool parse_args(int argc, char** argv, Args& a) {
     else if (k == "--fracBits") a.frac_bits = atoi(v.c_str());
     else if (k == "--precision") a.precision = v;
     else if (k == "--device") a.device = atoi(v.c_str());
+    else if (k == "--numGpus") a.num_gpus = atoi(v.c_str());
     else if (k == "--maxPrefs" || k == "--randomSeed" || k == "--tempDir" || k == "--startPhase" || k == "--endPhase") {
       // accepted for compatibility
     } else {
@@ -141,12 +144,24 @@ int main(int argc, char** argv) {
     fprintf(stderr, "maxSimilarItemsPerItem must be greater then 0!\n");
     return -1;
   }
-  if (a.precision != "rescored" && a.precision != "tensor") {
-    fprintf(stderr, "--precision must be rescored or tensor\n");
+  if (a.precision != "rescored" && a.precision != "tensor" && a.precision != "certified") {
+    fprintf(stderr, "--precision must be rescored, certified or tensor\n");
     return -1;
   }
+  const int precision = a.precision == "tensor" ? MB200_PRECISION_TENSOR
+                        : a.precision == "certified" ? MB200_PRECISION_CERTIFIED : MB200_PRECISION_RESCORED;
   mb200_ctx* ctx = nullptr;
-  TRY(mb200_create(a.device, &ctx));
+  mb200_multi* multi = nullptr;
+  if (a.num_gpus >= 0) {
+    // --numGpus: one process, N GPUs; the preparation phase runs on the first of them
+    if (mb200_create_multi(a.num_gpus, nullptr, &multi) != MB200_OK) {
+      fprintf(stderr, "itemsimilarity failed: %s\n", mb200_last_error(nullptr));
+      return -1;
+    }
+    TRY(mb200_multi_ctx(multi, 0, &ctx));
+  } else {
+    TRY(mb200_create(a.device, &ctx));
+  }
 
   // the input goes to page-locked memory, from there to the device once
   FILE* f = fopen(a.input.c_str(), "rb");
@@ -178,6 +193,39 @@ int main(int argc, char** argv) {
     float* pref = nullptr;
     TRY(mb200_prefs_columns(pm, &row, &user, &pref));
     TRY(mb200_prefs_user_columns(pm, &ucol));
+    const int k = a.max_sim;
+    std::vector<int64_t> idx((size_t)num_items * k);
+    std::vector<double> sim((size_t)num_items * k);
+    std::vector<int32_t> cnt((size_t)num_items);
+    if (multi) {
+      // phase 1 as one call over all GPUs: the prepared events go back to the host columns the job takes
+      std::vector<int64_t> h_row((size_t)n), h_key((size_t)n);
+      std::vector<float> h_pref((size_t)n);
+      TRY(mb200_prefs_read(pm, h_row.data(), exact ? nullptr : h_key.data(), exact ? h_key.data() : nullptr, h_pref.data()));
+      mb200_job_params jp;
+      memset(&jp, 0, sizeof(jp));
+      const int64_t one = 1, zero = 0;
+      jp.k = k;
+      jp.threshold = a.has_threshold ? a.threshold : 0.0;
+      jp.width = exact ? (int32_t)std::max<int64_t>(num_users, 1) : a.width;
+      jp.depth = exact ? 1 : a.depth;
+      jp.seed = a.seed;
+      jp.hash_a = exact ? &one : nullptr;
+      jp.hash_b = exact ? &zero : nullptr;
+      jp.frac_bits = a.frac_bits;
+      jp.dtype = MB200_DTYPE_F16;
+      jp.precision = precision;
+      mb200_job_stats st;
+      if (mb200_job_item_similarity(multi, h_row.data(), h_key.data(), h_pref.data(), n, num_items, &jp, idx.data(), sim.data(),
+                                    cnt.data(), &st) != MB200_OK) {
+        fprintf(stderr, "itemsimilarity failed: %s\n", mb200_multi_last_error(multi));
+        return -1;
+      }
+      // RowSimilarityJob.Counters (RowSimilarityJob.java:84), as far as they exist on this path
+      fprintf(stderr, "ROWS=%lld USED_OBSERVATIONS=%lld SIMILARITIES=%lld gpus=%d fallback_rows=%lld route=%.3fs build=%.3fs cosine=%.3fs\n",
+              (long long)st.rows, (long long)st.events, (long long)st.similarities_kept, st.n_gpus, (long long)st.fallback_rows,
+              st.route_s, st.build_s, st.cosine_s);
+    } else {
     mb200_bank* bank = nullptr;
     if (exact) {
       const int64_t one = 1, zero = 0;
@@ -188,14 +236,10 @@ int main(int argc, char** argv) {
       TRY(mb200_bank_update(bank, row, user, pref, n, MB200_MEM_DEVICE));
     }
     TRY(mb200_bank_check(bank));
-    const int k = a.max_sim;
-    std::vector<int64_t> idx((size_t)num_items * k);
-    std::vector<double> sim((size_t)num_items * k);
-    std::vector<int32_t> cnt((size_t)num_items);
-    TRY(mb200_bank_cosine_topk(bank, k, a.has_threshold ? a.threshold : 0.0, 1, MB200_DTYPE_F16,
-                               a.precision == "tensor" ? MB200_PRECISION_TENSOR : MB200_PRECISION_RESCORED, idx.data(),
+    TRY(mb200_bank_cosine_topk(bank, k, a.has_threshold ? a.threshold : 0.0, 1, MB200_DTYPE_F16, precision, idx.data(),
                                sim.data(), cnt.data(), MB200_MEM_HOST));
     mb200_bank_destroy(bank);
+    }
     // MostSimilarItemPairsMapper / Reducer
     std::map<std::pair<int64_t, int64_t>, double> pairs;
     for (int64_t r = 0; r < num_items; r++)
@@ -215,6 +259,7 @@ int main(int argc, char** argv) {
   for (auto& l : lines)
     fprintf(out, "%lld\t%lld\t%s\n", (long long)l.first.first, (long long)l.first.second, java_double(l.second).c_str());
   fclose(out);
-  mb200_destroy(ctx);
+  if (multi) mb200_multi_destroy(multi);
+  else mb200_destroy(ctx);
   return 0;
 }

@@ -992,6 +992,20 @@ int mb200_prefs_user_columns(mb200_prefs* p, int64_t** ucol) {
   return MB200_OK;
 }
 
+int mb200_prefs_read(mb200_prefs* p, int64_t* row, int64_t* user, int64_t* ucol, float* pref) {
+  if (!p) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_prefs_read: prefs is NULL");
+  mb200_ctx* ctx = p->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (p->n == 0) return MB200_OK;
+  if (row) MB_CUDA(ctx, cudaMemcpyAsync(row, p->row, (size_t)p->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (user) MB_CUDA(ctx, cudaMemcpyAsync(user, p->user, (size_t)p->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ucol) MB_CUDA(ctx, cudaMemcpyAsync(ucol, p->ucol, (size_t)p->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pref) MB_CUDA(ctx, cudaMemcpyAsync(pref, p->pref, (size_t)p->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MB200_OK;
+}
+
 int mb200_prefs_tables(mb200_prefs* p, int64_t* item_id, int32_t* index_values) {
   if (!p) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_prefs_tables: prefs is NULL");
   if (item_id && p->num_items) memcpy(item_id, p->item_id.data(), (size_t)p->num_items * 8);

@@ -208,3 +208,31 @@ def test_native_cli_equals_python_job(tmp_path, measure):
     assert r.returncode == 0, r.stderr
     assert py_out.read_text() == cc_out.read_text()
     assert len(py_out.read_text().splitlines()) > 100
+
+
+@pytest.mark.parametrize("measure", ["SIMILARITY_COSINE", "SIMILARITY_SKETCH_COSINE"])
+def test_native_cli_num_gpus_writes_the_same_file(tmp_path, measure):
+    """--numGpus N: phase 1 as ONE mb200_job_item_similarity call over N GPUs of the process (csrc/job.cu).  With the
+    re-scored precision the similarities are bit-equal to DoubleCountMinSketch.cosine however the items are sharded,
+    so the output file must be byte-identical to the single-GPU run -- for 1, 2 and all visible GPUs."""
+    import subprocess
+    import torch
+    from mahout_b200 import build
+    rng = np.random.Generator(np.random.PCG64(19))
+    n = 30000
+    lines = [f"{u},{i * 5},{p}" for u, i, p in zip(rng.integers(1, 500, n), rng.integers(1, 300, n),
+                                                   rng.integers(1, 11, n) * 0.5)]
+    inp = tmp_path / "prefs.csv"
+    inp.write_text("\n".join(lines) + "\n")
+    flags = ["-s", measure, "-m", "9", "-mp", "2", "--sketchWidth", "1024", "--sketchDepth", "4"]
+    base = tmp_path / "single.tsv"
+    r = subprocess.run([build.CLI_BIN, "-i", str(inp), "-o", str(base), *flags], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert len(base.read_text().splitlines()) > 100
+    for g in sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()}):
+        out = tmp_path / f"gpus{g}.tsv"
+        r = subprocess.run([build.CLI_BIN, "-i", str(inp), "-o", str(out), *flags, "--numGpus", str(g)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert f"gpus={g}" in r.stderr and "USED_OBSERVATIONS=" in r.stderr
+        assert out.read_text() == base.read_text(), g
