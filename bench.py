@@ -529,17 +529,27 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
     b_id = (world, 1) if world > 1 else (1, plan.rows_per_shard)
     out = {}
 
+    dbg = os.environ.get("MB200_BENCH_DEBUG") is not None
+    outs = {pr: (torch.empty((plan.rows_per_shard, C3_K), dtype=torch.int64, device=dev),
+                 torch.empty((plan.rows_per_shard, C3_K), dtype=torch.float64, device=dev),
+                 torch.empty((plan.rows_per_shard,), dtype=torch.int32, device=dev)) for pr in ("tensor", "certified", "rescored")}
+
     def step(precision, b_cnt=None):
+        t_dbg = time.perf_counter()
         N.check(N.lib().mb200_bank_normalize(bank.handle, N.DTYPE_F16, C.c_void_p(a_rows.data_ptr()),
                                              C.c_void_p(a_valid.data_ptr())), ctx.handle)
+        if dbg:
+            print(f"[bench debug] {precision}: K2 call {1e3 * (time.perf_counter() - t_dbg):.2f} ms", file=sys.stderr)
         if world > 1:
             dist.all_gather_into_tensor(b_rows.view(-1, plan.rows_per_shard, ld), a_rows)
             dist.all_gather_into_tensor(b_valid.view(-1, vw), a_valid)
             br, bv = b_rows, b_valid
         else:
             br, bv = a_rows.unsqueeze(0), a_valid.unsqueeze(0)
+        # outputs are allocated once: torch.empty inside the loop falls through to cudaMalloc on this non-default
+        # stream, which costs milliseconds on a process that holds tens of GB (measured: 5 - 30 ms per step)
         return cosine_topk_blocks(ctx, a_rows, a_valid, br, bv, C3_DEPTH, C3_WIDTH, C3_K, a_id=(world, rank),
-                                  b_id=b_id, dtype="f16", precision=precision,
+                                  b_id=b_id, dtype="f16", precision=precision, out=outs[precision],
                                   a_counters=a_cnt if precision != "tensor" else None, b_counters=b_cnt if precision != "tensor" else None)
 
     def barrier():
@@ -637,7 +647,7 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                 N.check(N.lib().mb200_bank_normalize(bank.handle, N.DTYPE_F16, C.c_void_p(peers.rows.data_ptr()),
                                                      C.c_void_p(peers.valid.data_ptr())), ctx.handle)
                 return sim.fused_gather_cosine(be, plan, peers, C3_K, None, "f16", "certified", a_counters=a_cnt,
-                                               counter_blocks=blocks)
+                                               counter_blocks=blocks, out=outs["certified"])
         else:
             cstep = None
         if cstep is not None:

@@ -70,6 +70,9 @@ int mb200_sync(mb200_ctx* ctx);
                                         the device first (default 65536; 0 = always; INT64_MAX = never) */
 #define MB200_OPT_GROUP_PREFETCH 2   /* the partition passes of that grouping pull their next tile into L2 with
                                         cp.async.bulk.prefetch (default 0: measured neutral on B200, profiles/r2_k1_bank.md) */
+#define MB200_OPT_SINGLE_KERNEL 3    /* single-sketch K1: 0 = first form (2 x 512 threads, 4096 direct-mapped slots),
+                                        1 = one 1024-thread CTA per SM with a 2-way cache of 14336 keys, 2 = the same with
+                                        warp-level aggregation of equal keys (default) */
 int mb200_set_option(mb200_ctx* ctx, int option, int64_t value);
 /* the cosine stage keeps its device workspaces (candidate lists, gathered rows of the single-GPU
  * convenience call) on the context between calls; this frees them */

@@ -24,6 +24,23 @@ public final class NativeSketch {
   public static final int DTYPE_BF16 = 1;
   public static final int PRECISION_TENSOR = 0;
   public static final int PRECISION_RESCORED = 1;
+  public static final int PRECISION_CERTIFIED = 2;
+  /** words of the stats array of jobItemSimilarity: gpus, events, rows, similarities kept, fallback rows,
+   *  events on the busiest GPU, route / build / cosine milliseconds */
+  public static final int JOB_STATS_WORDS = 9;
+
+  public static int precisionOf(String name) {
+    if ("tensor".equals(name)) {
+      return PRECISION_TENSOR;
+    }
+    if ("certified".equals(name)) {
+      return PRECISION_CERTIFIED;
+    }
+    if ("rescored".equals(name)) {
+      return PRECISION_RESCORED;
+    }
+    throw new IllegalArgumentException("--precision must be rescored, certified or tensor");
+  }
 
   /** mb200_create / mb200_destroy: returns the opaque context handle. Throws if there is no B200. */
   public static native long createContext(int device);
@@ -81,6 +98,22 @@ public final class NativeSketch {
   public static native void prefsTables(long prefs, long[] itemId, int[] indexValues);
   public static native void updateFromPrefs(long bank, long prefs);
   public static native void destroyPrefs(long prefs);
+
+  /**
+   * mb200_create_multi / mb200_multi_destroy / mb200_job_item_similarity: phase 1 of ItemSimilarityJob.run
+   * (ItemSimilarityJob.java:146-162) as one call over numGpus GPUs of this process (0 = all).  row / key / value are
+   * the prepared events (dense rows, user keys, preferences); exactMeasure selects the identity hash family (one
+   * counter column per key, width = number of distinct keys).  outIdx / outSim are [numRows][k], outCnt [numRows].
+   */
+  public static native long createMulti(int numGpus);
+  public static native void destroyMulti(long multi);
+  public static native void jobItemSimilarity(long multi, long[] row, long[] key, float[] value, long numRows, int k,
+                                              double threshold, int width, int depth, long seed, boolean exactMeasure,
+                                              int fracBits, int dtype, int precision, long[] outIdx, double[] outSim,
+                                              int[] outCnt, long[] stats);
+
+  /** mb200_bank_update_u8: the narrow wire format (uint32 entity / key, one byte of quanta per event). */
+  public static native void updateU8(long bank, ByteBuffer entity, ByteBuffer key, ByteBuffer quanta, long n);
 
   /** mb200_host_alloc / mb200_host_free wrapped as a direct ByteBuffer. */
   public static native ByteBuffer allocPinned(long bytes);

@@ -166,3 +166,83 @@ JNIEXPORT void JNICALL JNI_FN(destroyPrefs)(JNIEnv* env, jclass c, jlong prefs) 
   mb200_prefs_destroy((mb200_prefs*)(intptr_t)prefs);
 }
 /* clearBank, check, queryMany, read, cmDims follow the same pattern (one C call each). */
+
+/* ---- the whole similarity phase over all GPUs of the process (csrc/job.cu) ------------------------------------ */
+static void throw_multi(JNIEnv* env, int rc, mb200_multi* m) {
+  const char* cls = rc == MB200_ERR_BAD_ARG ? "java/lang/IllegalArgumentException"
+                                            : "org/apache/mahout/cf/taste/common/TasteException";
+  (*env)->ThrowNew(env, (*env)->FindClass(env, cls), mb200_multi_last_error(m));
+}
+
+JNIEXPORT jlong JNICALL JNI_FN(createMulti)(JNIEnv* env, jclass c, jint numGpus) {
+  mb200_multi* m = NULL;
+  int rc = mb200_create_multi(numGpus, NULL, &m);
+  if (rc != MB200_OK) throw_multi(env, rc, NULL);
+  return (jlong)(intptr_t)m;
+}
+
+JNIEXPORT void JNICALL JNI_FN(destroyMulti)(JNIEnv* env, jclass c, jlong multi) {
+  mb200_multi_destroy((mb200_multi*)(intptr_t)multi);
+}
+
+JNIEXPORT void JNICALL JNI_FN(jobItemSimilarity)(JNIEnv* env, jclass c, jlong multi, jlongArray row, jlongArray key,
+                                                 jfloatArray value, jlong numRows, jint k, jdouble threshold, jint width,
+                                                 jint depth, jlong seed, jboolean exactMeasure, jint fracBits, jint dtype,
+                                                 jint precision, jlongArray outIdx, jdoubleArray outSim, jintArray outCnt,
+                                                 jlongArray stats) {
+  mb200_multi* m = (mb200_multi*)(intptr_t)multi;
+  const jsize n = (*env)->GetArrayLength(env, row);
+  jlong* prow = (*env)->GetLongArrayElements(env, row, NULL);
+  jlong* pkey = (*env)->GetLongArrayElements(env, key, NULL);
+  jfloat* pval = (*env)->GetFloatArrayElements(env, value, NULL);
+  jlong* pidx = (*env)->GetLongArrayElements(env, outIdx, NULL);
+  jdouble* psim = (*env)->GetDoubleArrayElements(env, outSim, NULL);
+  jint* pcnt = (*env)->GetIntArrayElements(env, outCnt, NULL);
+  const int64_t one = 1, zero = 0;
+  mb200_job_params p;
+  mb200_job_stats st;
+  p.k = k;
+  p.threshold = threshold;
+  p.width = width;
+  p.depth = depth;
+  p.seed = seed;
+  p.hash_a = exactMeasure ? &one : NULL;
+  p.hash_b = exactMeasure ? &zero : NULL;
+  p.frac_bits = fracBits;
+  p.dtype = dtype;
+  p.precision = precision;
+  int rc = mb200_job_item_similarity(m, (const int64_t*)prow, (const int64_t*)pkey, (const float*)pval, n, numRows, &p,
+                                     (int64_t*)pidx, (double*)psim, (int32_t*)pcnt, &st);
+  (*env)->ReleaseLongArrayElements(env, row, prow, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, key, pkey, JNI_ABORT);
+  (*env)->ReleaseFloatArrayElements(env, value, pval, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, outIdx, pidx, 0);
+  (*env)->ReleaseDoubleArrayElements(env, outSim, psim, 0);
+  (*env)->ReleaseIntArrayElements(env, outCnt, pcnt, 0);
+  if (rc != MB200_OK) {
+    throw_multi(env, rc, m);
+    return;
+  }
+  if (stats != NULL && (*env)->GetArrayLength(env, stats) >= 9) {
+    jlong w[9];
+    w[0] = st.n_gpus;
+    w[1] = st.events;
+    w[2] = st.rows;
+    w[3] = st.similarities_kept;
+    w[4] = st.fallback_rows;
+    w[5] = st.events_busiest_gpu;
+    w[6] = (jlong)(st.route_s * 1e3);
+    w[7] = (jlong)(st.build_s * 1e3);
+    w[8] = (jlong)(st.cosine_s * 1e3);
+    (*env)->SetLongArrayRegion(env, stats, 0, 9, w);
+  }
+}
+
+JNIEXPORT void JNICALL JNI_FN(updateU8)(JNIEnv* env, jclass c, jlong bank, jobject entity, jobject key, jobject quanta,
+                                        jlong n) {
+  const uint32_t* e = entity ? (const uint32_t*)(*env)->GetDirectBufferAddress(env, entity) : NULL;
+  const uint32_t* k = (const uint32_t*)(*env)->GetDirectBufferAddress(env, key);
+  const uint8_t* q = (const uint8_t*)(*env)->GetDirectBufferAddress(env, quanta);
+  CHECK(mb200_bank_update_u8((mb200_bank*)(intptr_t)bank, e, k, q, n, MB200_MEM_HOST), NULL);
+}
+

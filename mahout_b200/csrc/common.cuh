@@ -56,6 +56,7 @@ struct mb200_ctx {
   std::vector<std::pair<void*, size_t>> ws_group;
   int64_t group_min_events = 1 << 16;  // MB200_OPT_GROUP_MIN_EVENTS
   int group_prefetch = 0;              // MB200_OPT_GROUP_PREFETCH
+  int single_kernel = 2;               // MB200_OPT_SINGLE_KERNEL
   // grow-only device staging of host-memory arguments (see io_slot in sketch.cu)
   std::pair<void*, size_t> io[3] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
   // pull-gather: per-block arrival flags written by the copy stream, read by K3 (+ 1 abort word)

@@ -224,6 +224,158 @@ __global__ void __launch_bounds__(512, 2) k_update_single(const UpdateArgs<T, K>
 }
 
 // ------------------------------------------------------------------------------------------
+// K1 (single-sketch mode), second form.  The first form is bound by the L2 reduction path (measured: 0.91 of the
+// RED.ADD.64 rate the chip sustains into a 32 MiB array) with 1.5 reductions per event, and three quarters of its
+// shared-memory atomic wavefronts are same-address replays of the Zipf head.  Here:
+//   * ONE CTA of 1024 threads per SM owns a 2-way set-associative cache of SETS x 2 keys (14336 slots instead of
+//     2 x 4096 direct-mapped ones, 32-bit tags): more of the head is absorbed, fewer reductions reach L2;
+//   * AGG: lanes of a warp that carry the same key are combined first (MATCH.ANY + REDUX.SUM): one shared-memory
+//     atomic -- or one queued miss -- per distinct key per warp instead of one per event.
+// ------------------------------------------------------------------------------------------
+static constexpr int V2_THREADS = 1024;
+static constexpr int V2_SETS = 7168;            // 2 ways each; 24 bytes per set
+static constexpr unsigned V2_EMPTY = 0xFFFFFFFFu;
+
+struct CacheV2 {
+  uint2* tags;       // [SETS] two 32-bit tags per set
+  unsigned int* lo;  // [2 * SETS]
+  int* hi;           // [2 * SETS]
+};
+
+// returns true when (key, q) was added to the CTA's cache; key < 2^32 - 1
+__device__ __forceinline__ bool cache_absorb_v2(const CacheV2& c, unsigned int t, long long q) {
+  const unsigned int set = __umulhi(t * 0x9E3779B1u, (unsigned)V2_SETS);
+  unsigned int* tg = reinterpret_cast<unsigned int*>(c.tags + set);
+  const unsigned long long both = *reinterpret_cast<volatile unsigned long long*>(c.tags + set);
+  const uint2 cur = make_uint2((unsigned)both, (unsigned)(both >> 32));
+  int way = -1;
+  if (cur.x == t) way = 0;
+  else if (cur.y == t) way = 1;
+  else {
+    if (cur.x == V2_EMPTY) {
+      const unsigned old = atomicCAS(tg, V2_EMPTY, t);
+      if (old == V2_EMPTY || old == t) way = 0;
+    }
+    if (way < 0) {
+      const unsigned y = *reinterpret_cast<volatile unsigned int*>(tg + 1);
+      if (y == t) way = 1;
+      else if (y == V2_EMPTY) {
+        const unsigned old = atomicCAS(tg + 1, V2_EMPTY, t);
+        if (old == V2_EMPTY || old == t) way = 1;
+      }
+    }
+  }
+  if (way < 0) return false;
+  const unsigned slot = 2u * set + (unsigned)way;
+  const unsigned int qlo = (unsigned int)(unsigned long long)q;
+  const int qhi = (int)(q >> 32);
+  const unsigned int old = atomicAdd(&c.lo[slot], qlo);
+  const int h = qhi + ((unsigned int)(old + qlo) < qlo ? 1 : 0);
+  if (h != 0) atomicAdd(&c.hi[slot], h);
+  return true;
+}
+
+__device__ __forceinline__ long long quanta_of(float v, double qscale, float qscale_f, unsigned& bad, unsigned long long& maxabs) {
+  // power-of-two quantum: the scaling is exact in float; an integral result below 2^23 needs no FP64
+  const float qf = v * qscale_f;
+  const int qi = (int)qf;
+  if (fabsf(qf) < 8388608.0f && (float)qi == qf) {
+    const unsigned long long aq = (unsigned long long)(qi < 0 ? -qi : qi);
+    maxabs = aq > maxabs ? aq : maxabs;
+    return qi;
+  }
+  return inc_to_quanta(v, qscale, bad, maxabs);
+}
+__device__ __forceinline__ long long quanta_of(double v, double qscale, float, unsigned& bad, unsigned long long& maxabs) {
+  return inc_to_quanta(v, qscale, bad, maxabs);
+}
+__device__ __forceinline__ long long quanta_of(unsigned char v, double qscale, float, unsigned& bad, unsigned long long& maxabs) {
+  return inc_to_quanta(v, qscale, bad, maxabs);
+}
+
+template <typename T, bool VEC, int D, typename K, bool AGG>
+__global__ void __launch_bounds__(V2_THREADS, 1) k_update_single_v2(const UpdateArgs<T, K> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CacheV2 c;
+  c.tags = reinterpret_cast<uint2*>(smem_raw);
+  c.lo = reinterpret_cast<unsigned int*>(c.tags + V2_SETS);
+  c.hi = reinterpret_cast<int*>(c.lo + 2 * V2_SETS);
+  long long* mq_key = reinterpret_cast<long long*>(c.hi + 2 * V2_SETS) + (threadIdx.x >> 5) * (2 * MISS_Q);
+  long long* mq_val = mq_key + MISS_Q;
+  for (int s = threadIdx.x; s < V2_SETS; s += blockDim.x) {
+    c.tags[s] = make_uint2(V2_EMPTY, V2_EMPTY);
+    c.lo[2 * s] = c.lo[2 * s + 1] = 0;
+    c.hi[2 * s] = c.hi[2 * s + 1] = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  int qn = 0;
+  unsigned int bad = 0;
+  unsigned long long maxabs = 0;
+  const float qscale_f = (float)p.qscale;
+  const long long n4 = p.n & ~3LL;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  const long long first = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * 4;
+  for (long long wbase = first; wbase < n4; wbase += stride) {
+    const long long base = wbase + (long long)lane * 4;
+    const bool live = base < n4;
+    Quad<T> ev;
+    if (live) load_quad<T, false, VEC, K>(p, base, ev);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      long long q = 0;
+      if (live) q = quanta_of(ev.inc[j], p.qscale, qscale_f, bad, maxabs);
+      const long long key = ev.key[j];
+      const bool act = live && q != 0;
+      // cacheable: the key fits the 32-bit tag; AGG also needs 32 of the increments to fit an int
+      bool elig = act && (unsigned long long)key < 0xFFFFFFFFull;
+      bool miss = act && !elig;
+      if (AGG) {
+        elig = elig && q > -(1 << 26) && q < (1 << 26);
+        miss = act && !elig;
+        const unsigned peers = __match_any_sync(0xffffffffu, elig ? (unsigned)key : V2_EMPTY);
+        const int qs = __reduce_add_sync(peers, elig ? (int)q : 0);
+        if (elig) {
+          if (lane == __ffs(peers) - 1) {
+            q = qs;
+            miss = qs != 0 && !cache_absorb_v2(c, (unsigned)key, qs);
+          }
+        }
+      } else if (elig) {
+        miss = !cache_absorb_v2(c, (unsigned)key, q);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, miss);
+      if (miss) {
+        const int at = qn + __popc(m & ((1u << lane) - 1u));
+        mq_key[at] = key;
+        mq_val[at] = q;
+      }
+      qn += __popc(m);
+      __syncwarp();
+      if (qn >= 32) {
+        qn -= 32;
+        scatter_event<D>(p.counters, p.hf, mq_key[qn + lane], mq_val[qn + lane]);
+        __syncwarp();
+      }
+    }
+  }
+  if (lane < qn) scatter_event<D>(p.counters, p.hf, mq_key[lane], mq_val[lane]);
+  if (blockIdx.x == 0 && threadIdx.x < (unsigned)(p.n - n4)) {
+    long long t = n4 + threadIdx.x;
+    long long q = inc_to_quanta(p.inc[t], p.qscale, bad, maxabs);
+    if (q != 0) scatter_event<D>(p.counters, p.hf, (long long)p.key[t], q);
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < 2 * V2_SETS; s += blockDim.x) {
+    const unsigned t = reinterpret_cast<const unsigned*>(c.tags)[s];
+    if (t == V2_EMPTY) continue;
+    const long long sum = (long long)(((unsigned long long)(unsigned int)c.hi[s] << 32) | c.lo[s]);
+    if (sum != 0) scatter_event<D>(p.counters, p.hf, (long long)t, sum);
+  }
+  publish_flags(p.flags, bad, 0u, maxabs);
+}
+
+// ------------------------------------------------------------------------------------------
 // small kernels: hash, point query, read-back, pair cosine
 // ------------------------------------------------------------------------------------------
 __global__ void k_hash_keys(uint64_t a_res, uint64_t b_res, uint32_t w, uint32_t wmask,
@@ -420,7 +572,31 @@ static int launch_update(mb200_bank* bk, const K* entity, const K* key, const T*
     if (bk->E > 1 && entity && mb200_group_applicable(bk, n)) return mb200_group_update<T>(bk, entity, key, inc, n);
   }
   ProfScope prof(ctx, MB200_K_UPDATE);
-  if (bk->E == 1) {
+  if (bk->E == 1 && ctx->single_kernel != 0) {
+    // single-sketch mode, second form: one 1024-thread CTA per SM, 2-way cache, optional warp aggregation
+    const size_t smem = (size_t)V2_SETS * 24 + (size_t)(V2_THREADS / 32) * 2 * MISS_Q * sizeof(long long);
+    long long want = ceil_div64(n, (int64_t)V2_THREADS * 4);
+    int grid = (int)(want < (long long)ctx->num_sms ? want : (long long)ctx->num_sms);
+#define LAUNCH_V2(VEC, D, AGG)                                                                               \
+  do {                                                                                                       \
+    MB_CUDA(ctx, cudaFuncSetAttribute(k_update_single_v2<T, VEC, D, K, AGG>,                                 \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    k_update_single_v2<T, VEC, D, K, AGG><<<grid, V2_THREADS, smem, ctx->stream>>>(p);                       \
+  } while (0)
+    const bool agg = ctx->single_kernel == 2;
+    if (d4) {
+      if (vec && agg) LAUNCH_V2(true, 4, true);
+      else if (vec) LAUNCH_V2(true, 4, false);
+      else if (agg) LAUNCH_V2(false, 4, true);
+      else LAUNCH_V2(false, 4, false);
+    } else {
+      if (vec && agg) LAUNCH_V2(true, 0, true);
+      else if (vec) LAUNCH_V2(true, 0, false);
+      else if (agg) LAUNCH_V2(false, 0, true);
+      else LAUNCH_V2(false, 0, false);
+    }
+#undef LAUNCH_V2
+  } else if (bk->E == 1) {
     // single-sketch mode: the entity column (if any) is not needed
     const int threads = 512;
     const size_t smem = (size_t)(1 << p.slots_log2) * 16 + (size_t)(threads / 32) * 2 * MISS_Q * sizeof(long long);

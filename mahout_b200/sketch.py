@@ -458,9 +458,19 @@ def cosine_topk_blocks(ctx: Context, a_rows, a_valid, b_rows, b_valid, depth: in
         ldc = blocks * ((b_count + bn - 1) // bn) * bn
         dense = torch.full((a_count, ldc), float("nan"), dtype=torch.float32, device=dev)
         args.dense_out, args.dense_ld = dense.data_ptr(), ldc
+    import os
+    import time
+    dbg = os.environ.get("MB200_BENCH_DEBUG") is not None
+    t0 = time.perf_counter()
     torch.cuda.synchronize(ctx.device)
+    t1 = time.perf_counter()
     N.check(N.lib().mb200_cosine_topk(ctx.handle, C.byref(args)), ctx.handle)
+    t2 = time.perf_counter()
     ctx.sync()
+    if dbg:
+        import sys
+        print(f"[bench debug] cosine_topk_blocks {precision}: sync before {1e3 * (t1 - t0):.2f} ms, call "
+              f"{1e3 * (t2 - t1):.2f} ms, sync after {1e3 * (time.perf_counter() - t2):.2f} ms", file=sys.stderr)
     return (idx, sim, cnt, dense) if want_dense else (idx, sim, cnt)
 
 

@@ -16,6 +16,8 @@ typedef jobject jclass;
 typedef jobject jlongArray;
 typedef jobject jdoubleArray;
 typedef jobject jintArray;
+typedef jobject jfloatArray;
+typedef jint jsize;
 struct JNINativeInterface_;
 typedef const struct JNINativeInterface_* JNIEnv;
 struct JNINativeInterface_ {
@@ -30,5 +32,8 @@ struct JNINativeInterface_ {
   void* (*GetDirectBufferAddress)(JNIEnv*, jobject);
   jobject (*NewDirectByteBuffer)(JNIEnv*, void*, jlong);
   void (*SetLongArrayRegion)(JNIEnv*, jlongArray, jint, jint, const jlong*);
+  jfloat* (*GetFloatArrayElements)(JNIEnv*, jfloatArray, jboolean*);
+  void (*ReleaseFloatArrayElements)(JNIEnv*, jfloatArray, jfloat*, jint);
+  jsize (*GetArrayLength)(JNIEnv*, jobject);
 };
 #endif
