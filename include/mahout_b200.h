@@ -71,8 +71,11 @@ int mb200_sync(mb200_ctx* ctx);
 #define MB200_OPT_GROUP_PREFETCH 2   /* the partition passes of that grouping pull their next tile into L2 with
                                         cp.async.bulk.prefetch (default 0: measured neutral on B200, profiles/r2_k1_bank.md) */
 #define MB200_OPT_SINGLE_KERNEL 3    /* single-sketch K1: 0 = first form (2 x 512 threads, 4096 direct-mapped slots),
-                                        1 = one 1024-thread CTA per SM with a 2-way cache of 14336 keys, 2 = the same with
-                                        warp-level aggregation of equal keys (default) */
+                                        1 = one 1024-thread CTA per SM with a 2-way cache of 14336 keys (default; measured
+                                        152 vs 103 G events/s on config 2), 2 = the same with warp-level aggregation of
+                                        equal keys through MATCH.ANY (measured 45 G events/s: kept for the record) */
+#define MB200_OPT_MAX_FALLBACK_ROWS 4 /* RESCORED / CERTIFIED: fail with MB200_ERR_UNSUPPORTED instead of sending more
+                                        than this many rows through the exact full-row path (default -1: no limit) */
 int mb200_set_option(mb200_ctx* ctx, int option, int64_t value);
 /* the cosine stage keeps its device workspaces (candidate lists, gathered rows of the single-GPU
  * convenience call) on the context between calls; this frees them */
@@ -105,6 +108,13 @@ typedef struct mb200_stats {
   int64_t last_fallback_rows;  /* rows of the last cosine call that took the exact full-row path */
   int32_t cosine_job_active;
   char device_name[64];
+  /* cumulative job counters of this context (RowSimilarityJob.Counters, RowSimilarityJob.java:84, as far as they
+   * exist on this path): events applied by mb200_bank_update* (USED_OBSERVATIONS), entity rows whose top-k was
+   * computed (ROWS), rows that took the exact full-row path */
+  int64_t events_updated;
+  int64_t rows_scored;
+  int64_t fallback_rows_total;
+  int64_t h2d_bytes, d2h_bytes;  /* bytes the library itself copied for MB200_MEM_HOST arguments / results */
 } mb200_stats;
 int mb200_get_stats(mb200_ctx* ctx, mb200_stats* out);
 
@@ -144,6 +154,12 @@ int mb200_bank_create_params(mb200_ctx* ctx, int64_t entities, int32_t depth, in
                              mb200_bank** out);
 int mb200_bank_destroy(mb200_bank* bank);
 int mb200_bank_clear(mb200_bank* bank);
+/* Checkpoint of a bank (the reference persists its per-user sketch configuration the same way, as a file next to
+ * the data: CountMinSketchConfig's .ser cache, CountMinSketchConfig.java:170-219): header (shape, quantum, hash
+ * parameters, event count) + the raw fixed-point counters.  mb200_bank_load creates a new bank with exactly the
+ * dumped state; MB200_ERR_BAD_ARG on a file that is not a dump or is truncated. */
+int mb200_bank_dump(mb200_bank* bank, const char* path);
+int mb200_bank_load(mb200_ctx* ctx, const char* path, mb200_bank** out);
 /* device pointer of the raw int64 counters (for an NCCL all-reduce of replica sketches) */
 int mb200_bank_counters(mb200_bank* bank, void** device_ptr, int64_t* cells);
 /* 64-byte CUDA IPC handle of the counters: another rank maps them with mb200_peer_open */

@@ -18,7 +18,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 DTYPE_F16, DTYPE_BF16 = 0, 1
 PRECISION_TENSOR, PRECISION_RESCORED, PRECISION_CERTIFIED = 0, 1, 2
 K_UPDATE, K_NORMALIZE, K_COSINE, K_RESCORE, K_PARSE, K_PREPARE, K_GROUP, K_ROUTE = 0, 1, 2, 3, 4, 5, 6, 7
-OPT_GROUP_MIN_EVENTS, OPT_GROUP_PREFETCH, OPT_SINGLE_KERNEL = 1, 2, 3
+OPT_GROUP_MIN_EVENTS, OPT_GROUP_PREFETCH, OPT_SINGLE_KERNEL, OPT_MAX_FALLBACK_ROWS = 1, 2, 3, 4
 MAX_DEPTH = 32
 
 
@@ -60,7 +60,9 @@ class Stats(C.Structure):
     """struct mb200_stats (include/mahout_b200.h)."""
     _fields_ = [("device", C.c_int32), ("num_sms", C.c_int32), ("launches", C.c_int64),
                 ("workspace_bytes", C.c_int64), ("staging_bytes", C.c_int64), ("last_fallback_rows", C.c_int64),
-                ("cosine_job_active", C.c_int32), ("device_name", C.c_char * 64)]
+                ("cosine_job_active", C.c_int32), ("device_name", C.c_char * 64), ("events_updated", C.c_int64),
+                ("rows_scored", C.c_int64), ("fallback_rows_total", C.c_int64), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64)]
 
 
 class JobParams(C.Structure):
@@ -113,6 +115,8 @@ _PROTOS = {
     "mb200_bank_ipc_handle": (C.c_int, [vp, vp]),
     "mb200_bank_narrow32": (C.c_int, [vp, vp]),
     "mb200_bank_counters": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+    "mb200_bank_dump": (C.c_int, [vp, C.c_char_p]),
+    "mb200_bank_load": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "mb200_bank_update": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
     "mb200_bank_update_f64": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),
     "mb200_bank_update_grouped": (C.c_int, [vp, vp, vp, vp, i64, C.c_int]),

@@ -56,7 +56,8 @@ struct mb200_ctx {
   std::vector<std::pair<void*, size_t>> ws_group;
   int64_t group_min_events = 1 << 16;  // MB200_OPT_GROUP_MIN_EVENTS
   int group_prefetch = 0;              // MB200_OPT_GROUP_PREFETCH
-  int single_kernel = 2;               // MB200_OPT_SINGLE_KERNEL
+  int single_kernel = 1;               // MB200_OPT_SINGLE_KERNEL
+  int64_t max_fallback_rows = -1;      // MB200_OPT_MAX_FALLBACK_ROWS
   // grow-only device staging of host-memory arguments (see io_slot in sketch.cu)
   std::pair<void*, size_t> io[3] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
   // pull-gather: per-block arrival flags written by the copy stream, read by K3 (+ 1 abort word)
@@ -65,6 +66,7 @@ struct mb200_ctx {
   uint32_t gather_epoch = 0;
   cudaEvent_t gather_ev = nullptr;
   int64_t last_fallback_rows = 0;
+  int64_t stat_events = 0, stat_rows = 0, stat_fallback = 0, stat_h2d = 0, stat_d2h = 0;
   struct mb200_cosine_job* active_job = nullptr;  // the cosine stage's workspaces serve one job at a time
 };
 

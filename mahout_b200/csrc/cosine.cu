@@ -2207,6 +2207,7 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
     j->mp.cand_bound = (float*)d_cbound.p;
   }
   ctx->last_fallback_rows = 0;
+  ctx->stat_rows += a->a_count;
   {
     ProfScope prof(ctx, MB200_K_RESCORE);
     MergeParams mp;
@@ -2323,6 +2324,11 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       TRACE("rescore");
       ctx->last_fallback_rows = nflag;
+      ctx->stat_fallback += nflag;
+      if (ctx->max_fallback_rows >= 0 && nflag > ctx->max_fallback_rows)
+        return mb200_fail(ctx, MB200_ERR_UNSUPPORTED,
+                          "%d rows cannot be certified from their candidate lists and would take the exact full-row path "
+                          "(limit MB200_OPT_MAX_FALLBACK_ROWS = %lld)", nflag, (long long)ctx->max_fallback_rows);
       if (nflag > 0) {
         // exact full-row path, in batches bounded by scratch memory
         rp.b_id_add = (uint32_t)fin->b_id_add;  // forward mapping for k_exact_*

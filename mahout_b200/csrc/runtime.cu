@@ -159,6 +159,11 @@ int mb200_get_stats(mb200_ctx* ctx, mb200_stats* out) {
   out->staging_bytes += 2 * (int64_t)ctx->stage_bytes;
   out->last_fallback_rows = ctx->last_fallback_rows;
   out->cosine_job_active = ctx->active_job ? 1 : 0;
+  out->events_updated = ctx->stat_events;
+  out->rows_scored = ctx->stat_rows;
+  out->fallback_rows_total = ctx->stat_fallback;
+  out->h2d_bytes = ctx->stat_h2d;
+  out->d2h_bytes = ctx->stat_d2h;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) {
     strncpy(out->device_name, prop.name, sizeof(out->device_name) - 1);
@@ -204,6 +209,9 @@ int mb200_set_option(mb200_ctx* ctx, int option, int64_t value) {
     case MB200_OPT_SINGLE_KERNEL:
       if (value < 0 || value > 2) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_set_option: SINGLE_KERNEL must be 0, 1 or 2");
       ctx->single_kernel = (int)value;
+      return MB200_OK;
+    case MB200_OPT_MAX_FALLBACK_ROWS:
+      ctx->max_fallback_rows = value;
       return MB200_OK;
     case MB200_OPT_GROUP_PREFETCH:
       ctx->group_prefetch = value ? 1 : 0;

@@ -697,6 +697,8 @@ static int bank_update_impl(mb200_bank* bk, const KIn* entity, const KIn* key, c
   if (bk->E > 1 && !entity)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_update: entity is NULL but the bank has %lld entities", (long long)bk->E);
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->stat_events += n;
+  if (mem == MB200_MEM_HOST) ctx->stat_h2d += n * (int64_t)(sizeof(K) + sizeof(T) + (entity && bk->E > 1 ? sizeof(K) : 0));
   if (mem == MB200_MEM_DEVICE)
     return launch_update<T, K>(bk, (const K*)entity, (const K*)key, inc, n);
   if (mem == MB200_MEM_HOST) return update_from_host<T, K>(bk, (const K*)entity, (const K*)key, inc, n);
@@ -744,6 +746,7 @@ struct OutBuf {
   }
   int release() {
     if (!staged) return MB200_OK;
+    ctx->stat_d2h += (int64_t)bytes;
     MB_CUDA(ctx, cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MB200_OK;
@@ -766,6 +769,7 @@ struct InBuf {
     }
     MB_CHECK(io_slot(ctx, slot, bytes, &dev));
     staged = true;
+    ctx->stat_h2d += (int64_t)bytes;
     MB_CUDA(ctx, cudaMemcpyAsync(dev, user, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return MB200_OK;
   }
@@ -866,6 +870,98 @@ int mb200_bank_clear(mb200_bank* bk) {
   MB_CUDA(ctx, cudaMemsetAsync(bk->flags, 0, FLAG_WORDS * sizeof(unsigned long long), ctx->stream));
   bk->events_total = 0;
   bk->virgin = true;
+  return MB200_OK;
+}
+
+// ---- checkpoint ----------------------------------------------------------------------------------------------
+struct DumpHeader {
+  char magic[8];  // "MB200BK1"
+  int64_t E;
+  int32_t d, W, frac_bits, reserved;
+  double events_total;
+  int64_t a[MB200_MAX_DEPTH], b[MB200_MAX_DEPTH];
+};
+
+int mb200_bank_dump(mb200_bank* bk, const char* path) {
+  if (!bk || !path) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_bank_dump: NULL argument");
+  mb200_ctx* ctx = bk->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MB_CHECK(check_flags(bk));  // a bank with pending errors is not worth keeping
+  FILE* f = fopen(path, "wb");
+  if (!f) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_dump: cannot write %s", path);
+  DumpHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "MB200BK1", 8);
+  h.E = bk->E;
+  h.d = bk->d;
+  h.W = bk->W;
+  h.frac_bits = bk->frac_bits;
+  h.events_total = bk->events_total;
+  memcpy(h.a, bk->a_raw, sizeof(h.a));
+  memcpy(h.b, bk->b_raw, sizeof(h.b));
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  const size_t cells = (size_t)bk->E * bk->d * bk->W, chunk = (size_t)8 << 20;  // 64 MiB of counters per copy
+  std::vector<long long> host(cells < chunk ? cells : chunk);
+  for (size_t off = 0; off < cells && ok; off += chunk) {
+    const size_t m = cells - off < chunk ? cells - off : chunk;
+    cudaError_t e = cudaMemcpyAsync(host.data(), bk->counters + off, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      fclose(f);
+      return mb200_fail(ctx, MB200_ERR_CUDA, "mb200_bank_dump: %s", cudaGetErrorString(e));
+    }
+    ok = fwrite(host.data(), 8, m, f) == m;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_dump: short write to %s", path);
+  ctx->stat_d2h += (int64_t)cells * 8;
+  return MB200_OK;
+}
+
+int mb200_bank_load(mb200_ctx* ctx, const char* path, mb200_bank** out) {
+  if (!ctx || !path || !out) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_load: NULL argument");
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_load: cannot read %s", path);
+  DumpHeader h;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "MB200BK1", 8) != 0 || h.E <= 0 || h.d <= 0 ||
+      h.d > MB200_MAX_DEPTH || h.W <= 0) {
+    fclose(f);
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_load: %s is not a bank dump", path);
+  }
+  mb200_bank* bk = nullptr;
+  int rc = mb200_bank_create_params(ctx, h.E, h.d, h.W, h.a, h.b, h.frac_bits, &bk);
+  if (rc != MB200_OK) {
+    fclose(f);
+    return rc;
+  }
+  std::lock_guard<std::mutex> g(ctx->mu);
+  const size_t cells = (size_t)h.E * h.d * h.W, chunk = (size_t)8 << 20;
+  std::vector<long long> host(cells < chunk ? cells : chunk);
+  for (size_t off = 0; off < cells; off += chunk) {
+    const size_t m = cells - off < chunk ? cells - off : chunk;
+    cudaError_t e = cudaSuccess;
+    if (fread(host.data(), 8, m, f) != m) {
+      fclose(f);
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(bk->counters);
+      cudaFree(bk->flags);
+      delete bk;
+      return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_bank_load: %s is truncated", path);
+    }
+    e = cudaMemcpyAsync(bk->counters + off, host.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      fclose(f);
+      return mb200_fail(ctx, MB200_ERR_CUDA, "mb200_bank_load: %s", cudaGetErrorString(e));
+    }
+  }
+  fclose(f);
+  bk->events_total = h.events_total;
+  bk->virgin = false;
+  ctx->stat_h2d += (int64_t)cells * 8;
+  *out = bk;
   return MB200_OK;
 }
 

@@ -294,6 +294,26 @@ class SketchBank:
     def clear(self):
         N.check(N.lib().mb200_bank_clear(self.handle), self.ctx.handle)
 
+    def dump(self, path: str):
+        """checkpoint: shape, quantum, hash parameters and the raw counters (mb200_bank_dump)"""
+        N.check(N.lib().mb200_bank_dump(self.handle, str(path).encode()), self.ctx.handle)
+
+    @classmethod
+    def load(cls, path: str, ctx: "Context | None" = None) -> "SketchBank":
+        """a new bank with exactly the dumped state (mb200_bank_load)"""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        N.check(N.lib().mb200_bank_load(ctx.handle, str(path).encode(), C.byref(h)), ctx.handle)
+        self = cls.__new__(cls)
+        self.ctx, self._h, self.hfBuilder = ctx, h, None
+        import struct
+        with open(path, "rb") as f:
+            head = f.read(8 + 8 + 16 + 8 + 16 * N.MAX_DEPTH)
+        self.E, self.d, self.w, self.frac_bits, _ = struct.unpack_from("<qiiii", head, 8)
+        self.a = np.frombuffer(head, np.int64, self.d, 40).copy()
+        self.b = np.frombuffer(head, np.int64, self.d, 40 + 8 * N.MAX_DEPTH).copy()
+        return self
+
     def update(self, entity, key, inc):
         """C[entity[t]][i][h_i(key[t])] += inc[t]; entity may be None when E == 1."""
         k = _Arg(key, np.int64, "int64")

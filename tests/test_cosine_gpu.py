@@ -421,3 +421,23 @@ def test_boolean_data_tie_groups_take_the_exact_path(mb, ctx, precision, monkeyp
             assert sim.tobytes() == osim.tobytes()
         results.append((idx, sim))
     assert (results[0][0] == results[1][0]).all() and results[0][1].tobytes() == results[1][1].tobytes()
+
+
+@pytest.mark.parametrize("dtype,k", [("bf16", 20), ("f16", 192), ("bf16", 192)])
+def test_bf16_rows_and_largest_k_keep_the_exact_contract(mb, ctx, dtype, k):
+    """BF16 rows (8-bit significand: a wide undecided band) and k at the fused top-k capacity (CAP - 64 = 192, no
+    re-scoring margin left): RESCORED must still be bit-equal to the oracle and CERTIFIED must return its sets --
+    through more fallback rows if that is what it takes."""
+    from mahout_b200.sketch import last_fallback_rows
+    E, d, w = 700, 2, 512
+    bank, ref = _make_bank(mb, ctx, E, d, w, 80 * E, seed=91 + k, empty=(5,))
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    idx, sim, cnt = bank.cosine_topk(k, dtype=dtype, precision="rescored")
+    assert (cnt == ocnt).all() and (idx == oidx).all() and sim.tobytes() == osim.tobytes()
+    cidx, csim, ccnt = bank.cosine_topk(k, dtype=dtype, precision="certified")
+    assert (ccnt == ocnt).all()
+    assert all(set(cidx[r, :ccnt[r]].tolist()) == set(oidx[r, :ocnt[r]].tolist()) for r in range(E))
+    assert last_fallback_rows(ctx) <= E
+    with pytest.raises(mb.NativeError):
+        bank.cosine_topk(193)                         # beyond the fused capacity: refused, never truncated
+    bank.close()

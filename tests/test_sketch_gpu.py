@@ -495,3 +495,67 @@ def test_context_stats(mb, ctx):
     st2 = ctx.stats()
     assert st2["launches"] > st["launches"] and st2["workspace_bytes"] > 0 and st2["cosine_job_active"] == 0
     bank.close()
+
+
+def test_bank_dump_and_load_round_trip(mb, ctx, tmp_path):
+    """checkpoint: a loaded bank has the dumped counters, hash family and quantum, keeps accepting updates, and a
+    truncated or foreign file is refused"""
+    rng = np.random.Generator(np.random.PCG64(44))
+    E, d, w, n = 37, 3, 1000, 20000
+    ent, key, inc = _events(rng, n, E, -50, 100000)
+    bank = mb.SketchBank(E, w, d, 1234, 1, ctx)
+    bank.update(ent, key, inc)
+    path = str(tmp_path / "bank.mb200")
+    bank.dump(path)
+    back = mb.SketchBank.load(path, ctx)
+    assert (back.E, back.d, back.w, back.frac_bits) == (E, d, w, 1)
+    assert back.a.tolist() == bank.a.tolist() and back.b.tolist() == bank.b.tolist()
+    assert back.read().tobytes() == bank.read().tobytes()
+    bank.update(ent[:500], key[:500], inc[:500])
+    back.update(ent[:500], key[:500], inc[:500])
+    assert back.read().tobytes() == bank.read().tobytes()
+    q = rng.integers(-50, 100000, 300).astype(np.int64)
+    qe = rng.integers(0, E, 300).astype(np.int64)
+    assert back.query(qe, q).tobytes() == bank.query(qe, q).tobytes()
+    raw = open(path, "rb").read()
+    open(path, "wb").write(raw[:len(raw) // 2])
+    with pytest.raises(ValueError, match="truncated"):
+        mb.SketchBank.load(path, ctx)
+    open(path, "wb").write(b"not a dump at all" * 100)
+    with pytest.raises(ValueError, match="not a bank dump"):
+        mb.SketchBank.load(path, ctx)
+    st = ctx.stats()
+    assert st["events_updated"] > 0 and st["h2d_bytes"] > 0 and st["d2h_bytes"] > 0
+    bank.close()
+    back.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_single_sketch_kernel_forms_bit_exact(mb, ctx, variant):
+    """MB200_OPT_SINGLE_KERNEL: the three forms of the single-sketch K1 (direct-mapped cache; 2-way cache in one
+    1024-thread CTA; the same with warp aggregation) give the oracle's counters on a Zipf stream with keys outside
+    the 32-bit tag range, negative increments and the n % 4 tail."""
+    from mahout_b200 import _native as N
+    rng = np.random.Generator(np.random.PCG64(70 + variant))
+    n, d, w = 400003, 4, 1 << 16
+    key = np.minimum(rng.zipf(1.1, n), 10 ** 7).astype(np.int64)
+    key[::50] = rng.integers(-2 ** 62, 2 ** 62, key[::50].shape[0])
+    key[1::97] = 2 ** 32 - 1
+    inc = (rng.integers(-6, 11, n) * 0.5).astype(np.float32)
+    a, b = orc.hash_params(42, d)
+    want = np.zeros((1, d, w))
+    orc.bank_update(want, d, w, a, b, None, key, inc)
+    ctx.set_option(N.OPT_SINGLE_KERNEL, variant)
+    try:
+        import torch
+        for dev in (False, True):
+            bank = mb.SketchBank(1, w, d, 42, 1, ctx)
+            if dev:
+                bank.update(None, torch.from_numpy(key).cuda(), torch.from_numpy(inc).cuda())
+            else:
+                bank.update(None, key, inc)
+            bank.check()
+            assert bank.read().tobytes() == want.tobytes(), (variant, dev)
+            bank.close()
+    finally:
+        ctx.set_option(N.OPT_SINGLE_KERNEL, 1)

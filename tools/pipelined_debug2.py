@@ -12,6 +12,7 @@ torch.cuda.set_device(local)
 dev = torch.device(f"cuda:{local}")
 dist.init_process_group("nccl", device_id=dev)
 ctx = mb.Context(local)
+ctx.set_option(N.OPT_MAX_FALLBACK_ROWS, 64)
 stream = torch.cuda.Stream(dev)
 torch.cuda.set_stream(stream)
 ctx.set_stream(stream.cuda_stream)
@@ -30,24 +31,30 @@ a_cnt = bank.counters_tensor()
 N.check(N.lib().mb200_bank_normalize(bank.handle, N.DTYPE_F16, C.c_void_p(peers.rows.data_ptr()), C.c_void_p(peers.valid.data_ptr())), ctx.handle)
 res = {}
 for form in ("fused", "pipelined8192", "pipelined32768", "fused"):
+  try:
+      torch.cuda.synchronize()
+      t0 = time.perf_counter()
+      if form == "fused":
+          r = sim.fused_gather_cosine(be, plan, peers, k, None, "f16", "certified", a_counters=a_cnt, counter_blocks=blocks)
+      else:
+          peers.refresh_narrow()
+          peers.barrier()
+          r = sim.pipelined_cosine(be, plan, peers.rows, peers.valid, k, None, "f16", "certified", None, int(form[9:]), a_cnt,
+                                   False, counter_blocks=blocks, counter_blocks32=peers.counter_blocks32)
+          peers.barrier()
+      torch.cuda.synchronize()
+      fb = last_fallback_rows(ctx)
+      print(f"rank {rank} {form}: {1e3 * (time.perf_counter() - t0):.1f} ms, fallback rows {fb}", flush=True)
+      if "fused" in res and form != "fused":
+          same = all(torch.equal(x, y) for x, y in zip(r, res["fused"]))
+          cnt_same = bool((r[2] == res["fused"][2]).all())
+          print(f"rank {rank} {form} equals fused: {same} (counts {cnt_same})", flush=True)
+      res[form] = tuple(t.clone() for t in r)
+
+  except Exception as ex:
+    print(f'rank {rank} {form}: FAILED {ex}', flush=True)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    if form == "fused":
-        r = sim.fused_gather_cosine(be, plan, peers, k, None, "f16", "certified", a_counters=a_cnt, counter_blocks=blocks)
-    else:
-        peers.refresh_narrow()
-        peers.barrier()
-        r = sim.pipelined_cosine(be, plan, peers.rows, peers.valid, k, None, "f16", "certified", None, int(form[9:]), a_cnt,
-                                 False, counter_blocks=blocks, counter_blocks32=peers.counter_blocks32)
-        peers.barrier()
-    torch.cuda.synchronize()
-    fb = last_fallback_rows(ctx)
-    print(f"rank {rank} {form}: {1e3 * (time.perf_counter() - t0):.1f} ms, fallback rows {fb}", flush=True)
-    if "fused" in res and form != "fused":
-        same = all(torch.equal(x, y) for x, y in zip(r, res["fused"]))
-        cnt_same = bool((r[2] == res["fused"][2]).all())
-        print(f"rank {rank} {form} equals fused: {same} (counts {cnt_same})", flush=True)
-    res[form] = tuple(t.clone() for t in r)
+    peers.barrier()
 peers.close()
 dist.barrier()
 dist.destroy_process_group()
