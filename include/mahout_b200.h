@@ -114,6 +114,7 @@ typedef struct mb200_stats {
   int64_t events_updated;
   int64_t rows_scored;
   int64_t fallback_rows_total;
+  int64_t band_rows_total;       /* rows settled by the band pass (second targeted K3 sweep) */
   int64_t h2d_bytes, d2h_bytes;  /* bytes the library itself copied for MB200_MEM_HOST arguments / results */
 } mb200_stats;
 int mb200_get_stats(mb200_ctx* ctx, mb200_stats* out);
@@ -407,8 +408,14 @@ int mb200_cosine_begin(mb200_ctx* ctx, const mb200_cosine_args* args, mb200_cosi
 int mb200_cosine_push(mb200_cosine_job* job, const mb200_cosine_piece* piece);
 int mb200_cosine_finish(mb200_cosine_job* job, const mb200_cosine_args* fin);
 int mb200_cosine_abort(mb200_cosine_job* job);
-/* rows whose top-k could not be certified from the tensor-core candidates and went through the
- * exact full-row path during the last mb200_cosine_topk / mb200_bank_cosine_topk on ctx */
+/* rows whose top-k could not be certified from the tensor-core candidates during the last mb200_cosine_topk /
+ * mb200_cosine_finish / mb200_bank_cosine_topk on ctx.  They first get a BAND PASS: a second K3 sweep over those rows
+ * only, with a fixed per-row cut below which no column can be in the top-k, every column above it re-scored exactly
+ * (needs the B side of a one-push job still resident: pass b_rows / b_valid again in the finish arguments; the
+ * one-shot calls do).  What the band pass cannot settle -- counters outside the exact-integer range, tie groups
+ * beyond 2048 columns, or no band pass possible -- takes the exact full-row path (every column, integer dot
+ * products at memory speed): mb200_cosine_last_fallback_rows. */
+int mb200_cosine_last_band_rows(mb200_ctx* ctx, int64_t* rows);
 int mb200_cosine_last_fallback_rows(mb200_ctx* ctx, int64_t* rows);
 
 /* ---- the whole item-similarity phase, on one GPU or on all GPUs of the box ------------------------------- */

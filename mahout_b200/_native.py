@@ -61,7 +61,8 @@ class Stats(C.Structure):
     _fields_ = [("device", C.c_int32), ("num_sms", C.c_int32), ("launches", C.c_int64),
                 ("workspace_bytes", C.c_int64), ("staging_bytes", C.c_int64), ("last_fallback_rows", C.c_int64),
                 ("cosine_job_active", C.c_int32), ("device_name", C.c_char * 64), ("events_updated", C.c_int64),
-                ("rows_scored", C.c_int64), ("fallback_rows_total", C.c_int64), ("h2d_bytes", C.c_int64),
+                ("rows_scored", C.c_int64), ("fallback_rows_total", C.c_int64), ("band_rows_total", C.c_int64),
+                ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64)]
 
 
@@ -160,6 +161,7 @@ _PROTOS = {
     "mb200_cosine_finish": (C.c_int, [vp, C.POINTER(CosineArgs)]),
     "mb200_cosine_abort": (C.c_int, [vp]),
     "mb200_cosine_last_fallback_rows": (C.c_int, [vp, C.POINTER(i64)]),
+    "mb200_cosine_last_band_rows": (C.c_int, [vp, C.POINTER(i64)]),
     "mb200_create_multi": (C.c_int, [i32, vp, C.POINTER(vp)]),
     "mb200_multi_destroy": (C.c_int, [vp]),
     "mb200_multi_gpus": (C.c_int, [vp, C.POINTER(i32)]),

@@ -71,6 +71,13 @@ struct CosParams {
   uint32_t epoch;
   int32_t rot, num_blocks;
   uint32_t* abort_flag;
+  // band pass (second chance of rows the candidate lists could not certify): the A rows are a compact copy of
+  // those rows, a_ids[row] is the row's global index, row_cut[row] the fixed admission threshold (scaled tensor
+  // value) below which a column is provably outside the row's top-k; every column above it is LISTED -- no
+  // selection, no threshold raising; a list that fills up marks band_overflow[row]
+  const uint32_t* a_ids;
+  const float* row_cut;
+  uint32_t* band_overflow;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -439,7 +446,10 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const int t0 = it.y, t1 = it.z;
       const long long grow = (long long)it.x * BM + row;
       const bool row_ok = grow < p.a_count;
-      const uint32_t my_id = (row_ok && p.exclude_self) ? (uint32_t)grow * p.a_id_mul + p.a_id_off : 0xFFFFFFFFu;
+      const bool band = p.row_cut != nullptr;
+      const uint32_t my_id = (row_ok && p.exclude_self)
+                                 ? (p.a_ids ? __ldg(p.a_ids + grow) : (uint32_t)grow * p.a_id_mul + p.a_id_off)
+                                 : 0xFFFFFFFFu;
       uint32_t rv = 0;  // bit dep set <=> (my row, dep) has a non-zero norm
       if (row_ok) {
         for (int dep = 0; dep < p.depth; dep++)
@@ -448,7 +458,7 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const size_t slot = ((size_t)w * 2 + half) * BM + row;
       uint2* list = p.lists + slot * CAP;
       int cnt = 0;
-      float thr = p.thr_init;
+      float thr = (band && row_ok) ? __ldg(p.row_cut + grow) : p.thr_init;
       float bound = -INFINITY;
       bool published = false;
       uint32_t* my_row_thr = p.row_thr + (size_t)it.x * BM + row;
@@ -505,6 +515,15 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                   cnt++;
                 }
               }
+            }
+            if (band) {
+              // everything above the cut is wanted: a list that cannot take another chunk gives up (the row then
+              // goes through the exact full-row path)
+              if (cnt > CAP - 32) {
+                p.band_overflow[grow] = 1u;
+                thr = INFINITY;
+              }
+              return;
             }
             // keep 32 free slots for the next chunk; raise the threshold early once so that the
             // other lists of the row can use it.  Threshold raises are warp-cooperative.
@@ -791,8 +810,11 @@ struct RescoreParams {
   long long* out_idx;
   double* out_sim;
   int32_t* out_cnt;
-  int32_t* row_flag;           // [a_count]: 1 = needs the exact full-row path
+  int32_t* row_flag;           // [a_count]: 1 = not certified (band pass, else exact full-row path), 2 = outside
+                               // the exact-integer range (exact full-row path)
   int32_t* flag_count;
+  float* row_cut;              // [a_count] scaled tensor value below which a column cannot be in the row's top-k
+  float thr_floor;             // the job's admission threshold (scaled)
 };
 
 __device__ __forceinline__ void b_locate(const RescoreParams& p, uint32_t id, long long& g, long long& l) {
@@ -897,10 +919,21 @@ __device__ __forceinline__ void rescore_finish_t(const RescoreParams& p, long lo
     if (b > -INFINITY && !certified_elsewhere) {
       const double bs = (double)(b * p.inv_scale2);
       const double ub = bs + fabs(bs) * (double)p.eps_rel + (double)p.eps_abs;
-      if (!(kth > ub)) flag = 1;
+      if (!(kth > ub) && flag == 0) flag = 1;
     }
     p.row_flag[r] = flag;
     if (flag) atomicAdd(p.flag_count, 1);
+    if (flag == 1 && p.row_cut) {
+      // The true k-th similarity is at least kth * (1 - eps) - eps_abs (kth may itself be a tensor value); a
+      // column whose tensor value is below cut has an exact value below cut * (1 + eps) + eps_abs, which is
+      // below that.  Fewer than k results so far: everything above the job's threshold is wanted.
+      float cut = p.thr_floor;
+      if (kth > -INFINITY) {
+        const double c = (kth * (1.0 - 2.0 * (double)p.eps_rel) - 2.0 * (double)p.eps_abs) / (double)p.inv_scale2;
+        cut = fmaxf(cut, nextafterf((float)c, -INFINITY));
+      }
+      p.row_cut[r] = nextafterf(cut, -INFINITY);
+    }
   }
 }
 
@@ -1007,7 +1040,7 @@ __global__ void __launch_bounds__(256) k_rescore(const RescoreParams p) {
     }
     __syncthreads();
   }
-  if (warp == 0) rescore_finish(p, r, n, s_min, s_bad, lane);
+  if (warp == 0) rescore_finish(p, r, n, s_min, s_bad ? 2 : 0, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1232,7 +1265,7 @@ __global__ void __launch_bounds__(256) k_certify(const RescoreParams p) {
   __syncthreads();
   for (int c = tid; c < nsel; c += blockDim.x) s_fin[s_sel[c]] = s_min[c];   // JAVA_MAX_DOUBLE = not comparable
   __syncthreads();
-  if (warp == 0) rescore_finish(p, r, n, s_fin, s_bad | s_flag, lane, true);
+  if (warp == 0) rescore_finish(p, r, n, s_fin, s_bad ? 2 : (s_flag ? 1 : 0), lane, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1371,7 +1404,7 @@ __global__ void __launch_bounds__(256) k_rescore32(const RescoreParams p, const 
     }
     __syncthreads();
   }
-  if (warp == 0) rescore_finish(p, r, n, s_min, s_bad, lane);
+  if (warp == 0) rescore_finish(p, r, n, s_min, s_bad ? 2 : 0, lane);
 }
 
 // K5b, 16-bit form (every |counter| < 2^15, W % 8 == 0): rows are read as biased unsigned shorts, two per
@@ -1629,9 +1662,222 @@ __global__ void __launch_bounds__(256) k_exact_topk(const RescoreParams p, const
   if (threadIdx.x == 0) p.out_cnt[r] = admitted;
 }
 
-__global__ void k_collect_flagged(const int32_t* row_flag, long long n, int32_t* flagged, int32_t* count) {
+// ------------------------------------------------------------------------------------------------
+// Band pass.  A row the candidate lists could not certify gets a second, targeted sweep instead of the exact
+// full-row path: its normalised row is copied into a compact A operand (k_band_gather), K3 runs over those rows
+// only, with a fixed per-row cut and no selection (every column above the cut is listed), and k_band_finish
+// re-scores what was listed exactly -- integer dot products, as in k_certify -- and writes the row's top-k.
+// The cost is that of K3 over the flagged rows plus a few hundred exact dot products per row, instead of one
+// exact dot product per column.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_band_gather(const uint16_t* __restrict__ rows16, const uint32_t* __restrict__ valid,
+                                                     long long a_count, long long a_vw, int d, int ld,
+                                                     const int32_t* __restrict__ flagged, int nf, long long nf_vw,
+                                                     uint32_t a_id_mul, uint32_t a_id_off, const float* __restrict__ row_cut,
+                                                     uint16_t* __restrict__ out_rows, uint32_t* __restrict__ out_valid,
+                                                     uint32_t* __restrict__ out_ids, float* __restrict__ out_cut) {
+  const int r2 = blockIdx.x;  // compact row
+  const long long r = flagged[r2];
+  for (int i = 0; i < d; i++) {
+    const uint4* src = reinterpret_cast<const uint4*>(rows16 + ((size_t)i * a_count + r) * ld);
+    uint4* dst = reinterpret_cast<uint4*>(out_rows + ((size_t)i * nf + r2) * ld);
+    for (int j = threadIdx.x; j < ld / 8; j += blockDim.x) dst[j] = __ldg(src + j);
+    if (threadIdx.x == 0 && ((__ldg(valid + (size_t)i * a_vw + (r >> 5)) >> (r & 31)) & 1u))
+      atomicOr(out_valid + (size_t)i * nf_vw + (r2 >> 5), 1u << (r2 & 31));
+  }
+  if (threadIdx.x == 0) {
+    out_ids[r2] = (uint32_t)r * a_id_mul + a_id_off;
+    out_cut[r2] = row_cut[r];
+  }
+}
+
+static constexpr int BAND_MAX = 2048;  // candidates per row the band pass can re-score
+
+struct BandParams {
+  const uint2* lists;
+  const int32_t* list_cnt;
+  const int32_t* slot_ptr;
+  const int32_t* slot_of;
+  const uint32_t* band_overflow;
+  const int32_t* flagged;   // compact row -> row of the job
+  int nf;
+};
+
+// exact sums of one (A row, B row, depth) pair by one warp; false when the integers leave the exact range
+__device__ __forceinline__ bool pair_sums_exact(const RescoreParams& p, const long long* __restrict__ a, long long g,
+                                                long long l, int i, int lane, double& va, double& vb, double& vab) {
+  long long aa = 0, bb = 0, ab = 0;
+  unsigned long long amax = 0, bmax = 0;
+  int bad = 0;
+  auto acc = [&](long long x, long long y) {
+    const unsigned long long ax = x < 0 ? (unsigned long long)(-x) : (unsigned long long)x;
+    const unsigned long long ay = y < 0 ? (unsigned long long)(-y) : (unsigned long long)y;
+    amax = ax > amax ? ax : amax;
+    bmax = ay > bmax ? ay : bmax;
+    aa += x * x;
+    bb += y * y;
+    ab += x * y;
+  };
+  if (p.b_blocks32 != nullptr) {
+    const int* b = p.b_blocks32[g] + ((size_t)l * p.d + i) * p.W;
+    int j = 0;
+    if ((p.W & 3) == 0 && (((uintptr_t)b) & 15) == 0 && (((uintptr_t)a) & 15) == 0) {
+      for (; j + 128 <= p.W; j += 128) {
+        const int4 y = __ldg(reinterpret_cast<const int4*>(b + j) + lane);
+        const longlong2 x0 = __ldg(reinterpret_cast<const longlong2*>(a + j) + 2 * lane);
+        const longlong2 x1 = __ldg(reinterpret_cast<const longlong2*>(a + j) + 2 * lane + 1);
+        if (y.x == INT_MIN || y.y == INT_MIN || y.z == INT_MIN || y.w == INT_MIN) bad = 1;
+        acc(x0.x, y.x);
+        acc(x0.y, y.y);
+        acc(x1.x, y.z);
+        acc(x1.y, y.w);
+      }
+    }
+    for (int jj = j + lane; jj < p.W; jj += 32) {
+      const int y = __ldg(b + jj);
+      if (y == INT_MIN) bad = 1;
+      acc(__ldg(a + jj), y);
+    }
+  } else {
+    const long long* b = b_row(p, g, l, i);
+    int j = 0;
+    if ((p.W & 1) == 0 && ((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0) {
+      const int pairs = p.W >> 1;
+      for (; j + 64 <= pairs; j += 64) {
+        const longlong2 x0 = __ldg(reinterpret_cast<const longlong2*>(a) + j + lane);
+        const longlong2 y0 = __ldg(reinterpret_cast<const longlong2*>(b) + j + lane);
+        const longlong2 x1 = __ldg(reinterpret_cast<const longlong2*>(a) + j + 32 + lane);
+        const longlong2 y1 = __ldg(reinterpret_cast<const longlong2*>(b) + j + 32 + lane);
+        acc(x0.x, y0.x);
+        acc(x0.y, y0.y);
+        acc(x1.x, y1.x);
+        acc(x1.y, y1.y);
+      }
+      j *= 2;
+    }
+    for (int jj = j + lane; jj < p.W; jj += 32) acc(__ldg(a + jj), __ldg(b + jj));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    aa += __shfl_xor_sync(0xffffffffu, aa, o);
+    bb += __shfl_xor_sync(0xffffffffu, bb, o);
+    ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    const unsigned long long oa = __shfl_xor_sync(0xffffffffu, amax, o), ob = __shfl_xor_sync(0xffffffffu, bmax, o);
+    amax = oa > amax ? oa : amax;
+    bmax = ob > bmax ? ob : bmax;
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  const double big = (double)(amax > bmax ? amax : bmax);
+  va = (double)aa;
+  vb = (double)bb;
+  vab = (double)ab;
+  return !bad && big * big * (double)p.W < TWO53 * 0.5;
+}
+
+// one CTA per flagged row: collect the listed columns, re-score them exactly, order, write the top-k
+__global__ void __launch_bounds__(256) k_band_finish(const RescoreParams p, const BandParams bp) {
+  __shared__ uint32_t s_id[BAND_MAX];
+  __shared__ double s_val[BAND_MAX];
+  __shared__ int s_n, s_bad;
+  const int r2 = blockIdx.x;
+  const long long r = bp.flagged[r2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    s_n = 0;
+    s_bad = bp.band_overflow[r2] ? 1 : 0;
+  }
+  __syncthreads();
+  const int m = r2 / BM, rr = r2 % BM;
+  for (int s = bp.slot_ptr[m]; s < bp.slot_ptr[m + 1]; s++) {
+    const int w = bp.slot_of[s];
+    for (int h = 0; h < 2; h++) {
+      const size_t slot = ((size_t)w * 2 + h) * BM + rr;
+      const int n = bp.list_cnt[slot];
+      const uint2* list = bp.lists + slot * CAP;
+      for (int e = tid; e < n; e += blockDim.x) {
+        const int at = atomicAdd(&s_n, 1);
+        if (at < BAND_MAX) s_id[at] = __ldcg(list + e).y;
+      }
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > BAND_MAX || s_bad) {
+    // a tie group (or a row of near-equal similarities) too large to settle here: the exact full-row path
+    if (tid == 0) p.row_flag[r] = 2;
+    return;
+  }
+  const long long* arow = p.a_counters + (size_t)r * p.d * p.W;
+  for (int c = warp; c < n; c += 8) {
+    long long g, l;
+    b_locate(p, s_id[c], g, l);
+    double mn = JAVA_MAX_DOUBLE;
+    for (int i = 0; i < p.d; i++) {
+      double va, vb, vab;
+      if (!pair_sums_exact(p, arow + (size_t)i * p.W, g, l, i, lane, va, vb, vab)) s_bad = 1;
+      const double den = __dmul_rn(sqrt(va), sqrt(vb));
+      if (den != 0.0) {
+        const double cs = __ddiv_rn(vab, den);
+        mn = cs < mn ? cs : mn;
+      }
+    }
+    // admitted iff not NaN (no comparable row), >= threshold and > Double.MIN_VALUE
+    if (lane == 0) s_val[c] = (mn != JAVA_MAX_DOUBLE && mn >= p.threshold && mn > 4.9e-324) ? mn : -INFINITY;
+  }
+  for (int c = n + tid; c < BAND_MAX; c += blockDim.x) {
+    s_val[c] = -INFINITY;
+    s_id[c] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) p.row_flag[r] = 2;
+    return;
+  }
+  // bitonic sort of the power of two that covers n, order (similarity desc, index asc)
+  int np2 = 32;
+  while (np2 < n) np2 <<= 1;
+  for (int kk = 2; kk <= np2; kk <<= 1) {
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      for (int e = tid; e < np2; e += blockDim.x) {
+        const int o = e ^ jj;
+        if (o > e) {
+          const bool desc = (e & kk) == 0;
+          const double ve = s_val[e], vo = s_val[o];
+          const uint32_t ie = s_id[e], io = s_id[o];
+          const bool e_first = ve > vo || (ve == vo && ie <= io);
+          if (e_first != desc) {
+            s_val[e] = vo;
+            s_val[o] = ve;
+            s_id[e] = io;
+            s_id[o] = ie;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  int admitted = 0;
+  for (int e = tid; e < p.k; e += blockDim.x) {
+    const bool ok = e < np2 && s_val[e] > -INFINITY;
+    p.out_idx[(size_t)r * p.k + e] = ok ? (long long)s_id[e] : -1LL;
+    p.out_sim[(size_t)r * p.k + e] = ok ? s_val[e] : 0.0;
+    admitted += ok ? 1 : 0;
+  }
+  // count of admitted results = number of finite values among the first k
+  __shared__ int s_adm;
+  if (tid == 0) s_adm = 0;
+  __syncthreads();
+  if (admitted) atomicAdd(&s_adm, admitted);
+  __syncthreads();
+  if (tid == 0) {
+    p.out_cnt[r] = s_adm;
+    p.row_flag[r] = 0;
+  }
+}
+
+// rows whose flag equals `want` (want == 0: any non-zero flag)
+__global__ void k_collect_flagged(const int32_t* row_flag, long long n, int32_t* flagged, int32_t* count, int want) {
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n && row_flag[r]) flagged[atomicAdd(count, 1)] = (int32_t)r;
+  if (r < n && (want ? row_flag[r] == want : row_flag[r] != 0)) flagged[atomicAdd(count, 1)] = (int32_t)r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1705,6 +1951,12 @@ extern "C" {
 
 int64_t mb200_row_ld(int32_t width) { return ((int64_t)width + BK - 1) / BK * BK; }
 int64_t mb200_valid_words(int64_t rows) { return (rows + 255) / 256 * 8; }
+
+int mb200_cosine_last_band_rows(mb200_ctx* ctx, int64_t* rows) {
+  if (!ctx || !rows) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_last_band_rows: NULL argument");
+  *rows = ctx->last_band_rows;
+  return MB200_OK;
+}
 
 int mb200_cosine_last_fallback_rows(mb200_ctx* ctx, int64_t* rows) {
   if (!ctx || !rows) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_last_fallback_rows: NULL argument");
@@ -1787,6 +2039,11 @@ struct mb200_cosine_job {
   bool pending = false;                      // lists of the last push not merged yet
   MergeParams mp;                            // ... described here (context workspace memory)
   int pushes = 0;
+  mb200_cosine_piece last_piece;             // the piece of the last push (re-swept by the band pass of a one-push job)
+  // band job (internal, see job_band_pass): compact A rows with explicit ids and fixed per-row cuts
+  const uint32_t* band_ids = nullptr;
+  const float* band_cut = nullptr;
+  uint32_t* band_overflow = nullptr;
   size_t ws_state = 0;                       // workspace slots of row_thr, best, best_bound
   size_t ws_base = 0, ws_next = 0;           // workspace slots [ws_base, ws_next) belong to the pending push
 };
@@ -1824,7 +2081,9 @@ static int job_begin_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t w
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: block_n must be 0, 128 or 256");
   const bool rescored = a->precision != MB200_PRECISION_TENSOR;
   // candidates kept per row: k + margin, at most CAP - 64
-  const int margin = rescored ? std::max(14, a->k / 4) : 0;
+  // re-scoring margin: the more candidates beyond k, the more often the k-th value clears what was dropped (rows
+  // that do not certify cost a band pass)
+  const int margin = rescored ? std::max(14, a->k >= 64 ? a->k / 2 : a->k / 4) : 0;
   int ksel = (a->k + margin + 31) / 32 * 32;
   if (ksel > CAP - 64) ksel = CAP - 64;
   if (a->k > ksel)
@@ -2110,6 +2369,9 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
     if (thr > 0.0 || abs_slack > 0.0) p.thr_init = nextafterf(p.thr_init, -INFINITY);
   }
   p.ksel = j->ksel;
+  p.a_ids = j->band_ids;
+  p.row_cut = j->band_cut;
+  p.band_overflow = j->band_overflow;
   p.lists = (uint2*)d_lists.p;
   p.list_cnt = (int32_t*)d_cnt.p;
   p.list_bound = (float*)d_bound.p;
@@ -2157,6 +2419,83 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   mp.rescored = j->rescored ? 1 : 0;
   j->pending = true;
   j->pushes++;
+  j->last_piece = *pc;
+  return MB200_OK;
+}
+
+// The band pass of a one-push job (see k_band_gather): `flagged` lists nband rows of the job whose row_cut is set.
+static int job_band_pass(mb200_cosine_job* j, const mb200_cosine_args* fin, const RescoreParams& rp, const int32_t* flagged,
+                         int nband, Workspace& ws) {
+  mb200_ctx* ctx = j->ctx;
+  const mb200_cosine_args* a = &j->a;
+  const int ld = j->ld;
+  const int batch_max = 16384;  // rows per sweep: bounds the compact operand and the list workspace
+  const size_t ws_mark = ws.next;
+  for (int off = 0; off < nband; off += batch_max) {
+    const int nf = std::min(batch_max, nband - off);
+    ws.next = ws_mark;
+    const int64_t nf_vw = mb200_valid_words(nf);
+    const int num_m = (nf + BM - 1) / BM;
+    DevBuf d_arows, d_avalid, d_ids, d_cut, d_over, d_thr;
+    MB_CHECK(d_arows.alloc(ws, (size_t)a->depth * nf * ld * 2));
+    MB_CHECK(d_avalid.alloc(ws, (size_t)a->depth * nf_vw * sizeof(uint32_t)));
+    MB_CHECK(d_ids.alloc(ws, (size_t)nf * sizeof(uint32_t)));
+    MB_CHECK(d_cut.alloc(ws, (size_t)num_m * BM * sizeof(float)));
+    MB_CHECK(d_over.alloc(ws, (size_t)num_m * BM * sizeof(uint32_t)));
+    MB_CHECK(d_thr.alloc(ws, (size_t)num_m * BM * sizeof(uint32_t)));
+    MB_CUDA(ctx, cudaMemsetAsync(d_avalid.p, 0, (size_t)a->depth * nf_vw * sizeof(uint32_t), ctx->stream));
+    MB_CUDA(ctx, cudaMemsetAsync(d_over.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
+    MB_CUDA(ctx, cudaMemsetAsync(d_thr.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
+    k_band_gather<<<nf, 256, 0, ctx->stream>>>((const uint16_t*)a->a_rows, a->a_valid, a->a_count, mb200_valid_words(a->a_count),
+                                               a->depth, ld, flagged + off, nf, nf_vw, (uint32_t)a->a_id_mul,
+                                               (uint32_t)a->a_id_off, rp.row_cut, (uint16_t*)d_arows.p, (uint32_t*)d_avalid.p,
+                                               (uint32_t*)d_ids.p, (float*)d_cut.p);
+    ctx->launches++;
+    // a job of its own over the compact rows: same planner, same K3, band mode
+    mb200_cosine_job bj;
+    bj.ctx = ctx;
+    bj.a = *a;
+    bj.a.a_rows = d_arows.p;
+    bj.a.a_valid = (const uint32_t*)d_avalid.p;
+    bj.a.a_count = nf;
+    bj.a.dense_out = nullptr;
+    bj.rescored = j->rescored;
+    bj.certified = j->certified;
+    bj.ksel = j->ksel;
+    bj.BN = j->BN;
+    bj.num_m = num_m;
+    bj.ld = ld;
+    bj.scale2 = j->scale2;
+    bj.eps_rel = j->eps_rel;
+    bj.row_thr = (uint32_t*)d_thr.p;
+    bj.band_ids = (const uint32_t*)d_ids.p;
+    bj.band_cut = (const float*)d_cut.p;
+    bj.band_overflow = (uint32_t*)d_over.p;
+    bj.ws_base = bj.ws_next = ws.next;
+    mb200_cosine_piece pc = j->last_piece;
+    pc.b_rows = fin->b_rows;
+    pc.b_valid = fin->b_valid;
+    pc.ready_flags = nullptr;  // every block of a pull-gather has landed by now
+    pc.ready_epoch = 0;
+    pc.first_block = 0;
+    MB_CHECK(job_push_locked(&bj, &pc));
+    BandParams bp;
+    bp.lists = bj.mp.lists;
+    bp.list_cnt = bj.mp.list_cnt;
+    bp.slot_ptr = bj.mp.slot_ptr;
+    bp.slot_of = bj.mp.slot_of;
+    bp.band_overflow = (const uint32_t*)d_over.p;
+    bp.flagged = flagged + off;
+    bp.nf = nf;
+    {
+      ProfScope prof(ctx, MB200_K_RESCORE);
+      k_band_finish<<<nf, 256, 0, ctx->stream>>>(rp, bp);
+    }
+    ctx->launches++;
+    MB_CUDA(ctx, cudaGetLastError());
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the batch's workspace is reused by the next one
+    ws.next = std::max(ws.next, bj.ws_next);
+  }
   return MB200_OK;
 }
 
@@ -2192,13 +2531,14 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
   const int64_t total_b = fin->b_count * fin->b_blocks;
 
   // merge (+ re-score)
-  DevBuf d_cand, d_ccnt, d_cbound, d_flag, d_fcount, d_cval;
+  DevBuf d_cand, d_ccnt, d_cbound, d_flag, d_fcount, d_cval, d_rcut;
   if (rescored) {
     MB_CHECK(d_cand.alloc(ws, (size_t)a->a_count * CAP * sizeof(uint32_t)));
     MB_CHECK(d_ccnt.alloc(ws, (size_t)a->a_count * sizeof(int32_t)));
     MB_CHECK(d_cbound.alloc(ws, (size_t)a->a_count * sizeof(float)));
     MB_CHECK(d_flag.alloc(ws, (size_t)a->a_count * sizeof(int32_t)));
     MB_CHECK(d_fcount.alloc(ws, 2 * sizeof(int32_t)));
+    MB_CHECK(d_rcut.alloc(ws, (size_t)a->a_count * sizeof(float)));
     MB_CHECK(d_cval.alloc(ws, j->certified ? (size_t)a->a_count * CAP * sizeof(float) : 4));
     MB_CUDA(ctx, cudaMemsetAsync(d_fcount.p, 0, 2 * sizeof(int32_t), ctx->stream));
     j->mp.cand_val = j->certified ? (float*)d_cval.p : nullptr;
@@ -2255,6 +2595,12 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       rp.out_cnt = fin->out_cnt;
       rp.row_flag = (int32_t*)d_flag.p;
       rp.flag_count = (int32_t*)d_fcount.p;
+      rp.row_cut = (float*)d_rcut.p;
+      {
+        const double thr = a->threshold > 0.0 ? a->threshold : 0.0;
+        const double abs_slack = a->mixed_sign ? (double)j->eps_rel : 0.0;
+        rp.thr_floor = (float)((thr * (1.0 - (double)j->eps_rel) - abs_slack) * (double)j->scale2);
+      }
       rp.cand_val = mp.cand_val;
       if (j->certified) {
         k_certify<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp);
@@ -2323,34 +2669,61 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       MB_CUDA(ctx, cudaMemcpyAsync(&nflag, d_fcount.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       TRACE("rescore");
-      ctx->last_fallback_rows = nflag;
-      ctx->stat_fallback += nflag;
-      if (ctx->max_fallback_rows >= 0 && nflag > ctx->max_fallback_rows)
-        return mb200_fail(ctx, MB200_ERR_UNSUPPORTED,
-                          "%d rows cannot be certified from their candidate lists and would take the exact full-row path "
-                          "(limit MB200_OPT_MAX_FALLBACK_ROWS = %lld)", nflag, (long long)ctx->max_fallback_rows);
+      ctx->last_band_rows = 0;
+      ctx->last_fallback_rows = 0;
       if (nflag > 0) {
-        // exact full-row path, in batches bounded by scratch memory
         rp.b_id_add = (uint32_t)fin->b_id_add;  // forward mapping for k_exact_*
-        DevBuf d_rows, d_scratch;
+        DevBuf d_rows;
         MB_CHECK(d_rows.alloc(ws, (size_t)nflag * sizeof(int32_t)));
-        k_collect_flagged<<<(unsigned)((a->a_count + 255) / 256), 256, 0, ctx->stream>>>(
-            rp.row_flag, a->a_count, (int32_t*)d_rows.p, rp.flag_count + 1);
+        int32_t* d_count = rp.flag_count + 1;
+        // ---- band pass: rows that are merely uncertified get a second, targeted K3 sweep (the B side of a
+        // one-push job is still where the push found it when the caller says so by passing it again)
+        const bool can_band = j->pushes == 1 && fin->b_rows != nullptr && fin->b_valid != nullptr && j->band_cut == nullptr &&
+                              getenv("MB200_NO_BAND") == nullptr;
+        if (can_band) {
+          MB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int32_t), ctx->stream));
+          k_collect_flagged<<<(unsigned)((a->a_count + 255) / 256), 256, 0, ctx->stream>>>(rp.row_flag, a->a_count,
+                                                                                       (int32_t*)d_rows.p, d_count, 1);
+          int32_t nband = 0;
+          MB_CUDA(ctx, cudaMemcpyAsync(&nband, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+          MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+          ctx->launches++;
+          if (nband > 0) MB_CHECK(job_band_pass(j, fin, rp, (const int32_t*)d_rows.p, nband, ws));
+          ctx->last_band_rows = nband;
+          ctx->stat_band += nband;
+        }
+        // ---- exact full-row path: rows outside the exact-integer range, band lists that overflowed, and every
+        // flagged row when no band pass was possible
+        MB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int32_t), ctx->stream));
+        k_collect_flagged<<<(unsigned)((a->a_count + 255) / 256), 256, 0, ctx->stream>>>(rp.row_flag, a->a_count,
+                                                                                     (int32_t*)d_rows.p, d_count, can_band ? 2 : 0);
         ctx->launches++;
-        const int batch = (int)std::max<int64_t>(1, std::min<int64_t>(nflag, (1LL << 30) / (total_b * 8)));
-        MB_CHECK(d_scratch.alloc(ws, (size_t)batch * total_b * sizeof(double)));
-        for (int off = 0; off < nflag; off += batch) {
-          const int m = std::min(batch, nflag - off);
-          if (getenv("MB200_EXACT_ROWS_SEQ") != nullptr) {  // the loop-for-loop form, kept for cross-checks
-            k_exact_rows<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, 1.0, 1.0, (double*)d_scratch.p, total_b);
-          } else {
-            dim3 grid((unsigned)m, (unsigned)((total_b + EXACT_COLS - 1) / EXACT_COLS));
-            k_exact_rows_fast<<<grid, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (double*)d_scratch.p, total_b);
+        int32_t nexact = 0;
+        MB_CUDA(ctx, cudaMemcpyAsync(&nexact, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->last_fallback_rows = nexact;
+        ctx->stat_fallback += nexact;
+        if (ctx->max_fallback_rows >= 0 && nexact > ctx->max_fallback_rows)
+          return mb200_fail(ctx, MB200_ERR_UNSUPPORTED,
+                            "%d rows cannot be certified from their candidate lists and would take the exact full-row path "
+                            "(limit MB200_OPT_MAX_FALLBACK_ROWS = %lld)", nexact, (long long)ctx->max_fallback_rows);
+        if (nexact > 0) {
+          DevBuf d_scratch;
+          const int batch = (int)std::max<int64_t>(1, std::min<int64_t>(nexact, (1LL << 30) / (total_b * 8)));
+          MB_CHECK(d_scratch.alloc(ws, (size_t)batch * total_b * sizeof(double)));
+          for (int off = 0; off < nexact; off += batch) {
+            const int m = std::min(batch, nexact - off);
+            if (getenv("MB200_EXACT_ROWS_SEQ") != nullptr) {  // the loop-for-loop form, kept for cross-checks
+              k_exact_rows<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, 1.0, 1.0, (double*)d_scratch.p, total_b);
+            } else {
+              dim3 grid((unsigned)m, (unsigned)((total_b + EXACT_COLS - 1) / EXACT_COLS));
+              k_exact_rows_fast<<<grid, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (double*)d_scratch.p, total_b);
+            }
+            k_exact_topk<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (const double*)d_scratch.p, total_b,
+                                                     a->exclude_self ? 1 : 0);
+            ctx->launches += 2;
+            MB_CUDA(ctx, cudaGetLastError());
           }
-          k_exact_topk<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (const double*)d_scratch.p, total_b,
-                                                   a->exclude_self ? 1 : 0);
-          ctx->launches += 2;
-          MB_CUDA(ctx, cudaGetLastError());
         }
       }
     }

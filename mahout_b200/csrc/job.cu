@@ -260,6 +260,8 @@ void worker(Shared& sh, int g) {
         fin.out_idx = (int64_t*)o_idx;
         fin.out_sim = (double*)o_sim;
         fin.out_cnt = (int32_t*)o_cnt;
+        fin.b_rows = staging;  // still resident: uncertified rows may take the band pass
+        fin.b_valid = (const uint32_t*)staging_v;
         if (P.precision != MB200_PRECISION_TENSOR) {
           fin.a_counters = (const int64_t*)sh.counters[g];
           fin.b_blocks = G;

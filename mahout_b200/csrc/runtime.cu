@@ -162,6 +162,7 @@ int mb200_get_stats(mb200_ctx* ctx, mb200_stats* out) {
   out->events_updated = ctx->stat_events;
   out->rows_scored = ctx->stat_rows;
   out->fallback_rows_total = ctx->stat_fallback;
+  out->band_rows_total = ctx->stat_band;
   out->h2d_bytes = ctx->stat_h2d;
   out->d2h_bytes = ctx->stat_d2h;
   cudaDeviceProp prop;

@@ -607,6 +607,7 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
         job.push(peers.staging_rows, peers.staging_valid, id_mul=G, id_add=1, ready=ready, first_block=plan.rank)
         if precision != "tensor":
             res = job.finish(a_counters=a_counters, b_counters=b_counters, b_id=(G, 1), out=out,
+                             resident_b=(peers.staging_rows, peers.staging_valid),
                              counter_blocks=counter_blocks, b_count=plan.rows_per_shard,
                              counter_blocks32=getattr(peers, "counter_blocks32", None) if counter_blocks is not None
                              else None)

@@ -531,7 +531,7 @@ class CosineJob:
         N.check(N.lib().mb200_cosine_push(self._h, C.byref(pc)), self.ctx.handle)
 
     def finish(self, a_counters=None, b_counters=None, b_id=(1, 0), out=None, counter_blocks=None, b_count=None,
-               counter_blocks32=None):
+               counter_blocks32=None, resident_b=None):
         """Returns (idx, sim, cnt) device tensors.  precision="rescored" / "certified" need the resident
         counters: a_counters [a_count, d, w], b_counters [blocks, b_count, d, w] with b_id = (id_mul, id_add);
         "certified" alternatively takes counter_blocks, a ctypes array of one device pointer per block
@@ -545,6 +545,9 @@ class CosineJob:
         idx, sim, cnt = out
         fin = N.CosineArgs()
         fin.out_idx, fin.out_sim, fin.out_cnt = idx.data_ptr(), sim.data_ptr(), cnt.data_ptr()
+        if resident_b is not None:
+            # the (single) pushed piece is still where the push found it: uncertified rows may take the band pass
+            fin.b_rows, fin.b_valid = resident_b[0].data_ptr(), resident_b[1].data_ptr()
         if a_counters is not None:
             fin.a_counters = a_counters.data_ptr()
             if counter_blocks is not None:
@@ -568,6 +571,12 @@ class CosineJob:
             self._keep = []
 
     __del__ = abort
+
+
+def last_band_rows(ctx: Context) -> int:
+    n = C.c_int64()
+    N.check(N.lib().mb200_cosine_last_band_rows(ctx.handle, C.byref(n)), ctx.handle)
+    return n.value
 
 
 def last_fallback_rows(ctx: Context) -> int:

@@ -392,7 +392,7 @@ def test_boolean_data_tie_groups_take_the_exact_path(mb, ctx, precision, monkeyp
     candidates tie exactly at the k-th value and the candidate lists cannot certify their rows -- they take the exact
     full-row path (k_exact_rows_fast + k_exact_topk).  Ties are broken by index, as in the oracle; the memory-speed
     integer form and the loop-for-loop FP64 form (MB200_EXACT_ROWS_SEQ) of that path must give the same answer."""
-    from mahout_b200.sketch import last_fallback_rows
+    from mahout_b200.sketch import last_band_rows, last_fallback_rows
     rng = np.random.Generator(np.random.PCG64(12))
     E, d, w, k = 900, 2, 256, 10
     users = 40
@@ -404,23 +404,30 @@ def test_boolean_data_tie_groups_take_the_exact_path(mb, ctx, precision, monkeyp
     orc.bank_update(ref, d, w, a, b, item, user, pref)
     oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
     results = []
-    for seq in (False, True):
-        if seq:
-            monkeypatch.setenv("MB200_EXACT_ROWS_SEQ", "1")
-        else:
-            monkeypatch.delenv("MB200_EXACT_ROWS_SEQ", raising=False)
+    # (band pass on: uncertified rows are settled by a second targeted sweep), (band pass off: they all take the exact
+    # full-row path, memory-speed form), (the same through the loop-for-loop FP64 form)
+    for band, seq in ((True, False), (False, False), (False, True)):
+        for name, on in (("MB200_NO_BAND", not band), ("MB200_EXACT_ROWS_SEQ", seq)):
+            if on:
+                monkeypatch.setenv(name, "1")
+            else:
+                monkeypatch.delenv(name, raising=False)
         bank = mb.SketchBank(E, w, d, 42, 1, ctx)
         bank.update(item, user, pref)
         idx, sim, cnt = bank.cosine_topk(k, precision=precision)
-        fb = last_fallback_rows(ctx)
+        fb, bd = last_fallback_rows(ctx), last_band_rows(ctx)
         bank.close()
-        assert fb > 0, "the tie groups were expected to defeat certification"
+        assert fb + bd > 0, "the tie groups were expected to defeat certification"
+        assert (bd > 0) == band, (fb, bd)
         assert (cnt == ocnt).all()
         assert (idx == oidx).all(), f"{(idx != oidx).sum()} index mismatches (fallback rows {fb})"
         if precision == "rescored":
             assert sim.tobytes() == osim.tobytes()
         results.append((idx, sim))
-    assert (results[0][0] == results[1][0]).all() and results[0][1].tobytes() == results[1][1].tobytes()
+    for other in results[1:]:
+        assert (results[0][0] == other[0]).all()
+        if precision == "rescored":
+            assert results[0][1].tobytes() == other[1].tobytes()
 
 
 @pytest.mark.parametrize("dtype,k", [("bf16", 20), ("f16", 192), ("bf16", 192)])
@@ -440,4 +447,37 @@ def test_bf16_rows_and_largest_k_keep_the_exact_contract(mb, ctx, dtype, k):
     assert last_fallback_rows(ctx) <= E
     with pytest.raises(mb.NativeError):
         bank.cosine_topk(193)                         # beyond the fused capacity: refused, never truncated
+    bank.close()
+
+
+@pytest.mark.parametrize("precision", ["certified", "rescored"])
+def test_band_pass_settles_flat_similarity_rows(mb, ctx, precision):
+    """Rows whose similarities are nearly flat around the k-th value (few distinct users, coarse sketches, BF16 rows:
+    the undecided band is wider than the candidate margin) cannot be certified from their lists; the band pass --
+    a second K3 sweep over those rows with a fixed cut, every column above it re-scored exactly -- must return the
+    oracle's answer without falling back to the exact full-row path."""
+    from mahout_b200.sketch import last_band_rows, last_fallback_rows
+    rng = np.random.Generator(np.random.PCG64(5))
+    E, d, w, k = 3000, 2, 128, 100
+    n = 60 * E
+    item = rng.integers(0, E, n).astype(np.int64)
+    user = rng.integers(1, 300, n).astype(np.int64)
+    pref = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
+    bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+    bank.update(item, user, pref)
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((E, d, w))
+    orc.bank_update(ref, d, w, a, b, item, user, pref)
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    idx, sim, cnt = bank.cosine_topk(k, dtype="bf16", precision=precision)
+    bd, fb = last_band_rows(ctx), last_fallback_rows(ctx)
+    assert bd > 0, "expected uncertified rows on this data"
+    assert fb == 0, (bd, fb)
+    assert (cnt == ocnt).all()
+    if precision == "rescored":
+        assert (idx == oidx).all() and sim.tobytes() == osim.tobytes()
+    else:
+        assert all(set(idx[r, :cnt[r]].tolist()) == set(oidx[r, :ocnt[r]].tolist()) for r in range(E))
+    st = ctx.stats()
+    assert st["band_rows_total"] >= bd
     bank.close()
