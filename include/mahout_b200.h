@@ -25,6 +25,7 @@ extern "C" {
  * DoubleCountMinSketch.java:117-118), CM_* -> AbstractCountMinSketch.CMException
  * (AbstractCountMinSketch.java:21-27,71-76), everything else -> TasteException / IOException. */
 #define MB200_OK 0
+#define MB200_BAND_PENDING 1     /* mb200_cosine_finish: not an error -- see mb200_cosine_args.defer_uncertified */
 #define MB200_ERR_BAD_ARG (-1)
 #define MB200_ERR_CUDA (-2)
 #define MB200_ERR_OOM (-3)
@@ -350,6 +351,12 @@ typedef struct mb200_cosine_args {
    * admission threshold, certification bound and undecided band accordingly.  mb200_bank_cosine_topk
    * sets it by itself. */
   int32_t mixed_sign;
+  /* mb200_cosine_finish of a job whose B side was STREAMED (several pushes; the pieces are gone): instead of sending
+   * the uncertified rows through the exact full-row path, return MB200_BAND_PENDING and keep the job alive.  The
+   * caller then pushes the same pieces once more -- K3 sweeps them for those rows only, with the fixed per-row cuts
+   * -- and calls mb200_cosine_finish again (its arguments are ignored the second time), which completes the band
+   * pass.  mb200_cosine_last_band_rows tells how many rows are waiting. */
+  int32_t defer_uncertified;
 } mb200_cosine_args;
 
 int mb200_cosine_topk(mb200_ctx* ctx, const mb200_cosine_args* args);

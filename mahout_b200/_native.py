@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmahout_b200.so")
 
 OK = 0
+BAND_PENDING = 1
 ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_INEXACT, ERR_RANGE = -1, -2, -3, -4, -5
 ERR_NO_DEVICE, ERR_CM_DELTA, ERR_CM_EPSILON, ERR_UNSUPPORTED = -6, -7, -8, -9
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -53,6 +54,7 @@ class CosineArgs(C.Structure):
         ("out_idx", C.c_void_p), ("out_sim", C.c_void_p), ("out_cnt", C.c_void_p),
         ("dense_out", C.c_void_p), ("dense_ld", C.c_int64),
         ("b_counter_blocks", C.c_void_p), ("b_counter_blocks32", C.c_void_p), ("mixed_sign", C.c_int32),
+        ("defer_uncertified", C.c_int32),
     ]
 
 

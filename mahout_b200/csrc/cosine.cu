@@ -37,6 +37,7 @@ using namespace tc05;
 // ------------------------------------------------------------------------------------------------
 static constexpr int BM = 128;            // rows of A per tile (TMEM lanes)
 static constexpr int BK = 64;             // K elements per pipeline stage (one 128-byte swizzle row)
+static constexpr int BAND_MAX = 2048;      // columns above the cut the band pass can re-score per row
 static constexpr int CAP = 256;           // candidate-list capacity per (row, column chunk, half)
 static constexpr int COS_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 static constexpr float F16_SCALE = 4096.0f;  // rows are stored as x/||x|| * 2^12 in FP16
@@ -74,10 +75,12 @@ struct CosParams {
   // band pass (second chance of rows the candidate lists could not certify): the A rows are a compact copy of
   // those rows, a_ids[row] is the row's global index, row_cut[row] the fixed admission threshold (scaled tensor
   // value) below which a column is provably outside the row's top-k; every column above it is LISTED -- no
-  // selection, no threshold raising; a list that fills up marks band_overflow[row]
+  // selection, no threshold raising, no lists: straight into the row's candidate buffer band_cand[row][BAND_MAX]
+  // through the cursor band_cnt[row] (a count beyond BAND_MAX sends the row to the exact full-row path)
   const uint32_t* a_ids;
   const float* row_cut;
-  uint32_t* band_overflow;
+  uint32_t* band_cand;
+  int32_t* band_cnt;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -505,6 +508,20 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
               for (int j = 0; j < 32; j++) dst[j] = __uint_as_float(v[j]) * p.inv_scale2;
             }
             const uint32_t id0 = (uint32_t)(l0 + c * 32) * p.b_id_mul + (uint32_t)g * p.b_id_add + p.b_id_base;
+            if (band) {
+              if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                  const float x = __uint_as_float(v[j]);
+                  const uint32_t id = id0 + (uint32_t)j * p.b_id_mul;
+                  if (x > thr && id != my_id) {
+                    const int at = atomicAdd(p.band_cnt + grow, 1);
+                    if (at < BAND_MAX) p.band_cand[(size_t)grow * BAND_MAX + at] = id;
+                  }
+                }
+              }
+              return;
+            }
 #pragma unroll
             for (int j = 0; j < 32; j++) {
               const float x = __uint_as_float(v[j]);
@@ -515,15 +532,6 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                   cnt++;
                 }
               }
-            }
-            if (band) {
-              // everything above the cut is wanted: a list that cannot take another chunk gives up (the row then
-              // goes through the exact full-row path)
-              if (cnt > CAP - 32) {
-                p.band_overflow[grow] = 1u;
-                thr = INFINITY;
-              }
-              return;
             }
             // keep 32 free slots for the next chunk; raise the threshold early once so that the
             // other lists of the row can use it.  Threshold raises are warp-cooperative.
@@ -1691,15 +1699,11 @@ __global__ void __launch_bounds__(256) k_band_gather(const uint16_t* __restrict_
   }
 }
 
-static constexpr int BAND_MAX = 2048;  // candidates per row the band pass can re-score
 
 struct BandParams {
-  const uint2* lists;
-  const int32_t* list_cnt;
-  const int32_t* slot_ptr;
-  const int32_t* slot_of;
-  const uint32_t* band_overflow;
   const int32_t* flagged;   // compact row -> row of the job
+  const uint32_t* cand;     // [nf][BAND_MAX] column ids above the row's cut, all sweeps
+  const int32_t* cand_cnt;  // [nf]
   int nf;
 };
 
@@ -1782,23 +1786,11 @@ __global__ void __launch_bounds__(256) k_band_finish(const RescoreParams p, cons
   const long long r = bp.flagged[r2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    s_n = 0;
-    s_bad = bp.band_overflow[r2] ? 1 : 0;
+    s_n = bp.cand_cnt[r2];
+    s_bad = 0;
   }
   __syncthreads();
-  const int m = r2 / BM, rr = r2 % BM;
-  for (int s = bp.slot_ptr[m]; s < bp.slot_ptr[m + 1]; s++) {
-    const int w = bp.slot_of[s];
-    for (int h = 0; h < 2; h++) {
-      const size_t slot = ((size_t)w * 2 + h) * BM + rr;
-      const int n = bp.list_cnt[slot];
-      const uint2* list = bp.lists + slot * CAP;
-      for (int e = tid; e < n; e += blockDim.x) {
-        const int at = atomicAdd(&s_n, 1);
-        if (at < BAND_MAX) s_id[at] = __ldcg(list + e).y;
-      }
-    }
-  }
+  for (int e = tid; e < s_n && e < BAND_MAX; e += blockDim.x) s_id[e] = bp.cand[(size_t)r2 * BAND_MAX + e];
   __syncthreads();
   const int n = s_n;
   if (n > BAND_MAX || s_bad) {
@@ -2040,19 +2032,36 @@ struct mb200_cosine_job {
   MergeParams mp;                            // ... described here (context workspace memory)
   int pushes = 0;
   mb200_cosine_piece last_piece;             // the piece of the last push (re-swept by the band pass of a one-push job)
-  // band job (internal, see job_band_pass): compact A rows with explicit ids and fixed per-row cuts
+  // band job (see band_setup): compact A rows with explicit ids and fixed per-row cuts
   const uint32_t* band_ids = nullptr;
   const float* band_cut = nullptr;
-  uint32_t* band_overflow = nullptr;
+  uint32_t* band_cand = nullptr;
+  int32_t* band_cnt = nullptr;
+  // band phase of THIS job: after a finish that deferred its uncertified rows, pushes feed `band` and the next
+  // finish completes it
+  struct BandState* band = nullptr;
+  bool band_pending = false;
   size_t ws_state = 0;                       // workspace slots of row_thr, best, best_bound
   size_t ws_base = 0, ws_next = 0;           // workspace slots [ws_base, ws_next) belong to the pending push
 };
 
 // the job's own state lives in context workspace slots [ws_state, ws_state + 3) (cudaMalloc / cudaFree
 // per job cost up to hundreds of ms on a process holding tens of GB -- they synchronise the device)
+struct BandState {
+  mb200_cosine_job bj;        // the nested job over the compact rows
+  RescoreParams rp;           // counters, outputs, flags of the main job's finish
+  BandParams bp;
+  mb200_cosine_args fin;      // the finish arguments (outputs, counters) of the main job
+  int32_t* d_rows = nullptr;  // flagged rows
+  int nband = 0;
+  int64_t total_b = 0;
+  size_t ws_mark = 0;         // workspace slots from here on are free for the exact path
+};
+
 static void job_free(mb200_cosine_job* j) {
   if (!j) return;
   if (j->ctx->active_job == j) j->ctx->active_job = nullptr;
+  delete j->band;
   delete j;
 }
 
@@ -2371,7 +2380,8 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   p.ksel = j->ksel;
   p.a_ids = j->band_ids;
   p.row_cut = j->band_cut;
-  p.band_overflow = j->band_overflow;
+  p.band_cand = j->band_cand;
+  p.band_cnt = j->band_cnt;
   p.lists = (uint2*)d_lists.p;
   p.list_cnt = (int32_t*)d_cnt.p;
   p.list_bound = (float*)d_bound.p;
@@ -2423,79 +2433,141 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   return MB200_OK;
 }
 
-// The band pass of a one-push job (see k_band_gather): `flagged` lists nband rows of the job whose row_cut is set.
-static int job_band_pass(mb200_cosine_job* j, const mb200_cosine_args* fin, const RescoreParams& rp, const int32_t* flagged,
-                         int nband, Workspace& ws) {
+// Band pass, three steps (see k_band_gather).  setup: compact copy of the flagged rows + the nested job; push: one
+// K3 sweep of the nested job over a piece of the B side + collection of what it listed; complete: exact re-scoring,
+// ordering, output.  A one-push job whose piece is still resident runs all three inside its finish; a multi-push job
+// (streamed B side) that asked to defer gets them spread over a second round of pushes.
+static int band_setup(mb200_cosine_job* j, const mb200_cosine_args* fin, const RescoreParams& rp, const int32_t* flagged,
+                      int nband, Workspace& ws, int64_t total_b) {
   mb200_ctx* ctx = j->ctx;
   const mb200_cosine_args* a = &j->a;
-  const int ld = j->ld;
-  const int batch_max = 16384;  // rows per sweep: bounds the compact operand and the list workspace
-  const size_t ws_mark = ws.next;
-  for (int off = 0; off < nband; off += batch_max) {
-    const int nf = std::min(batch_max, nband - off);
-    ws.next = ws_mark;
-    const int64_t nf_vw = mb200_valid_words(nf);
-    const int num_m = (nf + BM - 1) / BM;
-    DevBuf d_arows, d_avalid, d_ids, d_cut, d_over, d_thr;
-    MB_CHECK(d_arows.alloc(ws, (size_t)a->depth * nf * ld * 2));
-    MB_CHECK(d_avalid.alloc(ws, (size_t)a->depth * nf_vw * sizeof(uint32_t)));
-    MB_CHECK(d_ids.alloc(ws, (size_t)nf * sizeof(uint32_t)));
-    MB_CHECK(d_cut.alloc(ws, (size_t)num_m * BM * sizeof(float)));
-    MB_CHECK(d_over.alloc(ws, (size_t)num_m * BM * sizeof(uint32_t)));
-    MB_CHECK(d_thr.alloc(ws, (size_t)num_m * BM * sizeof(uint32_t)));
-    MB_CUDA(ctx, cudaMemsetAsync(d_avalid.p, 0, (size_t)a->depth * nf_vw * sizeof(uint32_t), ctx->stream));
-    MB_CUDA(ctx, cudaMemsetAsync(d_over.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
-    MB_CUDA(ctx, cudaMemsetAsync(d_thr.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
-    k_band_gather<<<nf, 256, 0, ctx->stream>>>((const uint16_t*)a->a_rows, a->a_valid, a->a_count, mb200_valid_words(a->a_count),
-                                               a->depth, ld, flagged + off, nf, nf_vw, (uint32_t)a->a_id_mul,
-                                               (uint32_t)a->a_id_off, rp.row_cut, (uint16_t*)d_arows.p, (uint32_t*)d_avalid.p,
-                                               (uint32_t*)d_ids.p, (float*)d_cut.p);
-    ctx->launches++;
-    // a job of its own over the compact rows: same planner, same K3, band mode
-    mb200_cosine_job bj;
-    bj.ctx = ctx;
-    bj.a = *a;
-    bj.a.a_rows = d_arows.p;
-    bj.a.a_valid = (const uint32_t*)d_avalid.p;
-    bj.a.a_count = nf;
-    bj.a.dense_out = nullptr;
-    bj.rescored = j->rescored;
-    bj.certified = j->certified;
-    bj.ksel = j->ksel;
-    bj.BN = j->BN;
-    bj.num_m = num_m;
-    bj.ld = ld;
-    bj.scale2 = j->scale2;
-    bj.eps_rel = j->eps_rel;
-    bj.row_thr = (uint32_t*)d_thr.p;
-    bj.band_ids = (const uint32_t*)d_ids.p;
-    bj.band_cut = (const float*)d_cut.p;
-    bj.band_overflow = (uint32_t*)d_over.p;
-    bj.ws_base = bj.ws_next = ws.next;
-    mb200_cosine_piece pc = j->last_piece;
-    pc.b_rows = fin->b_rows;
-    pc.b_valid = fin->b_valid;
-    pc.ready_flags = nullptr;  // every block of a pull-gather has landed by now
-    pc.ready_epoch = 0;
-    pc.first_block = 0;
-    MB_CHECK(job_push_locked(&bj, &pc));
-    BandParams bp;
-    bp.lists = bj.mp.lists;
-    bp.list_cnt = bj.mp.list_cnt;
-    bp.slot_ptr = bj.mp.slot_ptr;
-    bp.slot_of = bj.mp.slot_of;
-    bp.band_overflow = (const uint32_t*)d_over.p;
-    bp.flagged = flagged + off;
-    bp.nf = nf;
-    {
-      ProfScope prof(ctx, MB200_K_RESCORE);
-      k_band_finish<<<nf, 256, 0, ctx->stream>>>(rp, bp);
-    }
-    ctx->launches++;
-    MB_CUDA(ctx, cudaGetLastError());
-    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the batch's workspace is reused by the next one
-    ws.next = std::max(ws.next, bj.ws_next);
+  const int ld = j->ld, nf = nband;
+  const int64_t nf_vw = mb200_valid_words(nf);
+  const int num_m = (nf + BM - 1) / BM;
+  DevBuf d_arows, d_avalid, d_ids, d_cut, d_thr, d_cand, d_ccnt;
+  MB_CHECK(d_arows.alloc(ws, (size_t)a->depth * nf * ld * 2));
+  MB_CHECK(d_avalid.alloc(ws, (size_t)a->depth * nf_vw * sizeof(uint32_t)));
+  MB_CHECK(d_ids.alloc(ws, (size_t)nf * sizeof(uint32_t)));
+  MB_CHECK(d_cut.alloc(ws, (size_t)num_m * BM * sizeof(float)));
+  MB_CHECK(d_thr.alloc(ws, (size_t)num_m * BM * sizeof(uint32_t)));
+  MB_CHECK(d_cand.alloc(ws, (size_t)num_m * BM * BAND_MAX * sizeof(uint32_t)));
+  MB_CHECK(d_ccnt.alloc(ws, (size_t)num_m * BM * sizeof(int32_t)));
+  MB_CUDA(ctx, cudaMemsetAsync(d_avalid.p, 0, (size_t)a->depth * nf_vw * sizeof(uint32_t), ctx->stream));
+  MB_CUDA(ctx, cudaMemsetAsync(d_thr.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
+  MB_CUDA(ctx, cudaMemsetAsync(d_ccnt.p, 0, (size_t)num_m * BM * sizeof(int32_t), ctx->stream));
+  k_band_gather<<<nf, 256, 0, ctx->stream>>>((const uint16_t*)a->a_rows, a->a_valid, a->a_count, mb200_valid_words(a->a_count),
+                                             a->depth, ld, flagged, nf, nf_vw, (uint32_t)a->a_id_mul, (uint32_t)a->a_id_off,
+                                             rp.row_cut, (uint16_t*)d_arows.p, (uint32_t*)d_avalid.p, (uint32_t*)d_ids.p,
+                                             (float*)d_cut.p);
+  ctx->launches++;
+  MB_CUDA(ctx, cudaGetLastError());
+  delete j->band;
+  BandState* bs = j->band = new BandState();
+  mb200_cosine_job& bj = bs->bj;
+  bj.ctx = ctx;
+  bj.a = *a;
+  bj.a.a_rows = d_arows.p;
+  bj.a.a_valid = (const uint32_t*)d_avalid.p;
+  bj.a.a_count = nf;
+  bj.a.dense_out = nullptr;
+  bj.rescored = j->rescored;
+  bj.certified = j->certified;
+  bj.ksel = j->ksel;
+  bj.BN = j->BN;
+  bj.num_m = num_m;
+  bj.ld = ld;
+  bj.scale2 = j->scale2;
+  bj.eps_rel = j->eps_rel;
+  bj.row_thr = (uint32_t*)d_thr.p;
+  bj.band_ids = (const uint32_t*)d_ids.p;
+  bj.band_cut = (const float*)d_cut.p;
+  bj.band_cand = (uint32_t*)d_cand.p;
+  bj.band_cnt = (int32_t*)d_ccnt.p;
+  bj.ws_base = bj.ws_next = ws.next;
+  bs->rp = rp;
+  bs->fin = *fin;
+  bs->d_rows = const_cast<int32_t*>(flagged);
+  bs->nband = nband;
+  bs->total_b = total_b;
+  memset(&bs->bp, 0, sizeof(bs->bp));
+  bs->bp.flagged = flagged;
+  bs->bp.cand = (const uint32_t*)d_cand.p;
+  bs->bp.cand_cnt = (const int32_t*)d_ccnt.p;
+  bs->bp.nf = nf;
+  return MB200_OK;
+}
+
+static int band_push(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
+  mb200_ctx* ctx = j->ctx;
+  BandState* bs = j->band;
+  bs->bj.pending = false;  // every sweep's lists are consumed right away (k_band_collect)
+  MB_CHECK(job_push_locked(&bs->bj, pc));
+  (void)ctx;
+  bs->ws_mark = std::max(bs->ws_mark, bs->bj.ws_next);
+  return MB200_OK;
+}
+
+static int band_complete(mb200_cosine_job* j) {
+  mb200_ctx* ctx = j->ctx;
+  BandState* bs = j->band;
+  {
+    ProfScope prof(ctx, MB200_K_RESCORE);
+    k_band_finish<<<bs->bp.nf, 256, 0, ctx->stream>>>(bs->rp, bs->bp);
   }
+  ctx->launches++;
+  MB_CUDA(ctx, cudaGetLastError());
+  ctx->last_band_rows = bs->nband;
+  ctx->stat_band += bs->nband;
+  return MB200_OK;
+}
+
+// exact full-row path for the rows whose flag is `want` (0: any flag)
+static int exact_rows_pass(mb200_cosine_job* j, RescoreParams& rp, int32_t* d_rows, int want, int64_t total_b, Workspace& ws) {
+  mb200_ctx* ctx = j->ctx;
+  const mb200_cosine_args* a = &j->a;
+  int32_t* d_count = rp.flag_count + 1;
+  MB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int32_t), ctx->stream));
+  k_collect_flagged<<<(unsigned)((a->a_count + 255) / 256), 256, 0, ctx->stream>>>(rp.row_flag, a->a_count, d_rows, d_count, want);
+  ctx->launches++;
+  int32_t nexact = 0;
+  MB_CUDA(ctx, cudaMemcpyAsync(&nexact, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->last_fallback_rows = nexact;
+  ctx->stat_fallback += nexact;
+  if (ctx->max_fallback_rows >= 0 && nexact > ctx->max_fallback_rows)
+    return mb200_fail(ctx, MB200_ERR_UNSUPPORTED,
+                      "%d rows cannot be certified from their candidate lists and would take the exact full-row path "
+                      "(limit MB200_OPT_MAX_FALLBACK_ROWS = %lld)", nexact, (long long)ctx->max_fallback_rows);
+  if (nexact > 0) {
+    DevBuf d_scratch;
+    const int batch = (int)std::max<int64_t>(1, std::min<int64_t>(nexact, (1LL << 30) / (total_b * 8)));
+    MB_CHECK(d_scratch.alloc(ws, (size_t)batch * total_b * sizeof(double)));
+    for (int off = 0; off < nexact; off += batch) {
+      const int m = std::min(batch, nexact - off);
+      if (getenv("MB200_EXACT_ROWS_SEQ") != nullptr) {  // the loop-for-loop form, kept for cross-checks
+        k_exact_rows<<<m, 256, 0, ctx->stream>>>(rp, d_rows + off, 1.0, 1.0, (double*)d_scratch.p, total_b);
+      } else {
+        dim3 grid((unsigned)m, (unsigned)((total_b + EXACT_COLS - 1) / EXACT_COLS));
+        k_exact_rows_fast<<<grid, 256, 0, ctx->stream>>>(rp, d_rows + off, (double*)d_scratch.p, total_b);
+      }
+      k_exact_topk<<<m, 256, 0, ctx->stream>>>(rp, d_rows + off, (const double*)d_scratch.p, total_b, a->exclude_self ? 1 : 0);
+      ctx->launches += 2;
+      MB_CUDA(ctx, cudaGetLastError());
+    }
+  }
+  return MB200_OK;
+}
+
+// second finish of a job in its band phase: complete the band pass, then the exact path for what it left
+static int job_finish_band_phase(mb200_cosine_job* j) {
+  mb200_ctx* ctx = j->ctx;
+  BandState* bs = j->band;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MB_CHECK(band_complete(j));
+  Workspace ws(ctx);
+  ws.next = bs->ws_mark;
+  MB_CHECK(exact_rows_pass(j, bs->rp, bs->d_rows, 2, bs->total_b, ws));
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MB200_OK;
 }
 
@@ -2676,55 +2748,44 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
         DevBuf d_rows;
         MB_CHECK(d_rows.alloc(ws, (size_t)nflag * sizeof(int32_t)));
         int32_t* d_count = rp.flag_count + 1;
-        // ---- band pass: rows that are merely uncertified get a second, targeted K3 sweep (the B side of a
-        // one-push job is still where the push found it when the caller says so by passing it again)
-        const bool can_band = j->pushes == 1 && fin->b_rows != nullptr && fin->b_valid != nullptr && j->band_cut == nullptr &&
-                              getenv("MB200_NO_BAND") == nullptr;
-        if (can_band) {
+        // Rows that are merely uncertified get a band pass -- here and now when the (single) piece of the B side is
+        // still resident (the caller passes it again in fin), or spread over a second round of pushes when the
+        // caller asked to defer them; otherwise, and for what the band pass cannot settle, the exact full-row path.
+        const bool no_band = getenv("MB200_NO_BAND") != nullptr || j->band_cut != nullptr;
+        const bool band_now = !no_band && j->pushes == 1 && fin->b_rows != nullptr && fin->b_valid != nullptr;
+        const bool band_later = !no_band && !band_now && fin->defer_uncertified != 0;
+        int32_t nband = 0;
+        if (band_now || band_later) {
           MB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int32_t), ctx->stream));
           k_collect_flagged<<<(unsigned)((a->a_count + 255) / 256), 256, 0, ctx->stream>>>(rp.row_flag, a->a_count,
                                                                                        (int32_t*)d_rows.p, d_count, 1);
-          int32_t nband = 0;
+          ctx->launches++;
           MB_CUDA(ctx, cudaMemcpyAsync(&nband, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
           MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-          ctx->launches++;
-          if (nband > 0) MB_CHECK(job_band_pass(j, fin, rp, (const int32_t*)d_rows.p, nband, ws));
-          ctx->last_band_rows = nband;
-          ctx->stat_band += nband;
         }
-        // ---- exact full-row path: rows outside the exact-integer range, band lists that overflowed, and every
-        // flagged row when no band pass was possible
-        MB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int32_t), ctx->stream));
-        k_collect_flagged<<<(unsigned)((a->a_count + 255) / 256), 256, 0, ctx->stream>>>(rp.row_flag, a->a_count,
-                                                                                     (int32_t*)d_rows.p, d_count, can_band ? 2 : 0);
-        ctx->launches++;
-        int32_t nexact = 0;
-        MB_CUDA(ctx, cudaMemcpyAsync(&nexact, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->last_fallback_rows = nexact;
-        ctx->stat_fallback += nexact;
-        if (ctx->max_fallback_rows >= 0 && nexact > ctx->max_fallback_rows)
-          return mb200_fail(ctx, MB200_ERR_UNSUPPORTED,
-                            "%d rows cannot be certified from their candidate lists and would take the exact full-row path "
-                            "(limit MB200_OPT_MAX_FALLBACK_ROWS = %lld)", nexact, (long long)ctx->max_fallback_rows);
-        if (nexact > 0) {
-          DevBuf d_scratch;
-          const int batch = (int)std::max<int64_t>(1, std::min<int64_t>(nexact, (1LL << 30) / (total_b * 8)));
-          MB_CHECK(d_scratch.alloc(ws, (size_t)batch * total_b * sizeof(double)));
-          for (int off = 0; off < nexact; off += batch) {
-            const int m = std::min(batch, nexact - off);
-            if (getenv("MB200_EXACT_ROWS_SEQ") != nullptr) {  // the loop-for-loop form, kept for cross-checks
-              k_exact_rows<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, 1.0, 1.0, (double*)d_scratch.p, total_b);
-            } else {
-              dim3 grid((unsigned)m, (unsigned)((total_b + EXACT_COLS - 1) / EXACT_COLS));
-              k_exact_rows_fast<<<grid, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (double*)d_scratch.p, total_b);
-            }
-            k_exact_topk<<<m, 256, 0, ctx->stream>>>(rp, (const int32_t*)d_rows.p + off, (const double*)d_scratch.p, total_b,
-                                                     a->exclude_self ? 1 : 0);
-            ctx->launches += 2;
-            MB_CUDA(ctx, cudaGetLastError());
+        if (nband > 0) {
+          DevBuf d_brows;  // the band rows keep their own list: d_rows is reused by the exact path
+          MB_CHECK(d_brows.alloc(ws, (size_t)nband * sizeof(int32_t)));
+          MB_CUDA(ctx, cudaMemcpyAsync(d_brows.p, d_rows.p, (size_t)nband * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+          MB_CHECK(band_setup(j, fin, rp, (const int32_t*)d_brows.p, nband, ws, total_b));
+          j->band->d_rows = (int32_t*)d_rows.p;
+          if (band_later) {
+            // everything else (band sweeps, completion, the exact path for flag-2 rows) happens in the second round
+            j->band->ws_mark = ws.next;
+            ctx->last_band_rows = nband;
+            return MB200_BAND_PENDING;
           }
+          mb200_cosine_piece pc = j->last_piece;
+          pc.b_rows = fin->b_rows;
+          pc.b_valid = fin->b_valid;
+          pc.ready_flags = nullptr;  // every block of a pull-gather has landed by now
+          pc.ready_epoch = 0;
+          pc.first_block = 0;
+          MB_CHECK(band_push(j, &pc));
+          MB_CHECK(band_complete(j));
+          ws.next = std::max(ws.next, j->band->ws_mark);
         }
+        MB_CHECK(exact_rows_pass(j, rp, (int32_t*)d_rows.p, (band_now || band_later) ? 2 : 0, total_b, ws));
       }
     }
   }
@@ -2855,6 +2916,7 @@ int mb200_cosine_begin(mb200_ctx* ctx, const mb200_cosine_args* args, mb200_cosi
 int mb200_cosine_push(mb200_cosine_job* job, const mb200_cosine_piece* piece) {
   if (!job) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_cosine_push: job is NULL");
   std::lock_guard<std::mutex> g(job->ctx->mu);
+  if (job->band != nullptr && job->band_pending) return band_push(job, piece);
   return job_push_locked(job, piece);
 }
 
@@ -2862,7 +2924,16 @@ int mb200_cosine_finish(mb200_cosine_job* job, const mb200_cosine_args* fin) {
   if (!job) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_cosine_finish: job is NULL");
   mb200_ctx* ctx = job->ctx;
   std::lock_guard<std::mutex> g(ctx->mu);
-  int rc = job_finish_locked(job, fin);
+  int rc;
+  if (job->band != nullptr && job->band_pending) {
+    rc = job_finish_band_phase(job);
+  } else {
+    rc = job_finish_locked(job, fin);
+    if (rc == MB200_BAND_PENDING) {
+      job->band_pending = true;  // the job lives on: the caller pushes the B side once more, then finishes again
+      return rc;
+    }
+  }
   if (rc != MB200_OK) cudaStreamSynchronize(ctx->stream);
   job_free(job);
   return rc;

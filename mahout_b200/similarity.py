@@ -392,7 +392,9 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
         comm.wait_stream(comp)
         free = [None] * nbuf
     b_cnt = None
-    try:
+
+    def stream_pass(do_push: bool):
+        """one sweep over the B side: chunk c of every shard is gathered while chunk c-1 is consumed"""
         for ci, c0 in enumerate(range(0, E_loc, chunk_rows)):
             c1 = min(E_loc, c0 + chunk_rows)
             n, vw = c1 - c0, vw_of(c1 - c0)
@@ -416,18 +418,39 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
                     landed = torch.cuda.Event()
                     landed.record(comm)
                 comp.wait_event(landed)
-                job.push(out, vout, id_mul=G, id_add=1, id_base=c0 * G)
+                if do_push:
+                    job.push(out, vout, id_mul=G, id_add=1, id_base=c0 * G)
                 free[b] = torch.cuda.Event()
                 free[b].record(comp)
             else:
                 gather()
-                job.push(out.clone(), vout.clone(), id_mul=G, id_add=1, id_base=c0 * G)
+                if do_push:
+                    job.push(out.clone(), vout.clone(), id_mul=G, id_add=1, id_base=c0 * G)
+
+    try:
+        stream_pass(True)
         if precision != "tensor" and counter_blocks is not None:
             # the undecided candidates are read from their owners' banks through peer mappings
             # (PeerRows.map_counters): no counter is ever gathered -- what makes exact sets possible when the
-            # bank of all shards (config 5: 10^7 x 4096 x 8 B) could not exist on one GPU
+            # bank of all shards (config 5: 10^7 x 4096 x 8 B) could not exist on one GPU.  Rows the candidate
+            # lists cannot certify are deferred: the B side is streamed a second time for those rows only (band
+            # pass) -- on every rank if any rank has such rows, because the all-gathers are collective.
             res = job.finish(a_counters=a_counters, b_id=(G, 1), counter_blocks=counter_blocks,
-                             b_count=plan.rows_per_shard, counter_blocks32=counter_blocks32)
+                             b_count=plan.rows_per_shard, counter_blocks32=counter_blocks32, defer_uncertified=True)
+            pending = torch.tensor([1 if res is None else 0], dtype=torch.int32, device=a_rows.device)
+            if cuda:
+                comp.synchronize()
+                with torch.cuda.stream(comp):
+                    dist.all_reduce(pending, op=dist.ReduceOp.MAX, group=group)
+            else:
+                dist.all_reduce(pending, op=dist.ReduceOp.MAX, group=group)
+            if int(pending.item()):
+                if cuda:
+                    comm.wait_stream(comp)
+                    free = [None] * nbuf
+                stream_pass(res is None)
+                if res is None:
+                    res = job.finish()
         elif precision != "tensor":
             # the exact re-score reads the counters of arbitrary peers: gathered whole, behind the rows
             if cuda:

@@ -531,7 +531,7 @@ class CosineJob:
         N.check(N.lib().mb200_cosine_push(self._h, C.byref(pc)), self.ctx.handle)
 
     def finish(self, a_counters=None, b_counters=None, b_id=(1, 0), out=None, counter_blocks=None, b_count=None,
-               counter_blocks32=None, resident_b=None):
+               counter_blocks32=None, resident_b=None, defer_uncertified: bool = False):
         """Returns (idx, sim, cnt) device tensors.  precision="rescored" / "certified" need the resident
         counters: a_counters [a_count, d, w], b_counters [blocks, b_count, d, w] with b_id = (id_mul, id_add);
         "certified" alternatively takes counter_blocks, a ctypes array of one device pointer per block
@@ -559,8 +559,22 @@ class CosineJob:
                 fin.b_counters = b_counters.data_ptr()
                 fin.b_blocks, fin.b_count = int(b_counters.shape[0]), int(b_counters.shape[1])
             fin.b_id_mul, fin.b_id_add = b_id
+        if getattr(self, "_band_pending", None) is not None:
+            # second finish of a deferred job: completes the band pass, writes the rows that were waiting
+            idx, sim, cnt = self._band_pending
+            h, self._h, self._band_pending = self._h, None, None
+            N.check(N.lib().mb200_cosine_finish(h, C.byref(fin)), self.ctx.handle)
+            self._keep = []
+            return idx, sim, cnt
+        fin.defer_uncertified = int(bool(defer_uncertified))
+        rc = N.lib().mb200_cosine_finish(self._h, C.byref(fin))
+        if rc == N.BAND_PENDING:
+            # uncertified rows wait for a second round of pushes (the same pieces) and a second finish()
+            self._band_pending = (idx, sim, cnt)
+            self._keep += [a_counters, b_counters]
+            return None
         h, self._h = self._h, None
-        N.check(N.lib().mb200_cosine_finish(h, C.byref(fin)), self.ctx.handle)
+        N.check(rc, self.ctx.handle)
         self._keep = []
         return idx, sim, cnt
 

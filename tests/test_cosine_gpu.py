@@ -481,3 +481,50 @@ def test_band_pass_settles_flat_similarity_rows(mb, ctx, precision):
     st = ctx.stats()
     assert st["band_rows_total"] >= bd
     bank.close()
+
+
+def test_deferred_band_pass_of_a_streamed_job(mb, ctx):
+    """A job whose B side arrives in pieces cannot re-sweep it by itself: finish(defer_uncertified) returns "pending",
+    the caller pushes the same pieces once more (K3 sweeps them for the uncertified rows only) and finishes again.
+    Result == the one-shot call == the oracle's sets; nothing takes the exact full-row path."""
+    import torch
+    from mahout_b200.sketch import CosineJob, cosine_topk_blocks, last_band_rows, last_fallback_rows
+    rng = np.random.Generator(np.random.PCG64(6))
+    E, d, w, k = 2560, 2, 128, 100
+    n = 60 * E
+    item = rng.integers(0, E, n).astype(np.int64)
+    user = rng.integers(1, 300, n).astype(np.int64)
+    pref = (rng.integers(1, 11, n) * 0.5).astype(np.float32)
+    bank = mb.SketchBank(E, w, d, 42, 1, ctx)
+    bank.update(item, user, pref)
+    a, b = orc.hash_params(42, d)
+    ref = np.zeros((E, d, w))
+    orc.bank_update(ref, d, w, a, b, item, user, pref)
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k)
+    rows, valid = bank.normalize("bf16")
+    cnt_t = bank.counters_tensor()
+    one = cosine_topk_blocks(ctx, rows, valid, rows.unsqueeze(0), valid.unsqueeze(0), d, w, k, b_id=(1, E), dtype="bf16",
+                             precision="certified", a_counters=cnt_t, b_counters=cnt_t)
+    assert last_band_rows(ctx) > 0 and last_fallback_rows(ctx) == 0
+    job = CosineJob(ctx, rows, valid, d, w, k, dtype="bf16", precision="certified")
+
+    def pushes():
+        for c0 in range(0, E, 512):
+            c1 = min(E, c0 + 512)
+            rc = rows[:, c0:c1].contiguous().unsqueeze(0)
+            vw = int(mb._native.lib().mb200_valid_words(c1 - c0))
+            vc = torch.zeros((1, d, vw), dtype=torch.int32, device=rows.device)
+            words = valid[:, c0 // 32:(c1 + 31) // 32]
+            vc[0, :, :words.shape[1]] = words
+            job.push(rc, vc, id_mul=1, id_add=0, id_base=c0)
+
+    pushes()
+    res = job.finish(a_counters=cnt_t, b_counters=cnt_t.unsqueeze(0), b_id=(1, E), defer_uncertified=True)
+    assert res is None and last_band_rows(ctx) > 0          # rows are waiting for the second round
+    pushes()
+    got = job.finish()
+    assert last_fallback_rows(ctx) == 0
+    gi, gc = got[0].cpu().numpy(), got[2].cpu().numpy()
+    assert (gc == ocnt).all() and (gc == one[2].cpu().numpy()).all()
+    assert all(set(gi[r, :gc[r]].tolist()) == set(oidx[r, :ocnt[r]].tolist()) for r in range(E))
+    bank.close()
