@@ -38,10 +38,10 @@ ITEMS, USERS, ZIPF_S = 10_000_000, 1_000_000, 1.1
 # kernel reads 12 B per event (8 B key + 4 B preference; no entity column), a bank-mode event is 20 B.
 ALGO_BYTES_PER_EVENT = 12 + DEPTH * 16
 BANK_BYTES_PER_EVENT = 20 + DEPTH * 16
-# ncu --set full of k_update_single on this workload (profiles/r2_k_update_single_ncu.txt): DRAM bytes and L2
-# reductions per event -- the physical side of the roofline object
-K1_DRAM_BYTES_PER_EVENT = 12.2
-K1_REDS_PER_EVENT = 1.5
+# ncu --set full of k_update_single_v2 on this workload (profiles/r2_k_update_single_v2_ncu.txt, one launch of 2.5e8
+# events): 3.05 GB of DRAM traffic and 286.7 M RED requests -- the physical side of the roofline object
+K1_DRAM_BYTES_PER_EVENT = 12.21
+K1_REDS_PER_EVENT = 1.147
 C3_USERS, C3_ITEMS, C3_EVENTS, C3_WIDTH, C3_DEPTH, C3_K = 138_493, 26_744, 20_000_000, 4096, 4, 50
 C3_SEED = 20240003
 C3_CHUNKS = 4              # all-gather chunks per step of the pipelined multi-GPU cosine form
@@ -439,7 +439,7 @@ def run_ours(args):
             # copy bandwidth.  The 32 MiB sketch is L2-resident, so the algorithmic model of SURVEY.md 8d (every
             # counter RMW as 16 B of HBM traffic) describes traffic that never reaches DRAM; its figure is kept under
             # "model" and may exceed 1.  What binds the kernel is the L2 reduction path: "l2_atomic".
-            "roofline": {"bound": "hbm", "kernel": "k_update_single", "achieved": dram_gbps, "peak": peaks["hbm"],
+            "roofline": {"bound": "hbm", "kernel": "k_update_single_v2", "achieved": dram_gbps, "peak": peaks["hbm"],
                          "unit": "GB/s", "frac": dram_gbps / peaks["hbm"],
                          "traffic": K1_DRAM_BYTES_PER_EVENT * n, "peak_source": peaks["source"],
                          "kernel_ms_per_launch": kern_s * 1e3, "launches_timed": int(k_n),
@@ -447,7 +447,7 @@ def run_ours(args):
                          "model": {"algorithmic_bytes_per_event": ALGO_BYTES_PER_EVENT, "achieved": model_gbps,
                                    "frac": model_gbps / peaks["hbm"],
                                    "note": "12 B event + 4 x 16 B counter RMW as if every update went to HBM; the "
-                                           "counters are L2-resident and 2/3 of the events are absorbed in shared "
+                                           "counters are L2-resident and ~3/4 of the events are absorbed in shared "
                                            "memory, so this is not a physical bound"},
                          "l2_atomic": {"peak_red64_per_s": red_peak, "reds_per_event_ncu": K1_REDS_PER_EVENT,
                                        "achieved_red64_per_s": reds, "frac": reds / red_peak,

@@ -458,7 +458,7 @@ def test_band_pass_settles_flat_similarity_rows(mb, ctx, precision):
     oracle's answer without falling back to the exact full-row path."""
     from mahout_b200.sketch import last_band_rows, last_fallback_rows
     rng = np.random.Generator(np.random.PCG64(5))
-    E, d, w, k = 3000, 2, 128, 100
+    E, d, w, k = 1800, 2, 128, 100                 # fewer columns than the band pass can hold per row (2048)
     n = 60 * E
     item = rng.integers(0, E, n).astype(np.int64)
     user = rng.integers(1, 300, n).astype(np.int64)
@@ -490,7 +490,7 @@ def test_deferred_band_pass_of_a_streamed_job(mb, ctx):
     import torch
     from mahout_b200.sketch import CosineJob, cosine_topk_blocks, last_band_rows, last_fallback_rows
     rng = np.random.Generator(np.random.PCG64(6))
-    E, d, w, k = 2560, 2, 128, 100
+    E, d, w, k = 1792, 2, 128, 100
     n = 60 * E
     item = rng.integers(0, E, n).astype(np.int64)
     user = rng.integers(1, 300, n).astype(np.int64)
