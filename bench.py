@@ -408,8 +408,7 @@ def run_ours(args):
     cosine = None
     if not args.no_cosine:
         cosine = run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, args.steps, args.warmup)
-    big = run_big_stages(args, ctx, stream, world, rank, local, dev, peaks)
-
+    line = None
     if rank == 0:
         kern_s = (k_ms / max(k_n, 1)) * 1e-3
         model_gbps = ALGO_BYTES_PER_EVENT * n / kern_s / 1e9
@@ -456,9 +455,27 @@ def run_ours(args):
                          "atomic_updates_per_s": DEPTH * n / kern_s},
             "cpu_baseline": cpu, "parity": parity, "cosine": cosine,
         }
-        if big:
-            line.update(big)
-        print(json.dumps(line), flush=True)
+    # configs[3] / configs[4] run last, under a watchdog: if a stage hangs (a rank lost in a collective), the line
+    # measured so far is still printed -- once -- and the processes leave
+    printed = threading.Event()
+
+    def emit(extra):
+        if rank == 0 and not printed.is_set():
+            printed.set()
+            line.update(extra)
+            print(json.dumps(line), flush=True)
+
+    def bail_out():
+        emit({"big_stages": f"timed out after {args.big_timeout:.0f} s"})
+        sys.stdout.flush()
+        os._exit(0)
+
+    dog = threading.Timer(args.big_timeout, bail_out)
+    dog.daemon = True
+    dog.start()
+    big = run_big_stages(args, ctx, stream, world, rank, local, dev, peaks)
+    dog.cancel()
+    emit(big or {})
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -895,6 +912,7 @@ def main():
     ap.add_argument("--no-cosine", action="store_true", help="skip the secondary cosine-stage measurement")
     ap.add_argument("--big", default="auto", choices=["auto", "on", "off"],
                     help="configs[3] / configs[4] stages (auto: at 8 GPUs)")
+    ap.add_argument("--big-timeout", type=float, default=540.0, help="watchdog of the configs[3] / configs[4] stages")
     ap.add_argument("--c4-items", type=float, default=1e6)
     ap.add_argument("--c4-events", type=float, default=2e9)
     ap.add_argument("--c4-check-rows", type=float, default=4096)

@@ -218,7 +218,7 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
     ld = int(N.lib().mb200_row_ld(width))
     a_cnt = bank.counters_tensor()
     ctx.set_profiling(True)
-    peers = sim.PeerRows(ctx, plan, depth, width) if world > 1 else None
+    peers = sim.PeerRows(ctx, plan, depth, width, staging=(form == "fused")) if world > 1 else None
     out_t = (torch.empty((E_loc, k), dtype=torch.int64, device=dev), torch.empty((E_loc, k), dtype=torch.float64, device=dev),
              torch.empty((E_loc,), dtype=torch.int32, device=dev))
     if world > 1:

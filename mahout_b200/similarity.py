@@ -482,7 +482,7 @@ class PeerRows:
     buffers of every other rank (CUDA IPC over NVLink) and the local staging operand of the fused
     pull-gather (mb200_gather_pull).  Set up once per (shape, group); collective."""
 
-    def __init__(self, ctx, plan, depth: int, width: int, dtype: str = "f16", group=None):
+    def __init__(self, ctx, plan, depth: int, width: int, dtype: str = "f16", group=None, staging: bool = True):
         import ctypes as C
         import torch
         import torch.distributed as dist
@@ -520,8 +520,10 @@ class PeerRows:
                 N.check(N.lib().mb200_peer_open(ctx.handle, C.cast(hb, C.c_void_p), C.byref(q)), ctx.handle)
                 self._opened.append(q)
                 arr[g] = q.value
-        self.staging_rows = torch.empty((G, depth, E_loc, ld), dtype=tdt, device=dev)
-        self.staging_valid = torch.empty((G, depth, vw), dtype=torch.int32, device=dev)
+        # the local copy of every shard's rows the fused pull-gather sweeps; the streamed form (pipelined_cosine)
+        # never holds the gathered operand and does without it
+        self.staging_rows = torch.empty((G, depth, E_loc, ld), dtype=tdt, device=dev) if staging else None
+        self.staging_valid = torch.empty((G, depth, vw), dtype=torch.int32, device=dev) if staging else None
         self.token = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def map_counters(self, bank):
