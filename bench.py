@@ -459,23 +459,26 @@ def run_ours(args):
     # measured so far is still printed -- once -- and the processes leave
     printed = threading.Event()
 
+    big = {}
+
     def emit(extra):
         if rank == 0 and not printed.is_set():
             printed.set()
+            line.update(big)
             line.update(extra)
             print(json.dumps(line), flush=True)
 
     def bail_out():
-        emit({"big_stages": f"timed out after {args.big_timeout:.0f} s"})
+        emit({"big_stages": f"watchdog: stopped after {args.big_timeout:.0f} s; the stages present in this line completed"})
         sys.stdout.flush()
         os._exit(0)
 
     dog = threading.Timer(args.big_timeout, bail_out)
     dog.daemon = True
     dog.start()
-    big = run_big_stages(args, ctx, stream, world, rank, local, dev, peaks)
+    run_big_stages(args, ctx, stream, world, rank, local, dev, peaks, big)
     dog.cancel()
-    emit(big or {})
+    emit({})
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -857,48 +860,64 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
     return out
 
 
-def run_big_stages(args, ctx, stream, world, rank, local, dev, peaks):
+def run_big_stages(args, ctx, stream, world, rank, local, dev, peaks, out):
     """BASELINE.json configs[3] and configs[4] (bench_big.py): at 8 GPUs by default, at other N when asked for with
-    --big on (sizes then come from the --c4-* / --c5-* flags).  Returns {"config4": ..., "config5": ...} on rank 0."""
+    --big on (sizes then come from the --c4-* / --c5-* flags).  Fills `out` ({"config4": ..., "config5": ...}, rank 0)
+    stage by stage, so that whatever is complete when the watchdog fires is still reported; a stage is skipped when
+    the time already spent leaves no room for it (--big-budget)."""
     on = args.big == "on" or (args.big == "auto" and world == 8)
     if not on:
-        return None
+        return
     import torch
     import bench_big as bb
     env = bb.Env(ctx, stream, world, rank, local, dev, peaks)
-    out = {}
-    try:
-        c4 = []
-        for d, rows in ((1, args.c4_check_rows), (4, args.c4_check_rows_d4)):
-            if d == 4 and not args.c4_d4:
-                continue
-            c4.append(bb.big_cosine(
-                env, f"config4_d{d}", "configs[3]: 1M-item all-pairs sketch cosine (width 4096), fused top-100 epilogue, "
-                "item-hash sharded; sketch rows built from config-3-style Zipf(1.1) events routed to their owners",
-                int(args.c4_items), 5_000_000, args.c4_events, 1.1, d, 4096, 100, "fused", int(rows), 20240004))
-        out["config4"] = c4[0] if rank == 0 else None
-        if rank == 0 and len(c4) > 1:
-            out["config4"]["depth4"] = c4[1]
-    except Exception as ex:                      # a failed big stage must not lose the headline line
-        out["config4"] = {"error": repr(ex)[:400]}
-        torch.cuda.synchronize(dev)
-    try:
-        a = bb.skew_update(env, args.c5_events, 10_000_000, 1.5, DEPTH, WIDTH, max(1, min(args.steps, 3)), 1, 20240005)
-        b = bb.big_cosine(
+
+    def room(name, need_s):
+        used = env.elapsed()
+        if used + need_s > args.big_budget:
+            env.log(f"{name}: skipped ({used:.0f} s used of {args.big_budget:.0f} s, needs ~{need_s:.0f} s)")
+            if rank == 0:
+                out.setdefault("skipped_stages", []).append({"stage": name, "seconds_used": used, "seconds_needed": need_s})
+            return False
+        return True
+
+    def guarded(name, fn):
+        try:
+            return fn()
+        except Exception as ex:                      # a failed stage must not lose the rest of the line
+            env.log(f"{name}: FAILED {ex!r}")
+            torch.cuda.synchronize(dev)
+            return {"name": name, "error": repr(ex)[:400]}
+
+    c4 = "configs[3]: 1M-item all-pairs sketch cosine (width 4096), fused top-100 epilogue, item-hash sharded; " \
+         "sketch rows built from config-3-style Zipf(1.1) events routed to their owners"
+    r = guarded("config4_d1", lambda: bb.big_cosine(env, "config4_d1", c4, int(args.c4_items), 5_000_000, args.c4_events, 1.1, 1,
+                                                    4096, 100, "fused", int(args.c4_check_rows), 20240004))
+    if rank == 0:
+        out["config4"] = r
+    if args.c5_events > 0 and room("config5a_skew_update", 15):
+        r = guarded("config5a", lambda: bb.skew_update(env, args.c5_events, 10_000_000, 1.5, DEPTH, WIDTH,
+                                                       max(1, min(args.steps, 3)), 1, 20240005))
+        if rank == 0:
+            out.setdefault("config5", {})["skew_update"] = r
+    if args.c5_items > 0 and room("config5b_streamed_cosine", 150):
+        r = guarded("config5b", lambda: bb.big_cosine(
             env, "config5b_streamed_cosine", "configs[4]b (scaled): 10M-item cosine top-100 at "
             f"{int(args.c5_items)} items, width 4096, depth 1, in the STREAMED form -- row chunks of every shard "
             "gathered into two staging buffers while K3 consumes them; the gathered operand never exists",
             int(args.c5_items), 5_000_000, args.c5_cos_events, 1.1, 1, 4096, 100, "pipelined", int(args.c5_check_rows),
-            20240006, chunk_rows=int(args.c5_chunk_rows), warmup=0)
+            20240006, chunk_rows=int(args.c5_chunk_rows), warmup=0))
         if rank == 0:
-            out["config5"] = {"skew_update": a, "streamed_cosine": b,
-                              "scale_note": "configs[4] asks for 1e10 events and 1e7 items: the update leg runs at full size; "
-                                            "the cosine leg is scaled (2*N^2*W FLOP: 85 s at 1e7 items on 8 GPUs) -- "
-                                            "at 1e7 x 4096 the gathered FP16 operand would be 82 GB per depth row"}
-    except Exception as ex:
-        out["config5"] = {"error": repr(ex)[:400]}
-        torch.cuda.synchronize(dev)
-    return out if rank == 0 else None
+            out.setdefault("config5", {})["streamed_cosine"] = r
+            out["config5"]["scale_note"] = ("configs[4] asks for 1e10 events and 1e7 items: the update leg runs at full size; "
+                                            "the cosine leg is scaled (2*N^2*W FLOP: 85 s at 1e7 items on 8 GPUs) -- at 1e7 x "
+                                            "4096 the gathered FP16 operand would be 82 GB per depth row")
+    if args.c4_d4 and room("config4_d4", 90):
+        r = guarded("config4_d4", lambda: bb.big_cosine(env, "config4_d4", c4, int(args.c4_items), 5_000_000, args.c4_events, 1.1, 4,
+                                                        4096, 100, "fused", int(args.c4_check_rows_d4), 20240004))
+        if rank == 0 and isinstance(out.get("config4"), dict):
+            out["config4"]["depth4"] = r
+    env.log("big stages done")
 
 
 def main():
@@ -912,16 +931,17 @@ def main():
     ap.add_argument("--no-cosine", action="store_true", help="skip the secondary cosine-stage measurement")
     ap.add_argument("--big", default="auto", choices=["auto", "on", "off"],
                     help="configs[3] / configs[4] stages (auto: at 8 GPUs)")
-    ap.add_argument("--big-timeout", type=float, default=540.0, help="watchdog of the configs[3] / configs[4] stages")
+    ap.add_argument("--big-timeout", type=float, default=600.0, help="watchdog of the configs[3] / configs[4] stages")
+    ap.add_argument("--big-budget", type=float, default=420.0, help="no new big stage starts once this many seconds of them are spent")
     ap.add_argument("--c4-items", type=float, default=1e6)
     ap.add_argument("--c4-events", type=float, default=2e9)
     ap.add_argument("--c4-check-rows", type=float, default=4096)
-    ap.add_argument("--c4-check-rows-d4", type=float, default=512)
+    ap.add_argument("--c4-check-rows-d4", type=float, default=128)
     ap.add_argument("--c4-d4", type=int, default=1, help="also run configs[3] at depth 4")
     ap.add_argument("--c5-events", type=float, default=1e10)
     ap.add_argument("--c5-items", type=float, default=4e6)
     ap.add_argument("--c5-cos-events", type=float, default=8e9)
-    ap.add_argument("--c5-check-rows", type=float, default=1024)
+    ap.add_argument("--c5-check-rows", type=float, default=512)
     ap.add_argument("--c5-chunk-rows", type=float, default=8192)
     args = ap.parse_args()
     if args.impl == "reference":

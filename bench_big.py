@@ -32,6 +32,17 @@ class Env:
 
     def __init__(self, ctx, stream, world, rank, local, dev, peaks):
         self.ctx, self.stream, self.world, self.rank, self.local, self.dev, self.peaks = ctx, stream, world, rank, local, dev, peaks
+        self.t0 = time.perf_counter()
+
+    def log(self, msg: str):
+        """progress of the long stages, rank 0, stderr (stdout carries the one JSON line)"""
+        if self.rank == 0:
+            import sys
+            print(f"[bench_big +{time.perf_counter() - self.t0:6.1f} s] {msg}", file=sys.stderr, flush=True)
+
+    def elapsed(self) -> float:
+        """seconds since the stages started, agreed by all ranks (the slowest clock)"""
+        return self.max_over_ranks(time.perf_counter() - self.t0)
 
     def barrier(self):
         import torch
@@ -161,14 +172,18 @@ def sampled_parity(env: Env, plan, bank, got, k, rows_total, seed, block=8192):
     g_cnt = np.concatenate([p[2][2] for p in parts])[order]
     n_loc = plan.local_count(rank)
     col_ids = np.arange(n_loc, dtype=np.int64) * G + rank
-    threads = max(1, _host_threads() // max(world, 1))
+    # FP64 BLAS threads per rank: the products are skinny ([rows, W] x [W, 8192]) and OpenBLAS scales poorly on them
+    # (measured on the GPU boxes: 105 GFLOP/s on 12 threads, 48 on one) -- a few threads per rank, all ranks at once
+    threads = max(1, min(2 if world >= 4 else 4, _host_threads() // max(world, 1)))
 
     def loader(c0, c1):
         return cnt_t[c0:c1].to(torch.int32).cpu().numpy()
 
+    env.log(f"parity: {ids.shape[0]} sample rows x {n_loc} local columns per rank, {threads} BLAS thread(s) per rank")
     t0 = time.perf_counter()
     ps, pi = fast.rows_vs_columns_topk(sample_q, ids, None, col_ids, k, block=block, threads=threads, chunk_loader=loader)
     oracle_s = time.perf_counter() - t0
+    env.log(f"parity: oracle done in {oracle_s:.1f} s on this rank")
     allp = env.gather_objects((ps, pi, oracle_s))
     if rank != 0:
         return None
@@ -207,8 +222,10 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
     E_loc = plan.rows_per_shard
     cdf = torch.from_numpy(synth.zipf_cdf(items, zipf)).to(dev)
     perm = torch.from_numpy(synth.rank_permutation(items, 4) - 1).to(dev)
+    env.log(f"{name}: {items} items, {int(events)} events, depth {depth}, {form}")
     bank = mb.SketchBank(E_loc, width, depth, 42, 1, ctx)
     build = routed_build(env, plan, bank, seed, int(events), users, cdf, perm)
+    env.log(f"{name}: sketch build done (route {build['route_ms']:.1f} ms + K1 {build['k1_ms']:.1f} ms)")
     del cdf, perm
     N.check(N.lib().mb200_release_workspace(ctx.handle), ctx.handle)   # the grouping workspaces (20 B / event)
     torch.cuda.empty_cache()
@@ -265,6 +282,7 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
     e1.record(env.stream)
     env.barrier()
     ms = env.max_over_ranks(e0.elapsed_time(e1) / reps)
+    env.log(f"{name}: cosine step {ms:.1f} ms")
     k2_ms, k2_n = ctx.kernel_time(N.K_NORMALIZE)
     k3_ms, k3_n = ctx.kernel_time(N.K_COSINE)
     k5_ms, k5_n = ctx.kernel_time(N.K_RESCORE)
@@ -334,6 +352,7 @@ def skew_update(env: Env, events_total, items, zipf, depth, width, steps, warmup
     from mahout_b200.sketch import _as_tensor
     ctx, world, rank, dev = env.ctx, env.world, env.rank, env.dev
     n = int(events_total) // world
+    env.log(f"config5a: {int(events_total)} Zipf({zipf}) events into replica sketches")
     cdf_h = synth.zipf_cdf(items, zipf)
     cdf = torch.from_numpy(cdf_h).to(dev)
     _, item, pref = synth.events_device(ctx, seed, rank * n, n, 1_000_000, cdf, None, want_user=False)
