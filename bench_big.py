@@ -210,7 +210,7 @@ def sampled_parity(env: Env, plan, bank, got, k, rows_total, seed, block=8192):
 # N-item all-pairs cosine, certified top-k, items sharded
 # ------------------------------------------------------------------------------------------------------------------
 def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, width, k, form, check_rows, seed,
-               chunk_rows=8192, reps=1, warmup=1):
+               chunk_rows=8192, reps=1, warmup=1, fallback_limit=256):
     import torch
     import mahout_b200 as mb
     from mahout_b200 import _native as N
@@ -252,9 +252,25 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
 
     k2()
     mixed = be.mixed_sign("certified")
+    # a row that neither its candidate list nor the band pass can settle costs one exact dot product per COLUMN: a
+    # handful is fine, thousands would take the stage past its budget -- then the stage reports the error and the
+    # tensor-precision result instead of hanging
+    ctx.set_option(N.OPT_MAX_FALLBACK_ROWS, int(fallback_limit))
+    precision = ["certified"]
 
     def step():
         k2()
+        if precision[0] == "tensor":
+            if world == 1:
+                from mahout_b200.sketch import cosine_topk_blocks
+                return cosine_topk_blocks(ctx, rows, valid, rows.unsqueeze(0), valid.unsqueeze(0), depth, width, k,
+                                          a_id=(1, 0), b_id=(1, E_loc), precision="tensor", out=out_t)
+            if form == "fused":
+                return sim.fused_gather_cosine(be, plan, peers, k, None, "f16", "tensor", out=out_t)
+            peers.barrier()
+            r = sim.pipelined_cosine(be, plan, rows, valid, k, None, "f16", "tensor", None, chunk_rows, None)
+            peers.barrier()
+            return r
         if world == 1:
             from mahout_b200.sketch import cosine_topk_blocks
             return cosine_topk_blocks(ctx, rows, valid, rows.unsqueeze(0), valid.unsqueeze(0), depth, width, k,
@@ -270,15 +286,36 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
         peers.barrier()
         return r
 
-    import torch.distributed as dist
-    for _ in range(warmup):
-        step()
+    certified_error = None
+
+    def run_steps(nsteps):
+        """nsteps steps; an error on any rank is an error on all of them (the steps are collective)"""
+        err, out = None, None
+        for _ in range(nsteps):
+            try:
+                out = step()
+            except Exception as ex:
+                err = ex
+            if not sim.all_ranks_ok(err is None, dev):
+                return None, err or RuntimeError("the step failed on another rank")
+        return out, None
+
+    _, err = run_steps(max(warmup, 1))
+    if err is not None:
+        certified_error = repr(err)[:300]
+        env.log(f"{name}: certified precision abandoned ({certified_error}); tensor precision instead")
+        torch.cuda.synchronize(dev)
+        precision[0] = "tensor"
+        _, err = run_steps(1)
+        if err is not None:
+            raise err
     env.barrier()
     ctx.reset_profile()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(env.stream)
-    for _ in range(reps):
-        got = step()
+    got, err = run_steps(reps)
+    if err is not None:
+        raise err
     e1.record(env.stream)
     env.barrier()
     ms = env.max_over_ranks(e0.elapsed_time(e1) / reps)
@@ -287,6 +324,9 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
     k3_ms, k3_n = ctx.kernel_time(N.K_COSINE)
     k5_ms, k5_n = ctx.kernel_time(N.K_RESCORE)
     fallback = env.sum_over_ranks(last_fallback_rows(ctx))
+    from mahout_b200.sketch import last_band_rows
+    band_rows = last_band_rows(ctx)
+    ctx.set_option(N.OPT_MAX_FALLBACK_ROWS, -1)
     k3_s = env.max_over_ranks(k3_ms / max(reps, 1)) * 1e-3            # all K3 launches of one step, slowest rank
     ctx.set_profiling(False)
     parity = sampled_parity(env, plan, bank, got, k, check_rows, seed + 17) if check_rows > 0 else None
@@ -313,7 +353,10 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
         peak = env.peaks["bf16"] * world
         res = {
             "name": name, "metric": "item_pair_cosine_sims_per_sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
-            "ms_per_step": ms, "n_gpus": world, "precision": "certified (exact top-k sets, tensor-core values)",
+            "ms_per_step": ms, "n_gpus": world,
+            "precision": "certified (exact top-k sets, tensor-core values)" if precision[0] == "certified" else
+                         "tensor (certified precision abandoned: see certified_error)",
+            "certified_error": certified_error, "band_rows_this_rank": int(band_rows),
             "form": form if world > 1 else "single GPU", "certified_fallback_rows": int(fallback), "mixed_sign": bool(mixed),
             "config": {"workload": workload, "items": items, "depth": depth, "width": width, "k": k, "events": int(events),
                        "zipf_s": zipf, "rows_per_gpu": E_loc, "chunk_rows": chunk_rows if form == "pipelined" else None,

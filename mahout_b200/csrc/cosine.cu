@@ -37,7 +37,10 @@ using namespace tc05;
 // ------------------------------------------------------------------------------------------------
 static constexpr int BM = 128;            // rows of A per tile (TMEM lanes)
 static constexpr int BK = 64;             // K elements per pipeline stage (one 128-byte swizzle row)
-static constexpr int BAND_MAX = 2048;      // columns above the cut the band pass can re-score per row
+static constexpr int BAND_MAX = 8192;      // columns above the cut the band pass can hold per row, at most (the job's
+                                           // band_cap is 2048, 4096 or 8192: as much as 4 GB of buffers allow)
+static constexpr int BAND_MIN = 2048;
+static constexpr int LARGE_MAX = 2048;     // candidates per row of the multi-pass selection (k beyond CAP)
 static constexpr int CAP = 256;           // candidate-list capacity per (row, column chunk, half)
 static constexpr int COS_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 static constexpr float F16_SCALE = 4096.0f;  // rows are stored as x/||x|| * 2^12 in FP16
@@ -75,12 +78,17 @@ struct CosParams {
   // band pass (second chance of rows the candidate lists could not certify): the A rows are a compact copy of
   // those rows, a_ids[row] is the row's global index, row_cut[row] the fixed admission threshold (scaled tensor
   // value) below which a column is provably outside the row's top-k; every column above it is LISTED -- no
-  // selection, no threshold raising, no lists: straight into the row's candidate buffer band_cand[row][BAND_MAX]
-  // through the cursor band_cnt[row] (a count beyond BAND_MAX sends the row to the exact full-row path)
+  // selection, no threshold raising, no lists: straight into the row's candidate buffer band_cand[row][band_cap]
+  // through the cursor band_cnt[row] (a count beyond band_cap sends the row to the exact full-row path)
   const uint32_t* a_ids;
   const float* row_cut;
   uint32_t* band_cand;
+  float* band_val;
   int32_t* band_cnt;
+  int32_t band_cap;
+  // k beyond the fused capacity (large_k_topk_locked): the candidates are taken 128 ranks at a time; row_ceil[row] is
+  // the key (value desc, index asc) of the last candidate already taken -- only columns strictly after it qualify
+  const unsigned long long* row_ceil;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -461,6 +469,7 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const size_t slot = ((size_t)w * 2 + half) * BM + row;
       uint2* list = p.lists + slot * CAP;
       int cnt = 0;
+      const unsigned long long ceil_key = (p.row_ceil != nullptr && row_ok) ? __ldg(p.row_ceil + grow) : ~0ull;
       float thr = (band && row_ok) ? __ldg(p.row_cut + grow) : p.thr_init;
       float bound = -INFINITY;
       bool published = false;
@@ -516,7 +525,10 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                   const uint32_t id = id0 + (uint32_t)j * p.b_id_mul;
                   if (x > thr && id != my_id) {
                     const int at = atomicAdd(p.band_cnt + grow, 1);
-                    if (at < BAND_MAX) p.band_cand[(size_t)grow * BAND_MAX + at] = id;
+                    if (at < p.band_cap) {
+                      p.band_cand[(size_t)grow * p.band_cap + at] = id;
+                      p.band_val[(size_t)grow * p.band_cap + at] = x;
+                    }
                   }
                 }
               }
@@ -527,7 +539,7 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
               const float x = __uint_as_float(v[j]);
               if (x > thr) {  // NaN never passes
                 const uint32_t id = id0 + (uint32_t)j * p.b_id_mul;
-                if (id != my_id) {
+                if (id != my_id && make_key(v[j], id) < ceil_key) {
                   __stcg(list + cnt, make_uint2(v[j], id));
                   cnt++;
                 }
@@ -1702,8 +1714,13 @@ __global__ void __launch_bounds__(256) k_band_gather(const uint16_t* __restrict_
 
 struct BandParams {
   const int32_t* flagged;   // compact row -> row of the job
-  const uint32_t* cand;     // [nf][BAND_MAX] column ids above the row's cut, all sweeps
+  int cap;                  // candidates a row can hold (row stride of cand / cval; the kernel's dynamic smem is 12 * cap)
+  const uint32_t* cand;     // [nf][cap] column ids above the row's cut, all sweeps
   const int32_t* cand_cnt;  // [nf]
+  const float* cval;        // optional [nf][cap] scaled tensor values of the candidates
+  int certified;            // with cval: decide from the tensor values first, re-score only the undecided
+  const float* bound;       // optional [nf]: largest scaled tensor value NOT among the candidates (-inf: none); the
+                            // row is only accepted when its exact k-th similarity clears it (else flag 2)
   int nf;
 };
 
@@ -1778,58 +1795,11 @@ __device__ __forceinline__ bool pair_sums_exact(const RescoreParams& p, const lo
 }
 
 // one CTA per flagged row: collect the listed columns, re-score them exactly, order, write the top-k
-__global__ void __launch_bounds__(256) k_band_finish(const RescoreParams p, const BandParams bp) {
-  __shared__ uint32_t s_id[BAND_MAX];
-  __shared__ double s_val[BAND_MAX];
-  __shared__ int s_n, s_bad;
-  const int r2 = blockIdx.x;
-  const long long r = bp.flagged[r2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    s_n = bp.cand_cnt[r2];
-    s_bad = 0;
-  }
-  __syncthreads();
-  for (int e = tid; e < s_n && e < BAND_MAX; e += blockDim.x) s_id[e] = bp.cand[(size_t)r2 * BAND_MAX + e];
-  __syncthreads();
-  const int n = s_n;
-  if (n > BAND_MAX || s_bad) {
-    // a tie group (or a row of near-equal similarities) too large to settle here: the exact full-row path
-    if (tid == 0) p.row_flag[r] = 2;
-    return;
-  }
-  const long long* arow = p.a_counters + (size_t)r * p.d * p.W;
-  for (int c = warp; c < n; c += 8) {
-    long long g, l;
-    b_locate(p, s_id[c], g, l);
-    double mn = JAVA_MAX_DOUBLE;
-    for (int i = 0; i < p.d; i++) {
-      double va, vb, vab;
-      if (!pair_sums_exact(p, arow + (size_t)i * p.W, g, l, i, lane, va, vb, vab)) s_bad = 1;
-      const double den = __dmul_rn(sqrt(va), sqrt(vb));
-      if (den != 0.0) {
-        const double cs = __ddiv_rn(vab, den);
-        mn = cs < mn ? cs : mn;
-      }
-    }
-    // admitted iff not NaN (no comparable row), >= threshold and > Double.MIN_VALUE
-    if (lane == 0) s_val[c] = (mn != JAVA_MAX_DOUBLE && mn >= p.threshold && mn > 4.9e-324) ? mn : -INFINITY;
-  }
-  for (int c = n + tid; c < BAND_MAX; c += blockDim.x) {
-    s_val[c] = -INFINITY;
-    s_id[c] = 0xFFFFFFFFu;
-  }
-  __syncthreads();
-  if (s_bad) {
-    if (tid == 0) p.row_flag[r] = 2;
-    return;
-  }
-  // bitonic sort of the power of two that covers n, order (similarity desc, index asc)
-  int np2 = 32;
-  while (np2 < n) np2 <<= 1;
+// block-wide bitonic sort of s_val / s_id[0, np2) under (value desc, index asc)
+__device__ __forceinline__ void band_sort(double* s_val, uint32_t* s_id, int np2) {
   for (int kk = 2; kk <= np2; kk <<= 1) {
     for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-      for (int e = tid; e < np2; e += blockDim.x) {
+      for (int e = threadIdx.x; e < np2; e += blockDim.x) {
         const int o = e ^ jj;
         if (o > e) {
           const bool desc = (e & kk) == 0;
@@ -1847,6 +1817,110 @@ __global__ void __launch_bounds__(256) k_band_finish(const RescoreParams p, cons
       __syncthreads();
     }
   }
+}
+
+// One CTA per row: order what the band sweeps listed, decide as much as the tensor values allow (CERTIFIED with
+// bp.cval: a candidate is surely IN when the (k+1)-th tensor value cannot reach it, surely OUT when it cannot reach
+// the k-th), re-score the undecided rest exactly -- integer dot products -- and write the row's top-k.  RESCORED
+// (and the large-k path, which has no tensor values in band order) re-scores every candidate.
+#define BAND_IN_SHIFT 4.0   /* cosines are in [-1, 1]: a surely-in candidate sorts ahead of every exact value */
+__global__ void __launch_bounds__(256) k_band_finish(const RescoreParams p, const BandParams bp) {
+  extern __shared__ double s_band[];
+  double* s_val = s_band;
+  uint32_t* s_id = (uint32_t*)(s_band + bp.cap);
+  __shared__ int s_n, s_bad, s_adm;
+  const int r2 = blockIdx.x;
+  const long long r = bp.flagged[r2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    s_n = bp.cand_cnt[r2];
+    s_bad = 0;
+    s_adm = 0;
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > bp.cap) {
+    // a tie group (or a row of near-equal similarities) too large to settle here: the exact full-row path
+    if (tid == 0) p.row_flag[r] = 2;
+    return;
+  }
+  const bool classify = bp.cval != nullptr && bp.certified;
+  int np2 = 32;
+  while (np2 < n) np2 <<= 1;
+  for (int e = tid; e < np2; e += blockDim.x) {
+    s_id[e] = e < n ? bp.cand[(size_t)r2 * bp.cap + e] : 0xFFFFFFFFu;
+    s_val[e] = (e < n && classify) ? (double)(bp.cval[(size_t)r2 * bp.cap + e] * p.inv_scale2) : -INFINITY;
+  }
+  __syncthreads();
+  double v_k = -INFINITY, v_k1 = -INFINITY;  // k-th and (k+1)-th tensor value
+  if (classify) {
+    band_sort(s_val, s_id, np2);
+    if (n >= p.k) v_k = s_val[p.k - 1];
+    if (n > p.k) v_k1 = s_val[p.k];
+    __syncthreads();
+  }
+  const double er = (double)p.eps_rel, ea = (double)p.eps_abs;
+  const double k1_hi = v_k1 + fabs(v_k1) * er + ea;   // the most the (k+1)-th can really be
+  const double k_lo = v_k - fabs(v_k) * er - ea;      // the least the k-th can really be
+  const double thr = p.threshold > 0.0 ? p.threshold : 0.0;
+  const long long* arow = p.a_counters + (size_t)r * p.d * p.W;
+  for (int c = warp; c < n; c += 8) {
+    if (classify) {
+      const double v = s_val[c];
+      const double lo = v - fabs(v) * er - ea, hi = v + fabs(v) * er + ea;
+      // the admission cut (threshold, or positivity when the error is absolute) must be clear as well
+      const bool clear_of_thr = lo > thr || (thr == 0.0 && !p.mixed && v > 0.0);
+      if (c < p.k && (n <= p.k || k1_hi < lo) && clear_of_thr) {
+        if (lane == 0) s_val[c] = v + BAND_IN_SHIFT;   // surely in: keeps its tensor value
+        continue;
+      }
+      if (c >= p.k && k_lo > hi) {
+        if (lane == 0) s_val[c] = -INFINITY;           // surely out
+        continue;
+      }
+    }
+    long long g, l;
+    b_locate(p, s_id[c], g, l);
+    double mn = JAVA_MAX_DOUBLE;
+    for (int i = 0; i < p.d; i++) {
+      double va, vb, vab;
+      if (!pair_sums_exact(p, arow + (size_t)i * p.W, g, l, i, lane, va, vb, vab)) s_bad = 1;
+      const double den = __dmul_rn(sqrt(va), sqrt(vb));
+      if (den != 0.0) {
+        const double cs = __ddiv_rn(vab, den);
+        mn = cs < mn ? cs : mn;
+      }
+    }
+    // admitted iff not NaN (no comparable row), >= threshold and > Double.MIN_VALUE
+    if (lane == 0) s_val[c] = (mn != JAVA_MAX_DOUBLE && mn >= p.threshold && mn > 4.9e-324) ? mn : -INFINITY;
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) p.row_flag[r] = 2;
+    return;
+  }
+  // (surely in, by tensor value) ahead of (re-scored, by exact value): the first k are the row's top-k
+  band_sort(s_val, s_id, np2);
+  if (bp.bound != nullptr) {
+    const float b = bp.bound[r2];
+    const double kth = (p.k - 1 < np2) ? s_val[p.k - 1] : -INFINITY;
+    const double bs = (double)(b * p.inv_scale2);
+    if (b > -INFINITY && !(kth > bs + fabs(bs) * er + ea)) {
+      if (tid == 0) p.row_flag[r] = 2;
+      return;
+    }
+  }
+  if (classify) {
+    // back to plain values, everything beyond the k-th dropped, and the k results ordered by the value returned
+    __syncthreads();
+    for (int e = tid; e < np2; e += blockDim.x) {
+      double v = s_val[e];
+      if (v > 2.0) v -= BAND_IN_SHIFT;
+      s_val[e] = e < p.k ? v : -INFINITY;
+    }
+    __syncthreads();
+    band_sort(s_val, s_id, np2);
+  }
   int admitted = 0;
   for (int e = tid; e < p.k; e += blockDim.x) {
     const bool ok = e < np2 && s_val[e] > -INFINITY;
@@ -1854,10 +1928,6 @@ __global__ void __launch_bounds__(256) k_band_finish(const RescoreParams p, cons
     p.out_sim[(size_t)r * p.k + e] = ok ? s_val[e] : 0.0;
     admitted += ok ? 1 : 0;
   }
-  // count of admitted results = number of finite values among the first k
-  __shared__ int s_adm;
-  if (tid == 0) s_adm = 0;
-  __syncthreads();
   if (admitted) atomicAdd(&s_adm, admitted);
   __syncthreads();
   if (tid == 0) {
@@ -2036,7 +2106,10 @@ struct mb200_cosine_job {
   const uint32_t* band_ids = nullptr;
   const float* band_cut = nullptr;
   uint32_t* band_cand = nullptr;
+  float* band_val = nullptr;
   int32_t* band_cnt = nullptr;
+  int band_cap = 0;
+  const unsigned long long* row_ceil = nullptr;  // large-k passes (see CosParams)
   // band phase of THIS job: after a finish that deferred its uncertified rows, pushes feed `band` and the next
   // finish completes it
   struct BandState* band = nullptr;
@@ -2381,7 +2454,10 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   p.a_ids = j->band_ids;
   p.row_cut = j->band_cut;
   p.band_cand = j->band_cand;
+  p.band_val = j->band_val;
   p.band_cnt = j->band_cnt;
+  p.band_cap = j->band_cap;
+  p.row_ceil = j->row_ceil;
   p.lists = (uint2*)d_lists.p;
   p.list_cnt = (int32_t*)d_cnt.p;
   p.list_bound = (float*)d_bound.p;
@@ -2444,14 +2520,17 @@ static int band_setup(mb200_cosine_job* j, const mb200_cosine_args* fin, const R
   const int ld = j->ld, nf = nband;
   const int64_t nf_vw = mb200_valid_words(nf);
   const int num_m = (nf + BM - 1) / BM;
-  DevBuf d_arows, d_avalid, d_ids, d_cut, d_thr, d_cand, d_ccnt;
+  DevBuf d_arows, d_avalid, d_ids, d_cut, d_thr, d_cand, d_ccnt, d_cvals;
+  int cap = BAND_MAX;  // 8 bytes per slot: 8192 slots up to 64 Ki band rows, 2048 beyond 128 Ki
+  while (cap > BAND_MIN && (size_t)num_m * BM * cap * 8 > ((size_t)4 << 30)) cap >>= 1;
   MB_CHECK(d_arows.alloc(ws, (size_t)a->depth * nf * ld * 2));
   MB_CHECK(d_avalid.alloc(ws, (size_t)a->depth * nf_vw * sizeof(uint32_t)));
   MB_CHECK(d_ids.alloc(ws, (size_t)nf * sizeof(uint32_t)));
   MB_CHECK(d_cut.alloc(ws, (size_t)num_m * BM * sizeof(float)));
   MB_CHECK(d_thr.alloc(ws, (size_t)num_m * BM * sizeof(uint32_t)));
-  MB_CHECK(d_cand.alloc(ws, (size_t)num_m * BM * BAND_MAX * sizeof(uint32_t)));
+  MB_CHECK(d_cand.alloc(ws, (size_t)num_m * BM * cap * sizeof(uint32_t)));
   MB_CHECK(d_ccnt.alloc(ws, (size_t)num_m * BM * sizeof(int32_t)));
+  MB_CHECK(d_cvals.alloc(ws, (size_t)num_m * BM * cap * sizeof(float)));
   MB_CUDA(ctx, cudaMemsetAsync(d_avalid.p, 0, (size_t)a->depth * nf_vw * sizeof(uint32_t), ctx->stream));
   MB_CUDA(ctx, cudaMemsetAsync(d_thr.p, 0, (size_t)num_m * BM * sizeof(uint32_t), ctx->stream));
   MB_CUDA(ctx, cudaMemsetAsync(d_ccnt.p, 0, (size_t)num_m * BM * sizeof(int32_t), ctx->stream));
@@ -2482,7 +2561,9 @@ static int band_setup(mb200_cosine_job* j, const mb200_cosine_args* fin, const R
   bj.band_ids = (const uint32_t*)d_ids.p;
   bj.band_cut = (const float*)d_cut.p;
   bj.band_cand = (uint32_t*)d_cand.p;
+  bj.band_val = (float*)d_cvals.p;
   bj.band_cnt = (int32_t*)d_ccnt.p;
+  bj.band_cap = cap;
   bj.ws_base = bj.ws_next = ws.next;
   bs->rp = rp;
   bs->fin = *fin;
@@ -2491,6 +2572,10 @@ static int band_setup(mb200_cosine_job* j, const mb200_cosine_args* fin, const R
   bs->total_b = total_b;
   memset(&bs->bp, 0, sizeof(bs->bp));
   bs->bp.flagged = flagged;
+  bs->bp.cap = cap;
+  bs->bp.bound = nullptr;
+  bs->bp.cval = (const float*)d_cvals.p;
+  bs->bp.certified = j->certified ? 1 : 0;
   bs->bp.cand = (const uint32_t*)d_cand.p;
   bs->bp.cand_cnt = (const int32_t*)d_ccnt.p;
   bs->bp.nf = nf;
@@ -2512,7 +2597,9 @@ static int band_complete(mb200_cosine_job* j) {
   BandState* bs = j->band;
   {
     ProfScope prof(ctx, MB200_K_RESCORE);
-    k_band_finish<<<bs->bp.nf, 256, 0, ctx->stream>>>(bs->rp, bs->bp);
+    const int smem = bs->bp.cap * 12;
+    MB_CUDA(ctx, cudaFuncSetAttribute(k_band_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_band_finish<<<bs->bp.nf, 256, smem, ctx->stream>>>(bs->rp, bs->bp);
   }
   ctx->launches++;
   MB_CUDA(ctx, cudaGetLastError());
@@ -2803,6 +2890,201 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
   return MB200_OK;
 }
 
+// ---- k beyond the fused capacity -------------------------------------------------------------------------------
+// The reference takes any --maxSimilaritiesPerItem (ItemSimilarityJob.java:105).  The fused selection holds CAP - 64
+// candidates per row; beyond that the candidates are taken LARGE_KP ranks at a time: pass p is an ordinary
+// tensor-precision job that returns the next LARGE_KP columns after the last one already taken (row_ceil), in the
+// exact order of the tensor values.  The collected candidates are then written out (TENSOR) or re-scored exactly,
+// ordered and certified against the last value taken (k_band_finish); rows that do not certify take the exact
+// full-row path.  Cost: ceil((k + margin) / 128) sweeps of K3.
+static constexpr int LARGE_KP = 128;
+
+__global__ void k_largek_init(unsigned long long* ceil, int32_t* ccnt, float* bound, long long rows) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) {
+    ceil[r] = ~0ull;
+    ccnt[r] = 0;
+    bound[r] = -INFINITY;
+  }
+}
+
+// one warp per row: the pass's results join the row's candidates; the last one becomes the ceiling of the next pass
+__global__ void __launch_bounds__(256) k_largek_append(const long long* __restrict__ t_idx, const double* __restrict__ t_sim,
+                                                       const int32_t* __restrict__ t_cnt, long long rows, float scale2,
+                                                       uint32_t* __restrict__ cand, float* __restrict__ cval,
+                                                       int32_t* __restrict__ ccnt, unsigned long long* __restrict__ ceil,
+                                                       float* __restrict__ bound) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int n = t_cnt[r], off = ccnt[r];
+  for (int t = lane; t < n; t += 32) {
+    cand[(size_t)r * LARGE_MAX + off + t] = (uint32_t)t_idx[(size_t)r * LARGE_KP + t];
+    cval[(size_t)r * LARGE_MAX + off + t] = (float)(t_sim[(size_t)r * LARGE_KP + t] * (double)scale2);  // exact: power of two
+  }
+  __syncwarp();
+  if (lane == 0) {
+    ccnt[r] = off + n;
+    if (n == LARGE_KP) {
+      const float v = (float)(t_sim[(size_t)r * LARGE_KP + n - 1] * (double)scale2);
+      ceil[r] = make_key(__float_as_uint(v), (uint32_t)t_idx[(size_t)r * LARGE_KP + n - 1]);
+      bound[r] = v;
+    } else {
+      ceil[r] = 0ull;       // the row is exhausted: nothing else clears the admission threshold
+      bound[r] = -INFINITY;
+    }
+  }
+}
+
+__global__ void k_largek_emit(const uint32_t* __restrict__ cand, const float* __restrict__ cval, const int32_t* __restrict__ ccnt,
+                              long long rows, int k, float inv_scale2, long long* __restrict__ out_idx,
+                              double* __restrict__ out_sim, int32_t* __restrict__ out_cnt) {
+  const long long r = blockIdx.x;
+  const int n = min(ccnt[r], k);
+  for (int t = threadIdx.x; t < k; t += blockDim.x) {
+    out_idx[(size_t)r * k + t] = t < n ? (long long)cand[(size_t)r * LARGE_MAX + t] : -1LL;
+    out_sim[(size_t)r * k + t] = t < n ? (double)(cval[(size_t)r * LARGE_MAX + t] * inv_scale2) : 0.0;
+  }
+  if (threadIdx.x == 0) out_cnt[r] = n;
+}
+
+__global__ void k_iota32(int32_t* p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+
+static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc);
+static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin);
+
+static int large_k_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t ws_base) {
+  const bool rescored = a->precision != MB200_PRECISION_TENSOR;
+  const int want = a->k + (rescored ? std::max(64, a->k / 4) : 0);
+  const int P = (want + LARGE_KP - 1) / LARGE_KP;
+  if (P * LARGE_KP > LARGE_MAX)
+    return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_cosine_topk: k = %d is beyond what the multi-pass selection holds (%d)",
+                      a->k, LARGE_MAX - LARGE_MAX / 5);
+  if (rescored && a->b_counter_blocks)
+    return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "mb200_cosine_topk: k > %d needs the gathered b_counters (not b_counter_blocks)", CAP - 64);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long long rows = a->a_count;
+  Workspace ws(ctx);
+  ws.next = ws_base;
+  DevBuf d_cand, d_cval, d_ccnt, d_ceil, d_bound, d_tidx, d_tsim, d_tcnt, d_flag, d_fcount, d_rows;
+  MB_CHECK(d_cand.alloc(ws, (size_t)rows * LARGE_MAX * sizeof(uint32_t)));
+  MB_CHECK(d_cval.alloc(ws, (size_t)rows * LARGE_MAX * sizeof(float)));
+  MB_CHECK(d_ccnt.alloc(ws, (size_t)rows * sizeof(int32_t)));
+  MB_CHECK(d_ceil.alloc(ws, (size_t)rows * sizeof(unsigned long long)));
+  MB_CHECK(d_bound.alloc(ws, (size_t)rows * sizeof(float)));
+  MB_CHECK(d_tidx.alloc(ws, (size_t)rows * LARGE_KP * sizeof(long long)));
+  MB_CHECK(d_tsim.alloc(ws, (size_t)rows * LARGE_KP * sizeof(double)));
+  MB_CHECK(d_tcnt.alloc(ws, (size_t)rows * sizeof(int32_t)));
+  MB_CHECK(d_flag.alloc(ws, (size_t)rows * sizeof(int32_t)));
+  MB_CHECK(d_fcount.alloc(ws, 2 * sizeof(int32_t)));
+  MB_CHECK(d_rows.alloc(ws, (size_t)rows * sizeof(int32_t)));
+  const unsigned g256 = (unsigned)((rows + 255) / 256);
+  k_largek_init<<<g256, 256, 0, ctx->stream>>>((unsigned long long*)d_ceil.p, (int32_t*)d_ccnt.p, (float*)d_bound.p, rows);
+  const float scale = a->dtype == MB200_DTYPE_F16 ? F16_SCALE : 1.0f;
+  const float scale2 = scale * scale;
+  float eps_rel = 0.f;
+  for (int p = 0; p < P; p++) {
+    mb200_cosine_args sub = *a;
+    sub.k = LARGE_KP;
+    sub.precision = MB200_PRECISION_TENSOR;
+    // a pair whose exact similarity clears the threshold may show a tensor value a little below it: the passes admit
+    // with a lowered threshold, the exact one is applied after re-scoring
+    if (rescored && a->threshold > 0.0) sub.threshold = a->threshold * (a->dtype == MB200_DTYPE_F16 ? 0.995 : 0.96);
+    sub.dense_out = nullptr;
+    sub.out_idx = (int64_t*)d_tidx.p;
+    sub.out_sim = (double*)d_tsim.p;
+    sub.out_cnt = (int32_t*)d_tcnt.p;
+    mb200_cosine_job* j = nullptr;
+    MB_CHECK(job_begin_locked(ctx, &sub, ws.next, &j));
+    j->row_ceil = p > 0 ? (const unsigned long long*)d_ceil.p : nullptr;
+    eps_rel = j->eps_rel;
+    mb200_cosine_piece pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.b_rows = a->b_rows;
+    pc.b_valid = a->b_valid;
+    pc.b_count = a->b_count;
+    pc.b_blocks = a->b_blocks;
+    pc.b_id_mul = a->b_id_mul;
+    pc.b_id_add = a->b_id_add;
+    int rc = job_push_locked(j, &pc);
+    if (rc == MB200_OK) rc = job_finish_locked(j, &sub);
+    if (rc != MB200_OK) cudaStreamSynchronize(ctx->stream);
+    job_free(j);
+    MB_CHECK(rc);
+    k_largek_append<<<(unsigned)((rows + 7) / 8), 256, 0, ctx->stream>>>(
+        (const long long*)d_tidx.p, (const double*)d_tsim.p, (const int32_t*)d_tcnt.p, rows, scale2, (uint32_t*)d_cand.p,
+        (float*)d_cval.p, (int32_t*)d_ccnt.p, (unsigned long long*)d_ceil.p, (float*)d_bound.p);
+    ctx->launches++;
+    MB_CUDA(ctx, cudaGetLastError());
+  }
+  ctx->last_band_rows = 0;
+  ctx->last_fallback_rows = 0;
+  if (!rescored) {
+    k_largek_emit<<<(unsigned)rows, 128, 0, ctx->stream>>>((const uint32_t*)d_cand.p, (const float*)d_cval.p, (const int32_t*)d_ccnt.p,
+                                                          rows, a->k, 1.0f / scale2, (long long*)a->out_idx, a->out_sim, a->out_cnt);
+    ctx->launches++;
+    MB_CUDA(ctx, cudaGetLastError());
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MB200_OK;
+  }
+  // exact re-score of everything collected, certification against the last value taken
+  const bool contiguous = a->b_id_mul == 1 && (a->b_blocks == 1 || a->b_id_add == a->b_count);
+  RescoreParams rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.a_counters = (const long long*)a->a_counters;
+  rp.b_counters = (const long long*)a->b_counters;
+  rp.a_count = rows;
+  rp.b_count = a->b_count;
+  rp.d = a->depth;
+  rp.W = a->width;
+  rp.blocks = a->b_blocks;
+  rp.a_id_mul = (uint32_t)a->a_id_mul;
+  rp.a_id_off = (uint32_t)a->a_id_off;
+  rp.b_id_mul = (uint32_t)a->b_id_mul;
+  rp.b_id_add = contiguous ? (uint32_t)a->b_count : 1u;
+  rp.inv_scale2 = 1.0f / scale2;
+  rp.eps_rel = eps_rel;
+  rp.mixed = a->mixed_sign ? 1 : 0;
+  rp.eps_abs = a->mixed_sign ? eps_rel : eps_rel * 1e-3f;
+  rp.k = a->k;
+  rp.threshold = a->threshold > 0.0 ? a->threshold : 0.0;
+  rp.out_idx = (long long*)a->out_idx;
+  rp.out_sim = a->out_sim;
+  rp.out_cnt = a->out_cnt;
+  rp.row_flag = (int32_t*)d_flag.p;
+  rp.flag_count = (int32_t*)d_fcount.p;
+  MB_CUDA(ctx, cudaMemsetAsync(d_flag.p, 0, (size_t)rows * sizeof(int32_t), ctx->stream));
+  MB_CUDA(ctx, cudaMemsetAsync(d_fcount.p, 0, 2 * sizeof(int32_t), ctx->stream));
+  k_iota32<<<g256, 256, 0, ctx->stream>>>((int32_t*)d_rows.p, rows);
+  BandParams bp;
+  bp.flagged = (const int32_t*)d_rows.p;
+  bp.cand = (const uint32_t*)d_cand.p;
+  bp.cand_cnt = (const int32_t*)d_ccnt.p;
+  bp.bound = (const float*)d_bound.p;
+  bp.cval = nullptr;
+  bp.certified = 0;
+  bp.cap = LARGE_MAX;
+  bp.nf = (int)rows;
+  {
+    ProfScope prof(ctx, MB200_K_RESCORE);
+    MB_CUDA(ctx, cudaFuncSetAttribute(k_band_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, LARGE_MAX * 12));
+    k_band_finish<<<(unsigned)rows, 256, LARGE_MAX * 12, ctx->stream>>>(rp, bp);
+  }
+  ctx->launches += 2;
+  MB_CUDA(ctx, cudaGetLastError());
+  // rows that did not certify (or left the exact-integer range): every column, exactly
+  mb200_cosine_job fake;
+  fake.ctx = ctx;
+  fake.a = *a;
+  rp.b_id_add = (uint32_t)a->b_id_add;  // forward mapping for k_exact_*
+  MB_CHECK(exact_rows_pass(&fake, rp, (int32_t*)d_rows.p, 2, a->b_count * a->b_blocks, ws));
+  MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MB200_OK;
+}
+
 // the one-shot form: begin + one push of the whole B side + finish
 static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t ws_base) {
   if (!a) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: args is NULL");
@@ -2819,6 +3101,7 @@ static int cosine_topk_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t
                       "shards (mul=b_blocks, add=1)");
   if (a->precision != MB200_PRECISION_TENSOR && (!a->a_counters || !a->b_counters))
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_cosine_topk: MB200_PRECISION_RESCORED / _CERTIFIED need a_counters and b_counters");
+  if (a->k > CAP - 64) return large_k_topk_locked(ctx, a, ws_base);
   mb200_cosine_job* j = nullptr;
   MB_CHECK(job_begin_locked(ctx, a, ws_base, &j));
   mb200_cosine_piece pc;

@@ -435,22 +435,36 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
             # bank of all shards (config 5: 10^7 x 4096 x 8 B) could not exist on one GPU.  Rows the candidate
             # lists cannot certify are deferred: the B side is streamed a second time for those rows only (band
             # pass) -- on every rank if any rank has such rows, because the all-gathers are collective.
-            res = job.finish(a_counters=a_counters, b_id=(G, 1), counter_blocks=counter_blocks,
-                             b_count=plan.rows_per_shard, counter_blocks32=counter_blocks32, defer_uncertified=True)
-            pending = torch.tensor([1 if res is None else 0], dtype=torch.int32, device=a_rows.device)
+            err = None
+            try:
+                res = job.finish(a_counters=a_counters, b_id=(G, 1), counter_blocks=counter_blocks,
+                                 b_count=plan.rows_per_shard, counter_blocks32=counter_blocks32, defer_uncertified=True)
+            except Exception as ex:          # e.g. MB200_OPT_MAX_FALLBACK_ROWS: every rank must learn of it
+                err, res = ex, ()
+            pending = torch.tensor([2 if err is not None else (1 if res is None else 0)], dtype=torch.int32,
+                                   device=a_rows.device)
             if cuda:
                 comp.synchronize()
                 with torch.cuda.stream(comp):
                     dist.all_reduce(pending, op=dist.ReduceOp.MAX, group=group)
             else:
                 dist.all_reduce(pending, op=dist.ReduceOp.MAX, group=group)
-            if int(pending.item()):
+            state = int(pending.item())
+            if state == 2:
+                raise err if err is not None else RuntimeError("pipelined_cosine: the certified finish failed on another rank")
+            if state == 1:
                 if cuda:
                     comm.wait_stream(comp)
                     free = [None] * nbuf
                 stream_pass(res is None)
+                err = None
                 if res is None:
-                    res = job.finish()
+                    try:
+                        res = job.finish()
+                    except Exception as ex:
+                        err = ex
+                if not all_ranks_ok(err is None, a_rows.device, group):
+                    raise err if err is not None else RuntimeError("pipelined_cosine: the band pass failed on another rank")
         elif precision != "tensor":
             # the exact re-score reads the counters of arbitrary peers: gathered whole, behind the rows
             if cuda:
@@ -640,9 +654,24 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
             res = job.finish(out=out)
     except BaseException:
         job.abort()
+        # the peers are waiting at the closing barrier: meet them before the error leaves this rank, or the step
+        # deadlocks (the caller is expected to fail on every rank -- see `all_ranks_ok`)
+        peers.barrier()
         raise
     peers.barrier()
     return res
+
+
+def all_ranks_ok(ok: bool, device, group=None) -> bool:
+    """collective AND of a per-rank status: a step that failed on one rank (e.g. too many rows for the exact path)
+    must be abandoned by all of them together, or the next collective hangs"""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bool(ok)
+    t = torch.tensor([0 if ok else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item()) == 0
 
 
 def _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_result, num_items):

@@ -445,8 +445,31 @@ def test_bf16_rows_and_largest_k_keep_the_exact_contract(mb, ctx, dtype, k):
     assert (ccnt == ocnt).all()
     assert all(set(cidx[r, :ccnt[r]].tolist()) == set(oidx[r, :ocnt[r]].tolist()) for r in range(E))
     assert last_fallback_rows(ctx) <= E
-    with pytest.raises(mb.NativeError):
-        bank.cosine_topk(193)                         # beyond the fused capacity: refused, never truncated
+    bank.close()
+
+
+@pytest.mark.parametrize("k,threshold", [(193, None), (500, None), (700, 0.2)])
+def test_k_beyond_the_fused_capacity(mb, ctx, k, threshold):
+    """The reference takes any --maxSimilaritiesPerItem (ItemSimilarityJob.java:105).  Beyond the fused capacity (192)
+    the candidates are collected 128 ranks at a time (row ceilings): re-scored == the oracle bit for bit, certified ==
+    its sets, tensor values within tolerance; rows with fewer than k admissible columns return them all."""
+    E, d, w = 1500, 2, 512
+    bank, ref = _make_bank(mb, ctx, E, d, w, 70 * E, seed=7 + k, empty=(3, 900))
+    kw = {} if threshold is None else {"threshold": threshold}
+    oidx, osim, ocnt = orc.bank_cosine_topk(ref, k, **kw)
+    idx, sim, cnt = bank.cosine_topk(k, precision="rescored", **({} if threshold is None else {"threshold": threshold}))
+    assert (cnt == ocnt).all()
+    assert (idx == oidx).all() and sim.tobytes() == osim.tobytes()
+    cidx, csim, ccnt = bank.cosine_topk(k, precision="certified", **({} if threshold is None else {"threshold": threshold}))
+    assert (ccnt == ocnt).all()
+    assert all(set(cidx[r, :ccnt[r]].tolist()) == set(oidx[r, :ocnt[r]].tolist()) for r in range(E))
+    tidx, tsim, tcnt = bank.cosine_topk(k, precision="tensor", **({} if threshold is None else {"threshold": threshold}))
+    if threshold is None:
+        assert (tcnt == ocnt).all()
+    dense = orc.bank_cosine_dense(ref)
+    for r in range(0, E, 97):
+        for t in range(tcnt[r]):
+            assert abs(tsim[r, t] - dense[r, tidx[r, t]]) <= REL_TOL * abs(dense[r, tidx[r, t]])
     bank.close()
 
 
