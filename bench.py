@@ -891,10 +891,11 @@ def run_big_stages(args, ctx, stream, world, rank, local, dev, peaks, out):
 
     c4 = "configs[3]: 1M-item all-pairs sketch cosine (width 4096), fused top-100 epilogue, item-hash sharded; " \
          "sketch rows built from config-3-style Zipf(1.1) events routed to their owners"
-    r = guarded("config4_d1", lambda: bb.big_cosine(env, "config4_d1", c4, int(args.c4_items), 5_000_000, args.c4_events, 1.1, 1,
-                                                    4096, 100, "fused", int(args.c4_check_rows), 20240004))
-    if rank == 0:
-        out["config4"] = r
+    if args.c4_items > 0:
+        r = guarded("config4_d1", lambda: bb.big_cosine(env, "config4_d1", c4, int(args.c4_items), 5_000_000, args.c4_events, 1.1, 1,
+                                                        4096, 100, "fused", int(args.c4_check_rows), 20240004))
+        if rank == 0:
+            out["config4"] = r
     if args.c5_events > 0 and room("config5a_skew_update", 15):
         r = guarded("config5a", lambda: bb.skew_update(env, args.c5_events, 10_000_000, 1.5, DEPTH, WIDTH,
                                                        max(1, min(args.steps, 3)), 1, 20240005))
@@ -912,7 +913,7 @@ def run_big_stages(args, ctx, stream, world, rank, local, dev, peaks, out):
             out["config5"]["scale_note"] = ("configs[4] asks for 1e10 events and 1e7 items: the update leg runs at full size; "
                                             "the cosine leg is scaled (2*N^2*W FLOP: 85 s at 1e7 items on 8 GPUs) -- at 1e7 x "
                                             "4096 the gathered FP16 operand would be 82 GB per depth row")
-    if args.c4_d4 and room("config4_d4", 90):
+    if args.c4_d4 and args.c4_items > 0 and room("config4_d4", 90):
         r = guarded("config4_d4", lambda: bb.big_cosine(env, "config4_d4", c4, int(args.c4_items), 5_000_000, args.c4_events, 1.1, 4,
                                                         4096, 100, "fused", int(args.c4_check_rows_d4), 20240004))
         if rank == 0 and isinstance(out.get("config4"), dict):

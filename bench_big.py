@@ -255,7 +255,7 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
     # a row that neither its candidate list nor the band pass can settle costs one exact dot product per COLUMN: a
     # handful is fine, thousands would take the stage past its budget -- then the stage reports the error and the
     # tensor-precision result instead of hanging
-    ctx.set_option(N.OPT_MAX_FALLBACK_ROWS, int(fallback_limit))
+    ctx.set_option(N.OPT_MAX_FALLBACK_ROWS, max(8, int(fallback_limit) // max(depth, 1)))
     precision = ["certified"]
 
     def step():
@@ -325,7 +325,7 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
     k5_ms, k5_n = ctx.kernel_time(N.K_RESCORE)
     fallback = env.sum_over_ranks(last_fallback_rows(ctx))
     from mahout_b200.sketch import last_band_rows
-    band_rows = last_band_rows(ctx)
+    band_rows = env.sum_over_ranks(last_band_rows(ctx))
     ctx.set_option(N.OPT_MAX_FALLBACK_ROWS, -1)
     k3_s = env.max_over_ranks(k3_ms / max(reps, 1)) * 1e-3            # all K3 launches of one step, slowest rank
     ctx.set_profiling(False)
@@ -356,7 +356,7 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
             "ms_per_step": ms, "n_gpus": world,
             "precision": "certified (exact top-k sets, tensor-core values)" if precision[0] == "certified" else
                          "tensor (certified precision abandoned: see certified_error)",
-            "certified_error": certified_error, "band_rows_this_rank": int(band_rows),
+            "certified_error": certified_error, "band_rows": int(band_rows),
             "form": form if world > 1 else "single GPU", "certified_fallback_rows": int(fallback), "mixed_sign": bool(mixed),
             "config": {"workload": workload, "items": items, "depth": depth, "width": width, "k": k, "events": int(events),
                        "zipf_s": zipf, "rows_per_gpu": E_loc, "chunk_rows": chunk_rows if form == "pipelined" else None,

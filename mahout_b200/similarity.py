@@ -392,6 +392,17 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
         comm.wait_stream(comp)
         free = [None] * nbuf
     b_cnt = None
+    import os
+    import sys
+    import time
+    debug = os.environ.get("MB200_BENCH_DEBUG") is not None
+    t_start = time.perf_counter()
+
+    def note(what):
+        if debug:
+            if cuda:
+                torch.cuda.synchronize(a_rows.device)
+            print(f"[pipelined_cosine rank {plan.rank} +{time.perf_counter() - t_start:8.3f}s] {what}", file=sys.stderr, flush=True)
 
     def stream_pass(do_push: bool):
         """one sweep over the B side: chunk c of every shard is gathered while chunk c-1 is consumed"""
@@ -429,6 +440,7 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
 
     try:
         stream_pass(True)
+        note("first sweep queued and done")
         if precision != "tensor" and counter_blocks is not None:
             # the undecided candidates are read from their owners' banks through peer mappings
             # (PeerRows.map_counters): no counter is ever gathered -- what makes exact sets possible when the
@@ -450,6 +462,8 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
             else:
                 dist.all_reduce(pending, op=dist.ReduceOp.MAX, group=group)
             state = int(pending.item())
+            note(f"first finish: state {state} (0 done, 1 band pass pending somewhere, 2 failed), "
+                 f"band rows here {sk.last_band_rows(backend.ctx) if cuda else 0}")
             if state == 2:
                 raise err if err is not None else RuntimeError("pipelined_cosine: the certified finish failed on another rank")
             if state == 1:
@@ -457,12 +471,14 @@ def pipelined_cosine(backend, plan, a_rows, a_valid, k, threshold, dtype, precis
                     comm.wait_stream(comp)
                     free = [None] * nbuf
                 stream_pass(res is None)
+                note("band sweep done")
                 err = None
                 if res is None:
                     try:
                         res = job.finish()
                     except Exception as ex:
                         err = ex
+                note(f"band finish done ({'ok' if err is None else repr(err)[:200]})")
                 if not all_ranks_ok(err is None, a_rows.device, group):
                     raise err if err is not None else RuntimeError("pipelined_cosine: the band pass failed on another rank")
         elif precision != "tensor":

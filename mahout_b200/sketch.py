@@ -482,13 +482,14 @@ def cosine_topk_blocks(ctx: Context, a_rows, a_valid, b_rows, b_valid, depth: in
     import time
     dbg = os.environ.get("MB200_BENCH_DEBUG") is not None
     t0 = time.perf_counter()
-    torch.cuda.synchronize(ctx.device)
+    if dbg:
+        torch.cuda.synchronize(ctx.device)
     t1 = time.perf_counter()
-    N.check(N.lib().mb200_cosine_topk(ctx.handle, C.byref(args)), ctx.handle)
+    N.check(N.lib().mb200_cosine_topk(ctx.handle, C.byref(args)), ctx.handle)   # complete on return
     t2 = time.perf_counter()
-    ctx.sync()
     if dbg:
         import sys
+        ctx.sync()
         print(f"[bench debug] cosine_topk_blocks {precision}: sync before {1e3 * (t1 - t0):.2f} ms, call "
               f"{1e3 * (t2 - t1):.2f} ms, sync after {1e3 * (time.perf_counter() - t2):.2f} ms", file=sys.stderr)
     return (idx, sim, cnt, dense) if want_dense else (idx, sim, cnt)
