@@ -1283,7 +1283,11 @@ __global__ void __launch_bounds__(256) k_certify(const RescoreParams p) {
     __syncthreads();
   }
   __syncthreads();
-  for (int c = tid; c < nsel; c += blockDim.x) s_fin[s_sel[c]] = s_min[c];   // JAVA_MAX_DOUBLE = not comparable
+  // (a row that is already known to be uncertified skipped the exact sums: its candidates keep their tensor values,
+  // and the k-th of THOSE sets the band pass's cut -- dropping them instead would leave fewer than k values, no cut,
+  // and every positive column of the row in the band)
+  if (!s_flag)
+    for (int c = tid; c < nsel; c += blockDim.x) s_fin[s_sel[c]] = s_min[c];   // JAVA_MAX_DOUBLE = not comparable
   __syncthreads();
   if (warp == 0) rescore_finish(p, r, n, s_fin, s_bad ? 2 : (s_flag ? 1 : 0), lane, true);
 }

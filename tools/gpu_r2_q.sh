@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2 GPUs: the per-rank sizes of the 8-GPU big stages (configs[3] at depth 1 and the streamed configs[4] cosine)
-O=gpurun_out/r2q
+O=gpurun_out/r2r
 mkdir -p $O
 t0=$(date +%s)
 MB200_BENCH_DEBUG=1 timeout 480 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 bench.py \
