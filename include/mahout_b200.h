@@ -411,6 +411,16 @@ int mb200_gather_pull(mb200_ctx* ctx, void* staging_rows, uint32_t* staging_vali
                       int32_t my_block, int64_t rows_bytes_per_block, int64_t valid_bytes_per_block,
                       const uint32_t** ready_flags, uint32_t* epoch);
 int mb200_gather_wait(mb200_ctx* ctx);
+/* Copies of the peers' int32 counter banks (mb200_bank_narrow32) for MB200_PRECISION_CERTIFIED, when they fit the
+ * local memory: queued on the copy stream BEHIND the row pulls (call after mb200_gather_pull), one DMA per peer
+ * block dst_blocks[g] <- src_blocks[g] (g != my_block), in ring order.  The undecided candidates of k_certify and
+ * of the band pass are then read from local HBM instead of one NVLink round trip per row of counters -- the same
+ * peer rows are wanted by thousands of local rows (measured at 2 GPUs, 125000 x 250000, depth 4: k_certify
+ * 222-272 ms through the peer mappings, 46 ms on one GPU with half the columns).
+ *   mb200_gather_fence  the compute stream waits (on the device) for everything queued on the copy stream so far */
+int mb200_gather_pull_counters(mb200_ctx* ctx, void* const* dst_blocks, const void* const* src_blocks,
+                               int32_t blocks, int32_t my_block, int64_t bytes_per_block);
+int mb200_gather_fence(mb200_ctx* ctx);
 int mb200_cosine_begin(mb200_ctx* ctx, const mb200_cosine_args* args, mb200_cosine_job** job);
 int mb200_cosine_push(mb200_cosine_job* job, const mb200_cosine_piece* piece);
 int mb200_cosine_finish(mb200_cosine_job* job, const mb200_cosine_args* fin);

@@ -158,6 +158,8 @@ _PROTOS = {
     "mb200_peer_free": (C.c_int, [vp, vp]),
     "mb200_gather_pull": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i64, i64, C.POINTER(vp), C.POINTER(C.c_uint32)]),
     "mb200_gather_wait": (C.c_int, [vp]),
+    "mb200_gather_pull_counters": (C.c_int, [vp, vp, vp, i32, i32, i64]),
+    "mb200_gather_fence": (C.c_int, [vp]),
     "mb200_cosine_begin": (C.c_int, [vp, C.POINTER(CosineArgs), C.POINTER(vp)]),
     "mb200_cosine_push": (C.c_int, [vp, C.POINTER(CosinePiece)]),
     "mb200_cosine_finish": (C.c_int, [vp, C.POINTER(CosineArgs)]),

@@ -65,6 +65,7 @@ struct mb200_ctx {
   uint32_t* gather_abort = nullptr;
   uint32_t gather_epoch = 0;
   cudaEvent_t gather_ev = nullptr;
+  cudaEvent_t fence_ev = nullptr;  // mb200_gather_fence
   int64_t last_fallback_rows = 0;
   int64_t last_band_rows = 0, stat_band = 0;
   int64_t stat_events = 0, stat_rows = 0, stat_fallback = 0, stat_h2d = 0, stat_d2h = 0;

@@ -2766,6 +2766,10 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
       }
       rp.cand_val = mp.cand_val;
       if (j->certified) {
+        if (trace) {
+          cudaStreamSynchronize(ctx->stream);
+          TRACE("K3+merge");
+        }
         k_certify<<<(unsigned)a->a_count, 256, 0, ctx->stream>>>(rp);
         ctx->launches++;
       } else {
@@ -2872,8 +2876,20 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
           pc.ready_flags = nullptr;  // every block of a pull-gather has landed by now
           pc.ready_epoch = 0;
           pc.first_block = 0;
+          if (trace) {
+            cudaStreamSynchronize(ctx->stream);
+            TRACE("band setup");
+          }
           MB_CHECK(band_push(j, &pc));
+          if (trace) {
+            cudaStreamSynchronize(ctx->stream);
+            TRACE("band sweep");
+          }
           MB_CHECK(band_complete(j));
+          if (trace) {
+            cudaStreamSynchronize(ctx->stream);
+            TRACE("band finish");
+          }
           ws.next = std::max(ws.next, j->band->ws_mark);
         }
         MB_CHECK(exact_rows_pass(j, rp, (int32_t*)d_rows.p, (band_now || band_later) ? 2 : 0, total_b, ws));
@@ -3343,6 +3359,37 @@ int mb200_gather_pull(mb200_ctx* ctx, void* staging_rows, uint32_t* staging_vali
   }
   *ready_flags = ctx->gather_flags;
   *epoch = ep;
+  return MB200_OK;
+}
+
+int mb200_gather_pull_counters(mb200_ctx* ctx, void* const* dst_blocks, const void* const* src_blocks, int32_t blocks,
+                               int32_t my_block, int64_t bytes_per_block) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_gather_pull_counters: ctx is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!dst_blocks || !src_blocks || blocks <= 0 || blocks > MB200_MAX_BLOCKS || my_block < 0 || my_block >= blocks ||
+      bytes_per_block <= 0)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_gather_pull_counters: bad arguments (blocks=%d my_block=%d)", blocks, my_block);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->gather_ev) MB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->gather_ev, cudaEventDisableTiming));
+  // after everything queued so far on the compute stream (the caller's cross-rank barrier sits there)
+  MB_CUDA(ctx, cudaEventRecord(ctx->gather_ev, ctx->stream));
+  MB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gather_ev, 0));
+  for (int s = 1; s < blocks; s++) {
+    const int b = (my_block + s) % blocks;
+    if (!dst_blocks[b] || !src_blocks[b])
+      return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_gather_pull_counters: block pointer %d is NULL", b);
+    MB_CUDA(ctx, cudaMemcpyAsync(dst_blocks[b], src_blocks[b], (size_t)bytes_per_block, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+  }
+  return MB200_OK;
+}
+
+int mb200_gather_fence(mb200_ctx* ctx) {
+  if (!ctx) return mb200_fail(nullptr, MB200_ERR_BAD_ARG, "mb200_gather_fence: ctx is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->fence_ev) MB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fence_ev, cudaEventDisableTiming));
+  MB_CUDA(ctx, cudaEventRecord(ctx->fence_ev, ctx->copy_stream));
+  MB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->fence_ev, 0));
   return MB200_OK;
 }
 

@@ -131,6 +131,7 @@ int mb200_destroy(mb200_ctx* ctx) {
     if (w.first) cudaFree(w.first);
   if (ctx->gather_flags) cudaFree(ctx->gather_flags);
   if (ctx->gather_ev) cudaEventDestroy(ctx->gather_ev);
+  if (ctx->fence_ev) cudaEventDestroy(ctx->fence_ev);
   for (int i = 0; i < 2; i++) {
     if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     cudaEventDestroy(ctx->stage_free[i]);

@@ -22,6 +22,8 @@ import numpy as np
 
 from . import sketch as sk
 
+LOCAL_COUNTERS_MAX_BYTES = 64 << 30      # PeerRows: local copies of the peers' int32 banks are held up to this size ...
+LOCAL_COUNTERS_KEEP_FREE = 40 << 30      # ... and only if this much device memory stays free for the cosine workspaces
 NO_THRESHOLD = 4.9e-324          # RowSimilarityJob.NO_THRESHOLD = Double.MIN_VALUE (RowSimilarityJob.java:56)
 DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM = 100   # ItemSimilarityJob.java:88
 DEFAULT_MIN_PREFS_PER_USER = 1
@@ -602,7 +604,45 @@ class PeerRows:
             N.check(N.lib().mb200_peer_open(ctx.handle, C.cast(hb, C.c_void_p), C.byref(q)), ctx.handle)
             self._opened.append(q)
             self.counter_blocks32[g] = q.value
+        # Local copies of the peers' int32 banks, when they fit beside everything else (the fused form only: the
+        # streamed form exists for shapes whose gathered operands do not fit): the undecided candidates are then
+        # read from local HBM -- the same peer rows are wanted by thousands of local rows, and every read through
+        # a peer mapping is an NVLink round trip.  Filled per step by pull_counters().
+        self.local32, self.local_blocks32 = None, None
+        nbytes = E * d * w * 4
+        free, _ = torch.cuda.mem_get_info(ctx.device)
+        want = (G - 1) * nbytes
+        fits = torch.tensor([1 if (self.staging_rows is not None and G > 1 and want <= LOCAL_COUNTERS_MAX_BYTES
+                                   and free - want >= LOCAL_COUNTERS_KEEP_FREE) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=self.group)      # the same path on every rank
+        if int(fits.item()) == 1:
+            self.local32 = [None if g == self.plan.rank else torch.empty(E * d * w, dtype=torch.int32, device=dev)
+                            for g in range(G)]
+            self.local_blocks32 = (C.c_void_p * G)()
+            for g in range(G):
+                self.local_blocks32[g] = p32.value if g == self.plan.rank else self.local32[g].data_ptr()
+            self._counter_bytes = nbytes
         return self.counter_blocks
+
+    def pull_counters(self):
+        """queue the copies of the peers' int32 banks behind the row pulls (no-op when they are read in place)"""
+        import ctypes as C
+        from . import _native as N
+        if self.local_blocks32 is None:
+            return
+        N.check(N.lib().mb200_gather_pull_counters(self.ctx.handle, C.cast(self.local_blocks32, C.c_void_p),
+                                                   C.cast(self.counter_blocks32, C.c_void_p), self.plan.G, self.plan.rank,
+                                                   self._counter_bytes), self.ctx.handle)
+
+    def fence(self):
+        """the compute stream waits for the copies queued so far"""
+        from . import _native as N
+        N.check(N.lib().mb200_gather_fence(self.ctx.handle), self.ctx.handle)
+
+    @property
+    def blocks32(self):
+        """where k_certify reads the int32 counters of every block: local copies if held, else the peer mappings"""
+        return self.local_blocks32 if getattr(self, "local_blocks32", None) is not None else getattr(self, "counter_blocks32", None)
 
     def refresh_narrow(self):
         """bring this rank's int32 copy up to date with its bank (before the step's first barrier)"""
@@ -636,6 +676,7 @@ class PeerRows:
         self.barrier()                       # nobody is still reading my buffers
         torch.cuda.synchronize(self.ctx.device)
         self.rows = self.valid = None
+        self.local32 = self.local_blocks32 = None
         for q in self._opened:
             N.lib().mb200_peer_close(self.ctx.handle, q)
         for p in self._own:
@@ -656,16 +697,19 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
         peers.refresh_narrow()
     peers.barrier()
     ready = peers.pull()
+    if counter_blocks is not None and precision != "tensor":
+        peers.pull_counters()
     job = backend.begin(plan, peers.rows, peers.valid, k, threshold, dtype, precision,
                         **({"mixed_sign": True} if mixed_sign else {}))
     try:
         job.push(peers.staging_rows, peers.staging_valid, id_mul=G, id_add=1, ready=ready, first_block=plan.rank)
         if precision != "tensor":
+            if counter_blocks is not None:
+                peers.fence()
             res = job.finish(a_counters=a_counters, b_counters=b_counters, b_id=(G, 1), out=out,
                              resident_b=(peers.staging_rows, peers.staging_valid),
                              counter_blocks=counter_blocks, b_count=plan.rows_per_shard,
-                             counter_blocks32=getattr(peers, "counter_blocks32", None) if counter_blocks is not None
-                             else None)
+                             counter_blocks32=peers.blocks32 if counter_blocks is not None else None)
         else:
             res = job.finish(out=out)
     except BaseException:
