@@ -23,6 +23,7 @@ import numpy as np
 from . import sketch as sk
 
 LOCAL_COUNTERS_MAX_BYTES = 64 << 30      # PeerRows: local copies of the peers' int32 banks are held up to this size ...
+LOCAL_COUNTERS_MIN_ROWS = 16384          # ... for shards of at least this many rows (below, the copies outlast K3) ...
 LOCAL_COUNTERS_KEEP_FREE = 40 << 30      # ... and only if this much device memory stays free for the cosine workspaces
 NO_THRESHOLD = 4.9e-324          # RowSimilarityJob.NO_THRESHOLD = Double.MIN_VALUE (RowSimilarityJob.java:56)
 DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM = 100   # ItemSimilarityJob.java:88
@@ -612,7 +613,9 @@ class PeerRows:
         nbytes = E * d * w * 4
         free, _ = torch.cuda.mem_get_info(ctx.device)
         want = (G - 1) * nbytes
-        fits = torch.tensor([1 if (self.staging_rows is not None and G > 1 and want <= LOCAL_COUNTERS_MAX_BYTES
+        # (worth it only when K3 is long enough to hide the copies: K3 time / copy time ~ 2.3e-4 * rows per shard)
+        fits = torch.tensor([1 if (self.staging_rows is not None and G > 1 and E >= LOCAL_COUNTERS_MIN_ROWS
+                                   and want <= LOCAL_COUNTERS_MAX_BYTES
                                    and free - want >= LOCAL_COUNTERS_KEEP_FREE) else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=self.group)      # the same path on every rank
         if int(fits.item()) == 1:

@@ -156,6 +156,11 @@ def _nccl_worker(rank, world, port, q):
     # certified across GPUs: the undecided candidates are read from the peers' banks over NVLink (no gather)
     res["certified"] = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N,
                                                    k=20, width=1024, depth=4, precision="certified")
+    # ... and from local copies of the peers' int32 banks, pulled behind the rows (what large shards do)
+    keep, sim.LOCAL_COUNTERS_MIN_ROWS = sim.LOCAL_COUNTERS_MIN_ROWS, 0
+    res["certified_local_copies"] = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N,
+                                                                k=20, width=1024, depth=4, precision="certified")
+    sim.LOCAL_COUNTERS_MIN_ROWS = keep
     for precision in ("rescored", "tensor"):
         res[precision] = sim.sharded_item_similarity(row[rank::world], user[rank::world], pref[rank::world], N,
                                                      k=20, width=1024, depth=4, precision=precision)
@@ -225,10 +230,11 @@ def test_sharded_two_gpus_nccl():
     idx, s, cnt = res["rescored"]
     assert (cnt == ocnt).all() and (idx == oidx).all() and s.tobytes() == osim.tobytes()
     assert res["fused_ok"], "fused pull-gather result differs from the all-gather + K3 result"
-    idx, s, cnt = res["certified"]
-    assert (cnt == ocnt).all()
-    for r in range(777):
-        assert set(idx[r, :cnt[r]].tolist()) == set(oidx[r, :cnt[r]].tolist()), r
+    for form in ("certified", "certified_local_copies"):
+        idx, s, cnt = res[form]
+        assert (cnt == ocnt).all()
+        for r in range(777):
+            assert set(idx[r, :cnt[r]].tolist()) == set(oidx[r, :cnt[r]].tolist()), (form, r)
     idx, s, cnt = res["tensor"]
     assert (cnt == ocnt).all()
     dense = orc.bank_cosine_dense(ref)
