@@ -40,6 +40,9 @@ static constexpr int BK = 64;             // K elements per pipeline stage (one 
 static constexpr int BAND_MAX = 8192;      // columns above the cut the band pass can hold per row, at most (the job's
                                            // band_cap is 2048, 4096 or 8192: as much as 4 GB of buffers allow)
 static constexpr int BAND_MIN = 2048;
+static constexpr int LCAP = 512;           // capacity of one K3 candidate list: a thread appends a whole tile's worth
+                                           // (<= BN / 2 entries) between two threshold raises, which run AFTER the
+                                           // accumulator has gone back to the MMA warp
 static constexpr int LARGE_MAX = 2048;     // candidates per row of the multi-pass selection (k beyond CAP)
 static constexpr int CAP = 256;           // candidate-list capacity per (row, column chunk, half)
 static constexpr int COS_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
@@ -59,7 +62,7 @@ struct CosParams {
   int32_t exclude_self, nonstrict;
   float thr_init;
   int32_t ksel;
-  uint2* lists;             // [item][half][128][CAP] (value bits, index)
+  uint2* lists;             // [item][half][128][LCAP] (value bits, index)
   int32_t* list_cnt;        // [item][half][128]
   float* list_bound;        // [item][half][128]: every candidate not in the list has value <= bound
   uint32_t* row_thr;        // [a rows padded]: best published lower bound of the row's ksel-th value (ordered uint)
@@ -229,9 +232,9 @@ __device__ __forceinline__ void warp_sort_desc(unsigned long long (&key)[NPL], i
 // Warp-cooperative compaction of one candidate list: keep the ksel best of its n entries, sorted.
 // Returns (to every lane) the value bits of the ksel-th entry, or 0xFFFFFFFF if n < ksel.
 __device__ __noinline__ uint32_t warp_compact_list(uint2* list, int n, int ksel, int lane) {
-  unsigned long long key[CAP / 32];
+  unsigned long long key[LCAP / 32];
 #pragma unroll
-  for (int s = 0; s < CAP / 32; s++) {
+  for (int s = 0; s < LCAP / 32; s++) {
     const int e = s * 32 + lane;
     key[s] = 0ull;
     if (e < n) {
@@ -239,11 +242,11 @@ __device__ __noinline__ uint32_t warp_compact_list(uint2* list, int n, int ksel,
       key[s] = make_key(x.x, x.y);
     }
   }
-  warp_sort_desc<CAP / 32>(key, lane);
+  warp_sort_desc<LCAP / 32>(key, lane);
   const int keep = n < ksel ? n : ksel;
   uint32_t kth = 0xFFFFFFFFu;
 #pragma unroll
-  for (int s = 0; s < CAP / 32; s++) {
+  for (int s = 0; s < LCAP / 32; s++) {
     const int e = s * 32 + lane;
     if (e < keep) __stcg(list + e, key_entry(key[s]));
     // the ksel-th entry lives in slot s = (ksel-1)/32 of lane (ksel-1)%32
@@ -260,9 +263,9 @@ __device__ __noinline__ uint32_t warp_compact_list(uint2* list, int n, int ksel,
 // unsorted.  Never cuts inside a group of equal values, so ties need no index rule here.
 // Returns T in the ordered-uint domain; *new_n = survivors.
 __device__ __noinline__ uint32_t warp_select_list(uint2* list, int n, int ksel, int lane, int* new_n) {
-  uint32_t ord[CAP / 32], idv[CAP / 32];
+  uint32_t ord[LCAP / 32], idv[LCAP / 32];
 #pragma unroll
-  for (int s = 0; s < CAP / 32; s++) {
+  for (int s = 0; s < LCAP / 32; s++) {
     const int e = s * 32 + lane;
     ord[s] = 0u;
     idv[s] = 0u;
@@ -278,7 +281,7 @@ __device__ __noinline__ uint32_t warp_select_list(uint2* list, int n, int ksel, 
     const uint32_t cand = T | (1u << bit);
     int c = 0;
 #pragma unroll
-    for (int s = 0; s < CAP / 32; s++) c += (ord[s] >= cand) ? 1 : 0;
+    for (int s = 0; s < LCAP / 32; s++) c += (ord[s] >= cand) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
     if (c >= ksel) {
       T = cand;
@@ -288,7 +291,7 @@ __device__ __noinline__ uint32_t warp_select_list(uint2* list, int n, int ksel, 
   __syncwarp();
   int base = 0;
 #pragma unroll
-  for (int s = 0; s < CAP / 32; s++) {
+  for (int s = 0; s < LCAP / 32; s++) {
     const bool keep = ord[s] >= T && ord[s] != 0u;
     const unsigned b = __ballot_sync(0xffffffffu, keep);
     if (keep) __stcg(list + base + __popc(b & ((1u << lane) - 1u)), make_uint2(ord2f(ord[s]), idv[s]));
@@ -467,13 +470,66 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           rv |= ((__ldg(p.a_valid + (size_t)dep * p.a_vw + (grow >> 5)) >> (grow & 31)) & 1u) << dep;
       }
       const size_t slot = ((size_t)w * 2 + half) * BM + row;
-      uint2* list = p.lists + slot * CAP;
+      uint2* list = p.lists + slot * LCAP;
       int cnt = 0;
       const unsigned long long ceil_key = (p.row_ceil != nullptr && row_ok) ? __ldg(p.row_ceil + grow) : ~0ull;
       float thr = (band && row_ok) ? __ldg(p.row_cut + grow) : p.thr_init;
       float bound = -INFINITY;
-      bool published = false;
       uint32_t* my_row_thr = p.row_thr + (size_t)it.x * BM + row;
+      // Threshold raises: warp-cooperative, and only AFTER the accumulator stage has been handed back (a raise costs
+      // microseconds and the lanes of a warp tend to need theirs together: inside the chunk loop they stalled the
+      // MMA warp -- K3 lost 17 % between k = 10 and k = 100).  Optional raises (the list holds `wm` entries: 2 * ksel,
+      // so that a fresh threshold is published early) are rationed to two per accumulation step and warp, which fits
+      // in the shadow of the next step's MMAs; a list that has no room left for a whole tile (HALF entries) is
+      // raised at once, and at the end of the sweep every list is cut down to what the merge will want.
+      const int wm = min(max(2 * p.ksel, 128), LCAP - HALF);
+      auto raise_thresholds = [&](bool tile_done, bool sweep_done) {
+        const bool must = (tile_done && cnt > LCAP - HALF) || (sweep_done && cnt > p.ksel + 32);
+        unsigned need_must = __ballot_sync(0xffffffffu, must);
+        unsigned need_opt = __ballot_sync(0xffffffffu, cnt >= wm && !must);
+        int budget = 2;
+        while (need_must != 0u || (budget > 0 && need_opt != 0u)) {
+          int src;
+          if (need_must != 0u) {
+            src = __ffs(need_must) - 1;
+            need_must &= need_must - 1;
+          } else {
+            src = __ffs(need_opt) - 1;
+            need_opt &= need_opt - 1;
+            budget--;
+          }
+          __syncwarp();
+          uint2* l2 = (uint2*)__shfl_sync(0xffffffffu, (unsigned long long)list, src);
+          const int n2 = __shfl_sync(0xffffffffu, cnt, src);
+          int n3 = 0;
+          const uint32_t T = warp_select_list(l2, n2, p.ksel, lane, &n3);
+          uint32_t kth = 0xFFFFFFFFu;
+          if (n3 > p.ksel + 32) {  // a large group of equal values: cut it by index (exact sort)
+            __syncwarp();
+            kth = warp_compact_list(l2, n3, p.ksel, lane);
+          }
+          if (lane == src) {
+            if (kth != 0xFFFFFFFFu) {
+              cnt = min(n3, p.ksel);
+              const float kv = __uint_as_float(kth);
+              bound = fmaxf(bound, kv);
+              // ties at the k-th value may still win on the index unless the scan order is
+              // index-monotone: admit them by stepping the threshold one ulp down
+              const uint32_t ko = f2ord(kth);
+              const uint32_t to = p.nonstrict && ko > 0 ? ko - 1 : ko;
+              thr = fmaxf(thr, __uint_as_float(ord2f(to)));
+              // other lists of the row scan other index ranges: they must keep admitting ties
+              atomicMax(my_row_thr, ko > 0 ? ko - 1 : 0u);
+            } else if (T != 0u) {
+              cnt = n3;
+              bound = fmaxf(bound, __uint_as_float(ord2f(T)));
+              thr = fmaxf(thr, __uint_as_float(ord2f(T - 1)));  // x > thr  <=>  x >= T
+              atomicMax(my_row_thr, T - 1);
+            }
+          }
+          __syncwarp();
+        }
+      };
       for (int t = t0; t < t1; t += it.w) {
         const int gs = t / p.tiles_per_block;
         const int l0 = (t - gs * p.tiles_per_block) * BN + half * HALF;
@@ -545,44 +601,6 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                 }
               }
             }
-            // keep 32 free slots for the next chunk; raise the threshold early once so that the
-            // other lists of the row can use it.  Threshold raises are warp-cooperative.
-            unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - 32 || (!published && cnt >= 2 * p.ksel));
-            while (need) {
-              const int src = __ffs(need) - 1;
-              need &= need - 1;
-              __syncwarp();
-              uint2* l2 = (uint2*)__shfl_sync(0xffffffffu, (unsigned long long)list, src);
-              const int n2 = __shfl_sync(0xffffffffu, cnt, src);
-              int n3 = 0;
-              const uint32_t T = warp_select_list(l2, n2, p.ksel, lane, &n3);
-              uint32_t kth = 0xFFFFFFFFu;
-              if (n3 > p.ksel + 32) {  // a large group of equal values: cut it by index (exact sort)
-                __syncwarp();
-                kth = warp_compact_list(l2, n3, p.ksel, lane);
-              }
-              if (lane == src) {
-                published = true;
-                if (kth != 0xFFFFFFFFu) {
-                  cnt = min(n3, p.ksel);
-                  const float kv = __uint_as_float(kth);
-                  bound = fmaxf(bound, kv);
-                  // ties at the k-th value may still win on the index unless the scan order is
-                  // index-monotone: admit them by stepping the threshold one ulp down
-                  const uint32_t ko = f2ord(kth);
-                  const uint32_t to = p.nonstrict && ko > 0 ? ko - 1 : ko;
-                  thr = fmaxf(thr, __uint_as_float(ord2f(to)));
-                  // other lists of the row scan other index ranges: they must keep admitting ties
-                  atomicMax(my_row_thr, ko > 0 ? ko - 1 : 0u);
-                } else if (T != 0u) {
-                  cnt = n3;
-                  bound = fmaxf(bound, __uint_as_float(ord2f(T)));
-                  thr = fmaxf(thr, __uint_as_float(ord2f(T - 1)));  // x > thr  <=>  x >= T
-                  atomicMax(my_row_thr, T - 1);
-                }
-              }
-              __syncwarp();
-            }
           };
 #pragma unroll
           for (int c = 0; c < CHUNKS; c++) {
@@ -619,9 +637,10 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
               select_chunk(c, v);
             }
           }
+          if (!band) raise_thresholds(last, last && t + it.w >= t1);
         }
       }
-      // the list stays unsorted (<= CAP entries); K5 merges and orders
+      // the list stays unsorted (<= LCAP entries); K5 merges and orders
       p.list_cnt[slot] = cnt;
       p.list_bound[slot] = bound;
     }
@@ -742,7 +761,7 @@ __global__ void __launch_bounds__(256) k_merge(const MergeParams p) {
       const size_t slot = ((size_t)w * 2 + h) * BM + rr;
       const int n = p.list_cnt[slot];
       bound = fmaxf(bound, p.list_bound[slot]);
-      const uint2* list = p.lists + slot * CAP;
+      const uint2* list = p.lists + slot * LCAP;
       for (int e0 = 0; e0 < n; e0 += 32) {
         const int e = e0 + lane;
         bool keep = false;
@@ -2169,7 +2188,9 @@ static int job_begin_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t w
   // candidates kept per row: k + margin, at most CAP - 64
   // re-scoring margin: the more candidates beyond k, the more often the k-th value clears what was dropped (rows
   // that do not certify cost a band pass)
-  const int margin = rescored ? std::max(14, a->k >= 64 ? a->k / 2 : a->k / 4) : 0;
+  int margin = rescored ? std::max(14, a->k >= 64 ? a->k / 2 : a->k / 4) : 0;
+  if (const char* ev = getenv("MB200_MARGIN"))  // tuning override
+    if (rescored && atoi(ev) >= 0) margin = atoi(ev);
   int ksel = (a->k + margin + 31) / 32 * 32;
   if (ksel > CAP - 64) ksel = CAP - 64;
   if (a->k > ksel)
@@ -2394,7 +2415,7 @@ static int job_push_locked(mb200_cosine_job* j, const mb200_cosine_piece* pc) {
   MB_CHECK(d_slot.alloc(ws, slot_of.size() * sizeof(int32_t)));
   MB_CHECK(d_sptr.alloc(ws, slot_ptr.size() * sizeof(int32_t)));
   const size_t nlists = (size_t)num_items * 2 * BM;
-  MB_CHECK(d_lists.alloc(ws, nlists * CAP * sizeof(uint2)));
+  MB_CHECK(d_lists.alloc(ws, nlists * LCAP * sizeof(uint2)));
   MB_CHECK(d_cnt.alloc(ws, nlists * sizeof(int32_t)));
   MB_CHECK(d_bound.alloc(ws, nlists * sizeof(float)));
   j->ws_next = ws.next;
