@@ -2187,8 +2187,10 @@ static int job_begin_locked(mb200_ctx* ctx, const mb200_cosine_args* a, size_t w
   const bool rescored = a->precision != MB200_PRECISION_TENSOR;
   // candidates kept per row: k + margin, at most CAP - 64
   // re-scoring margin: the more candidates beyond k, the more often the k-th value clears what was dropped (rows
-  // that do not certify cost a band pass)
-  int margin = rescored ? std::max(14, a->k >= 64 ? a->k / 2 : a->k / 4) : 0;
+  // that do not certify cost a band pass).  Measured at 500000 x 500000, depth 1, k = 100 (profiles/
+  // r2_margin_500k.txt): 160 kept -> 10 % of the rows take the band pass, step 2233 ms; 192 kept -> none, 2077 ms
+  // (the epilogue's threshold raises no longer stall the MMA warp, so a longer list costs K3 ~1 %).
+  int margin = rescored ? std::max(14, a->k >= 64 ? a->k : a->k / 4) : 0;
   if (const char* ev = getenv("MB200_MARGIN"))  // tuning override
     if (rescored && atoi(ev) >= 0) margin = atoi(ev);
   int ksel = (a->k + margin + 31) / 32 * 32;

@@ -474,12 +474,13 @@ def test_k_beyond_the_fused_capacity(mb, ctx, k, threshold):
 
 
 @pytest.mark.parametrize("precision", ["certified", "rescored"])
-def test_band_pass_settles_flat_similarity_rows(mb, ctx, precision):
+def test_band_pass_settles_flat_similarity_rows(mb, ctx, precision, monkeypatch):
     """Rows whose similarities are nearly flat around the k-th value (few distinct users, coarse sketches, BF16 rows:
     the undecided band is wider than the candidate margin) cannot be certified from their lists; the band pass --
     a second K3 sweep over those rows with a fixed cut, every column above it re-scored exactly -- must return the
     oracle's answer without falling back to the exact full-row path."""
     from mahout_b200.sketch import last_band_rows, last_fallback_rows
+    monkeypatch.setenv("MB200_MARGIN", "28")       # 128 candidates kept for k = 100: many rows cannot be certified
     rng = np.random.Generator(np.random.PCG64(5))
     E, d, w, k = 3000, 2, 128, 100                 # (203 band rows, some with more than 2048 columns above their cut)
     n = 60 * E
@@ -507,12 +508,13 @@ def test_band_pass_settles_flat_similarity_rows(mb, ctx, precision):
     bank.close()
 
 
-def test_deferred_band_pass_of_a_streamed_job(mb, ctx):
+def test_deferred_band_pass_of_a_streamed_job(mb, ctx, monkeypatch):
     """A job whose B side arrives in pieces cannot re-sweep it by itself: finish(defer_uncertified) returns "pending",
     the caller pushes the same pieces once more (K3 sweeps them for the uncertified rows only) and finishes again.
     Result == the one-shot call == the oracle's sets; nothing takes the exact full-row path."""
     import torch
     from mahout_b200.sketch import CosineJob, cosine_topk_blocks, last_band_rows, last_fallback_rows
+    monkeypatch.setenv("MB200_MARGIN", "28")       # (see test_band_pass_settles_flat_similarity_rows)
     rng = np.random.Generator(np.random.PCG64(6))
     E, d, w, k = 1792, 2, 128, 100
     n = 60 * E

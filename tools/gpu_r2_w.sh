@@ -1,6 +1,6 @@
 #!/bin/bash
 # 1 GPU: candidate margin of the certified precision (k + 50 -> 160 kept, k + 92 -> 192 kept) on 500000 items, depth 1
-O=gpurun_out/r2w
+O=gpurun_out/r2w2
 mkdir -p $O
 ARGS="--gpus 1 --steps 1 --warmup 3 --events 1e8 --e2e-events 4194304 --no-cosine --big on --c4-items 500000 --c4-events 1e9 --c4-check-rows 64 --c4-d4 0 --c5-events 0 --c5-items 0"
 for m in 50 92; do

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--ks", default="10,50,100,150")
     ap.add_argument("--precision", default="tensor")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--chunks", default="0", help="MB200_COS_CHUNKS values to try (0 = the planner's choice)")
     args = ap.parse_args()
     import torch
     import mahout_b200 as mb
@@ -41,7 +42,11 @@ def main():
     bank.update(item, user, pref)
     del user, item, pref
     flops = 2.0 * d * float(E) ** 2 * int(N.lib().mb200_row_ld(w))
-    for k in [int(x) for x in args.ks.split(",")]:
+    for k, chunks in [(int(x), int(c)) for x in args.ks.split(",") for c in args.chunks.split(",")]:
+        if chunks > 0:
+            os.environ["MB200_COS_CHUNKS"] = str(chunks)
+        else:
+            os.environ.pop("MB200_COS_CHUNKS", None)
         bank.cosine_topk(k, precision=args.precision, device=True)   # warm-up (workspaces)
         ctx.set_profiling(True)
         ctx.reset_profile()
@@ -51,7 +56,7 @@ def main():
         ms5, _ = ctx.kernel_time(N.K_RESCORE)
         ctx.set_profiling(False)
         ms /= args.reps
-        print(json.dumps({"tool": "k3_k_sweep", "items": E, "depth": d, "k": k, "precision": args.precision,
+        print(json.dumps({"tool": "k3_k_sweep", "items": E, "depth": d, "k": k, "chunks": chunks, "precision": args.precision,
                           "K3_ms": ms, "K3_launches_per_call": cnt / args.reps, "K5_ms": ms5 / args.reps,
                           "TFLOPs": flops / (ms * 1e-3) / 1e12}), flush=True)
     bank.close()
