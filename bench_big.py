@@ -256,37 +256,42 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
     # handful is fine, thousands would take the stage past its budget -- then the stage reports the error and the
     # tensor-precision result instead of hanging
     ctx.set_option(N.OPT_MAX_FALLBACK_ROWS, max(8, int(fallback_limit) // max(depth, 1)))
-    precision = ["certified"]
+    # The stage climbs down a ladder when a form fails on any rank: the fused pull-gather (DMA pulls + arrival flags)
+    # is the fastest form but depends on the copy engines moving peer memory beside a kernel that holds every SM; if
+    # a block does not arrive in time (the kernel reports it after ~4 s) the stage is repeated in the streamed form
+    # (NCCL all-gathers of row chunks); if the certified precision itself fails (rows for the exact path beyond the
+    # limit above), the tensor precision is reported instead, and the line says so.
+    ladder = [(form, "certified")]
+    if world > 1 and form == "fused":
+        ladder.append(("pipelined", "certified"))
+    ladder.append((ladder[-1][0], "tensor"))
+    if getattr(env, "fused_failed", False) and world > 1:
+        ladder = [m for m in ladder if m[0] != "fused"]
+    mode = [ladder[0]]
 
     def step():
+        cur_form, cur_prec = mode[0]
         k2()
-        if precision[0] == "tensor":
-            if world == 1:
-                from mahout_b200.sketch import cosine_topk_blocks
-                return cosine_topk_blocks(ctx, rows, valid, rows.unsqueeze(0), valid.unsqueeze(0), depth, width, k,
-                                          a_id=(1, 0), b_id=(1, E_loc), precision="tensor", out=out_t)
-            if form == "fused":
-                return sim.fused_gather_cosine(be, plan, peers, k, None, "f16", "tensor", out=out_t)
-            peers.barrier()
-            r = sim.pipelined_cosine(be, plan, rows, valid, k, None, "f16", "tensor", None, chunk_rows, None)
-            peers.barrier()
-            return r
         if world == 1:
             from mahout_b200.sketch import cosine_topk_blocks
+            kw = dict(a_counters=a_cnt, b_counters=a_cnt, mixed_sign=mixed) if cur_prec == "certified" else {}
             return cosine_topk_blocks(ctx, rows, valid, rows.unsqueeze(0), valid.unsqueeze(0), depth, width, k,
-                                      a_id=(1, 0), b_id=(1, E_loc), precision="certified", a_counters=a_cnt,
-                                      b_counters=a_cnt, out=out_t, mixed_sign=mixed)
-        if form == "fused":
+                                      a_id=(1, 0), b_id=(1, E_loc), precision=cur_prec, out=out_t, **kw)
+        if cur_form == "fused":
+            if cur_prec == "tensor":
+                return sim.fused_gather_cosine(be, plan, peers, k, None, "f16", "tensor", out=out_t)
             return sim.fused_gather_cosine(be, plan, peers, k, None, "f16", "certified", a_counters=a_cnt,
                                            counter_blocks=blocks, out=out_t, mixed_sign=mixed)
-        peers.refresh_narrow()
+        if cur_prec == "certified":
+            peers.refresh_narrow()
         peers.barrier()
-        r = sim.pipelined_cosine(be, plan, rows, valid, k, None, "f16", "certified", None, chunk_rows, a_cnt, mixed,
-                                 counter_blocks=blocks, counter_blocks32=peers.counter_blocks32)
+        if cur_prec == "tensor":
+            r = sim.pipelined_cosine(be, plan, rows, valid, k, None, "f16", "tensor", None, chunk_rows, None)
+        else:
+            r = sim.pipelined_cosine(be, plan, rows, valid, k, None, "f16", "certified", None, chunk_rows, a_cnt, mixed,
+                                     counter_blocks=blocks, counter_blocks32=peers.counter_blocks32)
         peers.barrier()
         return r
-
-    certified_error = None
 
     def run_steps(nsteps):
         """nsteps steps; an error on any rank is an error on all of them (the steps are collective)"""
@@ -300,24 +305,30 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
                 return None, err or RuntimeError("the step failed on another rank")
         return out, None
 
-    _, err = run_steps(max(warmup, 1))
-    if err is not None:
-        certified_error = repr(err)[:300]
-        env.log(f"{name}: certified precision abandoned ({certified_error}); tensor precision instead")
+    abandoned = []
+    got = None
+    for m in ladder:
+        mode[0] = m
+        _, err = run_steps(max(warmup, 1))
+        if err is None:
+            env.barrier()
+            ctx.reset_profile()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(env.stream)
+            got, err = run_steps(reps)
+            e1.record(env.stream)
+            env.barrier()
+        if err is None:
+            break
+        abandoned.append({"form": m[0] if world > 1 else "single GPU", "precision": m[1], "error": repr(err)[:300]})
+        env.log(f"{name}: {m[0]} / {m[1]} abandoned ({repr(err)[:200]})")
+        if m[0] == "fused":
+            env.fused_failed = True              # the later stages of this run start in the streamed form
         torch.cuda.synchronize(dev)
-        precision[0] = "tensor"
-        _, err = run_steps(1)
-        if err is not None:
+        if m is ladder[-1]:
             raise err
-    env.barrier()
-    ctx.reset_profile()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(env.stream)
-    got, err = run_steps(reps)
-    if err is not None:
-        raise err
-    e1.record(env.stream)
-    env.barrier()
+    form, precision = mode[0][0], [mode[0][1]]
+    certified_error = abandoned[-1]["error"] if (abandoned and precision[0] == "tensor") else None
     ms = env.max_over_ranks(e0.elapsed_time(e1) / reps)
     env.log(f"{name}: cosine step {ms:.1f} ms")
     k2_ms, k2_n = ctx.kernel_time(N.K_NORMALIZE)
@@ -356,7 +367,7 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
             "ms_per_step": ms, "n_gpus": world,
             "precision": "certified (exact top-k sets, tensor-core values)" if precision[0] == "certified" else
                          "tensor (certified precision abandoned: see certified_error)",
-            "certified_error": certified_error, "band_rows": int(band_rows),
+            "certified_error": certified_error, "abandoned_forms": abandoned, "band_rows": int(band_rows),
             "form": form if world > 1 else "single GPU", "certified_fallback_rows": int(fallback), "mixed_sign": bool(mixed),
             "config": {"workload": workload, "items": items, "depth": depth, "width": width, "k": k, "events": int(events),
                        "zipf_s": zipf, "rows_per_gpu": E_loc, "chunk_rows": chunk_rows if form == "pipelined" else None,

@@ -379,8 +379,10 @@ k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
               while (*flag != p.epoch) {
                 __nanosleep(256);
                 // ~4 s: report instead of hanging the GPU.  The sweep then runs on incomplete data, but the abort
-                // word makes mb200_cosine_finish fail with MB200_ERR_CUDA before any result is handed out
-                if (clock64() - t_wait > 8000000000LL) {
+                // word makes mb200_cosine_finish fail with MB200_ERR_CUDA before any result is handed out -- and
+                // every other wait of this launch gives up at once (the word is sticky until finish clears it), so a
+                // lost block costs one time-out, not one per work item
+                if (clock64() - t_wait > 8000000000LL || *reinterpret_cast<volatile uint32_t*>(p.abort_flag) != 0u) {
                   atomicExch(p.abort_flag, 1u);
                   break;
                 }
@@ -3366,6 +3368,8 @@ int mb200_gather_pull(mb200_ctx* ctx, void* staging_rows, uint32_t* staging_vali
     MB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->gather_ev, cudaEventDisableTiming));
   }
   const uint32_t ep = ++ctx->gather_epoch;
+  // a time-out of an earlier launch whose job was aborted (never finished) must not poison this one
+  MB_CUDA(ctx, cudaMemsetAsync(ctx->gather_abort, 0, sizeof(uint32_t), ctx->stream));
   // the pulls start once everything queued so far on the compute stream is done (the caller's
   // cross-rank barrier sits there), and run on the copy engines beside K3
   MB_CUDA(ctx, cudaEventRecord(ctx->gather_ev, ctx->stream));
@@ -3393,10 +3397,9 @@ int mb200_gather_pull_counters(mb200_ctx* ctx, void* const* dst_blocks, const vo
       bytes_per_block <= 0)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_gather_pull_counters: bad arguments (blocks=%d my_block=%d)", blocks, my_block);
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!ctx->gather_ev) MB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->gather_ev, cudaEventDisableTiming));
-  // after everything queued so far on the compute stream (the caller's cross-rank barrier sits there)
-  MB_CUDA(ctx, cudaEventRecord(ctx->gather_ev, ctx->stream));
-  MB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gather_ev, 0));
+  if (!ctx->gather_flags)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_gather_pull_counters: call mb200_gather_pull first (the copies are ordered behind its row pulls)");
+  // (the copy stream already waits for the caller's cross-rank barrier: mb200_gather_pull put that wait there)
   for (int s = 1; s < blocks; s++) {
     const int b = (my_block + s) % blocks;
     if (!dst_blocks[b] || !src_blocks[b])

@@ -765,7 +765,20 @@ def _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_res
             elif precision != "tensor":
                 a_cnt = backend.counters()
                 kw.update(a_counters=a_cnt, b_counters=_all_gather(a_cnt, world, group))
-            idx, sim, cnt = fused_gather_cosine(backend, plan, peers, k, threshold, dtype, precision, **kw)
+            try:
+                res, err = fused_gather_cosine(backend, plan, peers, k, threshold, dtype, precision, **kw), None
+            except sk.N.NativeError as ex:
+                res, err = None, ex
+            if not all_ranks_ok(err is None, dev, group):
+                # a shard did not arrive through the copy engines in time on some rank (K3 reports it after ~4 s):
+                # every rank repeats the stage through the NCCL all-gather
+                import warnings
+                warnings.warn(f"fused pull-gather abandoned ({err!r}); falling back to the all-gather form")
+                peers.close()
+                peers = None
+                cur.wait_stream(comp)
+                return None
+            idx, sim, cnt = res
             if gather_result:
                 parts = [_all_gather(t, world, group).cpu().numpy() for t in (idx, sim, cnt)]      # C3
                 out = tuple(plan.assemble(list(p)) for p in parts)
@@ -840,7 +853,7 @@ def sharded_item_similarity(row, user, pref, num_items: int, k: int = DEFAULT_MA
         out = _fused_path(backend, plan, k, threshold, dtype, precision, group, gather_result, num_items)
         if out is not None:
             return out
-        # peer mappings are not available on this box (CUDA IPC refused): NCCL all-gather, then K3
+        # peer mappings are not available on this box (CUDA IPC refused), or a pull timed out: NCCL all-gather, then K3
     a_rows, a_valid = backend.normalized(dtype)
     a_cnt = backend.counters() if precision != "tensor" else None
     mixed = backend.mixed_sign(precision, group) if hasattr(backend, "mixed_sign") else False
