@@ -490,6 +490,26 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------
 
 
+def _collective_steps(fn, n, dev, check_each):
+    """n calls of a step that is collective across ranks (barriers inside).  A failure on one rank -- a shard that did
+    not arrive through the copy engines, say -- must become a failure on all of them at the same point, or the others
+    wait forever in the next collective: the ranks agree after every call (warm-up) or, so that the timed region holds
+    nothing but the steps, once after the last call (a failed rank keeps calling: every call meets its peers)."""
+    from mahout_b200 import similarity as sim
+    out, first = None, None
+    for _ in range(n):
+        try:
+            out = fn()
+        except Exception as ex:
+            first = first or ex
+            out = None
+        if check_each and not sim.all_ranks_ok(first is None, dev):
+            raise first or RuntimeError("the step failed on another rank")
+    if not check_each and not sim.all_ranks_ok(first is None, dev):
+        raise first or RuntimeError("the step failed on another rank")
+    return out
+
+
 def _cpu_cosine_rows(bank_host, rows, k, threads):
     """oracle top-k of the given global rows, one oracle call per row spread over `threads` host threads
     (the oracle's own OpenMP loop runs over rows, so single-row calls are dealt out here)."""
@@ -636,13 +656,11 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                                                      C.c_void_p(peers.valid.data_ptr())), ctx.handle)
                 return sim.fused_gather_cosine(be, plan, peers, C3_K, None, "f16", "tensor", out=fout)
 
-            for _ in range(warmup):
-                step_fused()
+            _collective_steps(step_fused, warmup, dev, True)
             barrier()
             ctx.reset_profile()
             e0.record(stream)
-            for _ in range(steps):
-                fidx, fs, fcnt = step_fused()
+            fidx, fs, fcnt = _collective_steps(step_fused, steps, dev, False)
             e1.record(stream)
             barrier()
             fused_ms = e0.elapsed_time(e1) / steps
@@ -671,14 +689,12 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
         else:
             cstep = None
         if cstep is not None:
-            for _ in range(warmup):
-                cstep()
+            _collective_steps(cstep, warmup, dev, True)
             barrier()
             ctx.reset_profile()
             t_c0 = time.perf_counter()
             e0.record(stream)
-            for _ in range(steps):
-                cidx, cs, ccnt = cstep()
+            cidx, cs, ccnt = _collective_steps(cstep, steps, dev, False)
             e1.record(stream)
             barrier()
             cert_wall_ms = (time.perf_counter() - t_c0) * 1e3 / steps
