@@ -150,3 +150,53 @@ def test_pipelined_driver_world2_gloo():
     """chunked all-gather + incremental job: two row chunks per shard ([0,256) and [256,301)), odd N so the
     last shard is one row short"""
     _run_world2(601, 6, 2, 32, 256)
+
+
+def _collective_worker(rank, world, port, out_q):
+    """a step that fails on rank 1 only (second call) must fail on every rank at the same point, in both modes"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    seen = {}
+    for check_each in (True, False):
+        calls = [0]
+
+        def step():
+            calls[0] += 1
+            dist.barrier()                                  # every call meets its peers, like the fused step
+            if rank == 1 and calls[0] == 2:
+                raise ValueError("lost block")
+            return calls[0]
+
+        try:
+            bench._collective_steps(step, 3, "cpu", check_each)
+            seen[check_each] = ("no error", calls[0])
+        except Exception as ex:
+            seen[check_each] = (type(ex).__name__, calls[0])
+    ok = sim.all_ranks_ok(True, "cpu")
+    out_q.put((rank, seen, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_step_failures_are_collective_world2_gloo():
+    world = 2
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = sck.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_collective_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict((r, (seen, ok)) for r, seen, ok in (q.get(timeout=90) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    # checked after every call: both ranks stop after the failing (second) call; checked once at the end: both make all
+    # three calls, then both fail -- the failing rank with its own error, the other with "failed on another rank"
+    assert got[0][0] == {True: ("RuntimeError", 2), False: ("RuntimeError", 3)}
+    assert got[1][0] == {True: ("ValueError", 2), False: ("ValueError", 3)}
+    assert got[0][1] and got[1][1]
