@@ -209,6 +209,23 @@ def sampled_parity(env: Env, plan, bank, got, k, rows_total, seed, block=8192):
 # ------------------------------------------------------------------------------------------------------------------
 # N-item all-pairs cosine, certified top-k, items sharded
 # ------------------------------------------------------------------------------------------------------------------
+def climb_down(ladder, attempt, on_abandon=None):
+    """Try the modes of `ladder` (tuples (form, precision)) in order: attempt(mode) -> (result, error).  Returns
+    (mode that worked, its result, [{"form", "precision", "error"} of the abandoned ones]); the last mode's error is
+    raised.  Everything in attempt must be collective across ranks, errors included (run_steps)."""
+    abandoned = []
+    for i, m in enumerate(ladder):
+        result, err = attempt(m)
+        if err is None:
+            return m, result, abandoned
+        abandoned.append({"form": m[0], "precision": m[1], "error": repr(err)[:300]})
+        if on_abandon is not None:
+            on_abandon(m, err)
+        if i == len(ladder) - 1:
+            raise err
+    raise ValueError("empty ladder")
+
+
 def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, width, k, form, check_rows, seed,
                chunk_rows=8192, reps=1, warmup=1, fallback_limit=256):
     import torch
@@ -305,28 +322,31 @@ def big_cosine(env: Env, name, workload, items, users, events, zipf, depth, widt
                 return None, err or RuntimeError("the step failed on another rank")
         return out, None
 
-    abandoned = []
-    got = None
-    for m in ladder:
+    def attempt(m):
+        """warm-up + the timed steps in mode m -> ((result, start event, end event), error)"""
         mode[0] = m
         _, err = run_steps(max(warmup, 1))
-        if err is None:
-            env.barrier()
-            ctx.reset_profile()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(env.stream)
-            got, err = run_steps(reps)
-            e1.record(env.stream)
-            env.barrier()
-        if err is None:
-            break
-        abandoned.append({"form": m[0] if world > 1 else "single GPU", "precision": m[1], "error": repr(err)[:300]})
+        if err is not None:
+            return None, err
+        env.barrier()
+        ctx.reset_profile()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(env.stream)
+        out, err = run_steps(reps)
+        e1.record(env.stream)
+        env.barrier()
+        return (out, e0, e1), err
+
+    def on_abandon(m, err):
         env.log(f"{name}: {m[0]} / {m[1]} abandoned ({repr(err)[:200]})")
         if m[0] == "fused":
             env.fused_failed = True              # the later stages of this run start in the streamed form
         torch.cuda.synchronize(dev)
-        if m is ladder[-1]:
-            raise err
+
+    done, (got, e0, e1), abandoned = climb_down(ladder, attempt, on_abandon)
+    mode[0] = done
+    for a_ in abandoned:
+        a_["form"] = a_["form"] if world > 1 else "single GPU"
     form, precision = mode[0][0], [mode[0][1]]
     certified_error = abandoned[-1]["error"] if (abandoned and precision[0] == "tensor") else None
     ms = env.max_over_ranks(e0.elapsed_time(e1) / reps)
