@@ -392,8 +392,9 @@ typedef struct mb200_cosine_piece {
 /* The all-gather fused into K3 (C1 + K3 of SURVEY.md 8e as one kernel's worth of time): every GPU keeps
  * its normalised rows in a peer-accessible buffer; mb200_gather_pull queues, on the context's copy
  * stream, one DMA per shard from the owner's memory over NVLink into the local staging operand
- * [blocks][d][b_count][ld] (own block first, then ring order), each followed by a stream memory
- * operation that publishes the block's arrival flag.  K3 is launched at once on the compute stream
+ * [blocks][d][b_count][ld] (ring order; the own block is copied on the compute stream itself, ahead of
+ * K3, because a copy inside one GPU may need SMs and the persistent K3 leaves none), each followed by a
+ * stream memory operation that publishes the block's arrival flag.  K3 is launched at once on the compute stream
  * with the flags in its piece: its TMA producer waits for a block's flag before the first tile of
  * that block, so the transfer of block g+1 hides behind the tensor-core sweep of block g and no SM
  * is spent on communication.  The caller provides the cross-rank ordering: all ranks must have

@@ -3382,11 +3382,16 @@ int mb200_gather_pull(mb200_ctx* ctx, void* staging_rows, uint32_t* staging_vali
   for (int s = 0; s < blocks; s++) {
     const int b = (my_block + s) % blocks;
     if (!peer_rows[b] || !peer_valid[b]) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "mb200_gather_pull: peer pointer %d is NULL", b);
+    // The own block is copied on the COMPUTE stream, ahead of K3 (a local copy at HBM speed: 0.3 ms per GB): a
+    // device-to-device copy inside one GPU may be carried out by SMs, and the persistent K3 CTAs leave none -- K3
+    // starts in the own block, so a copy that waited for K3 to end would time every CTA out.  The peers' blocks go
+    // through the copy engines over NVLink beside K3.
+    cudaStream_t via = s == 0 ? ctx->stream : ctx->copy_stream;
     MB_CUDA(ctx, cudaMemcpyAsync((char*)staging_rows + (size_t)b * rows_bytes, peer_rows[b], (size_t)rows_bytes,
-                                 cudaMemcpyDeviceToDevice, ctx->copy_stream));
+                                 cudaMemcpyDeviceToDevice, via));
     MB_CUDA(ctx, cudaMemcpyAsync((char*)staging_valid + (size_t)b * valid_bytes, peer_valid[b], (size_t)valid_bytes,
-                                 cudaMemcpyDeviceToDevice, ctx->copy_stream));
-    CUresult r = wv((CUstream)ctx->copy_stream, (CUdeviceptr)(uintptr_t)(ctx->gather_flags + b), ep, 0);
+                                 cudaMemcpyDeviceToDevice, via));
+    CUresult r = wv((CUstream)via, (CUdeviceptr)(uintptr_t)(ctx->gather_flags + b), ep, 0);
     if (r != CUDA_SUCCESS) return mb200_fail(ctx, MB200_ERR_CUDA, "cuStreamWriteValue32 failed with CUresult %d", (int)r);
   }
   *ready_flags = ctx->gather_flags;
