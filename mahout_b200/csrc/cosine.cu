@@ -312,12 +312,13 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 
 template <int BN, int ACC_STAGES, bool HAS_MIN>
-// Register cap instead of launch bounds (the two qualifiers exclude each other): 384 x 136 leaves 13 K of the SM's 64 K
-// registers free.  The persistent CTAs hold every SM for the whole sweep, and whatever else must run beside them in the
-// pull-gather mode gets only what they leave: with 138 - 150 registers (round 1) the fused form ran on every box, with
-// the 161 - 168 the compiler took after the lists grew to 512 entries a peer block never arrived while K3 was running
-// (profiles/r2_bench_n2_final_code_fused_timeout.log).  No variant in use spills at 136.
-__global__ void __maxnreg__(136)
+// Register cap instead of launch bounds (the two qualifiers exclude each other): the d = 1 kernel compiles to 128
+// registers under it, the d > 1 kernel to 144, which leaves 16 K / 10 K of the SM's 64 K registers free.  The persistent
+// CTAs hold every SM for the whole sweep, and whatever else must run beside them in the pull-gather mode gets only what
+// they leave: with 138 / 150 registers (12.5 K / 7.9 K free) the fused form ran on every box, with the 161 - 168 the
+// compiler took after the lists grew to 512 entries a peer block never arrived while K3 was running
+// (profiles/r2_bench_n2_final_code_fused_timeout.log).  No variant in use spills under the cap.
+__global__ void __maxnreg__(144)
 k_cosine(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
          const CosParams p) {
   static_assert((ACC_STAGES + (HAS_MIN ? 1 : 0)) * BN <= 512, "TMEM budget");
