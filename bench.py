@@ -490,6 +490,21 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------
 
 
+def _no_retries(fn):
+    """a fused step that only succeeded through its second sweep (a pull-gather time-out: seconds) is a failed step as
+    far as timing goes: the stage must report the other forms instead"""
+    from mahout_b200 import similarity as sim
+
+    def wrapped():
+        r0 = sim.FUSED_RETRIES[0]
+        out = fn()
+        if sim.FUSED_RETRIES[0] != r0:
+            raise RuntimeError("fused pull-gather: a peer block timed out (the result was recovered by a second sweep; "
+                               "the timing of this form is void)")
+        return out
+    return wrapped
+
+
 def _collective_steps(fn, n, dev, check_each):
     """n calls of a step that is collective across ranks (barriers inside).  A failure on one rank -- a shard that did
     not arrive through the copy engines, say -- must become a failure on all of them at the same point, or the others
@@ -656,11 +671,11 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
                                                      C.c_void_p(peers.valid.data_ptr())), ctx.handle)
                 return sim.fused_gather_cosine(be, plan, peers, C3_K, None, "f16", "tensor", out=fout)
 
-            _collective_steps(step_fused, warmup, dev, True)
+            _collective_steps(_no_retries(step_fused), warmup, dev, True)
             barrier()
             ctx.reset_profile()
             e0.record(stream)
-            fidx, fs, fcnt = _collective_steps(step_fused, steps, dev, False)
+            fidx, fs, fcnt = _collective_steps(_no_retries(step_fused), steps, dev, False)
             e1.record(stream)
             barrier()
             fused_ms = e0.elapsed_time(e1) / steps
@@ -689,12 +704,12 @@ def run_cosine_stage(ctx, stream, world, rank, local, dev, peaks, steps, warmup)
         else:
             cstep = None
         if cstep is not None:
-            _collective_steps(cstep, warmup, dev, True)
+            _collective_steps(_no_retries(cstep), warmup, dev, True)
             barrier()
             ctx.reset_profile()
             t_c0 = time.perf_counter()
             e0.record(stream)
-            cidx, cs, ccnt = _collective_steps(cstep, steps, dev, False)
+            cidx, cs, ccnt = _collective_steps(_no_retries(cstep), steps, dev, False)
             e1.record(stream)
             barrier()
             cert_wall_ms = (time.perf_counter() - t_c0) * 1e3 / steps

@@ -72,6 +72,7 @@ struct Shared {
   std::vector<int> rc;
   std::vector<std::string> msg;
   std::vector<int64_t> fallback;
+  std::vector<int32_t> pull_retries;  // 1 = this GPU repeated its cosine phase without arrival flags
   std::vector<int32_t> mixed;
   int64_t* out_idx;
   double* out_sim;
@@ -240,44 +241,58 @@ void worker(Shared& sh, int g) {
       a.threshold = P.threshold;
       a.exclude_self = 1;
       a.mixed_sign = mixed;
-      mb200_cosine_job* job = nullptr;
-      if (OK_SO_FAR) JOB_TRY(mb200_cosine_begin(ctx, &a, &job));
-      if (OK_SO_FAR) {
-        mb200_cosine_piece pc;
-        memset(&pc, 0, sizeof(pc));
-        pc.b_rows = staging;
-        pc.b_valid = (const uint32_t*)staging_v;
-        pc.b_count = E;
-        pc.b_blocks = G;
-        pc.b_id_mul = G;
-        pc.b_id_add = 1;
-        pc.ready_flags = flags;
-        pc.ready_epoch = epoch;
-        pc.first_block = g;
-        JOB_TRY(mb200_cosine_push(job, &pc));
-        mb200_cosine_args fin;
-        memset(&fin, 0, sizeof(fin));
-        fin.out_idx = (int64_t*)o_idx;
-        fin.out_sim = (double*)o_sim;
-        fin.out_cnt = (int32_t*)o_cnt;
-        fin.b_rows = staging;  // still resident: uncertified rows may take the band pass
-        fin.b_valid = (const uint32_t*)staging_v;
-        if (P.precision != MB200_PRECISION_TENSOR) {
-          fin.a_counters = (const int64_t*)sh.counters[g];
-          fin.b_blocks = G;
-          fin.b_count = E;
-          fin.b_id_mul = G;
-          fin.b_id_add = 1;
-          if (P.precision == MB200_PRECISION_CERTIFIED) {
-            fin.b_counter_blocks = (const int64_t* const*)sh.counters.data();
-            fin.b_counter_blocks32 = (const int32_t* const*)sh.n32.data();
-          } else {
-            fin.b_counters = (const int64_t*)sh.gathered[g];
+      // Attempt 0: K3 starts at once and waits block by block on the arrival flags.  If a pull has not landed when
+      // K3 gives up (~4 s: MB200_ERR_CUDA from finish), attempt 1 waits for the copy stream and sweeps the fully
+      // staged operand without flags -- a local decision: the peers' rows and counters stay alive until the barrier
+      // below, so no other worker needs to know.
+      for (int attempt = 0; attempt < 2 && OK_SO_FAR; attempt++) {
+        if (attempt == 1) JOB_TRY(mb200_gather_wait(ctx));
+        mb200_cosine_job* job = nullptr;
+        int rc = mb200_cosine_begin(ctx, &a, &job);
+        if (rc == MB200_OK) {
+          mb200_cosine_piece pc;
+          memset(&pc, 0, sizeof(pc));
+          pc.b_rows = staging;
+          pc.b_valid = (const uint32_t*)staging_v;
+          pc.b_count = E;
+          pc.b_blocks = G;
+          pc.b_id_mul = G;
+          pc.b_id_add = 1;
+          pc.ready_flags = attempt == 0 ? flags : nullptr;
+          pc.ready_epoch = attempt == 0 ? epoch : 0;
+          pc.first_block = g;
+          rc = mb200_cosine_push(job, &pc);
+          mb200_cosine_args fin;
+          memset(&fin, 0, sizeof(fin));
+          fin.out_idx = (int64_t*)o_idx;
+          fin.out_sim = (double*)o_sim;
+          fin.out_cnt = (int32_t*)o_cnt;
+          fin.b_rows = staging;  // still resident: uncertified rows may take the band pass
+          fin.b_valid = (const uint32_t*)staging_v;
+          if (P.precision != MB200_PRECISION_TENSOR) {
+            fin.a_counters = (const int64_t*)sh.counters[g];
+            fin.b_blocks = G;
+            fin.b_count = E;
+            fin.b_id_mul = G;
+            fin.b_id_add = 1;
+            if (P.precision == MB200_PRECISION_CERTIFIED) {
+              fin.b_counter_blocks = (const int64_t* const*)sh.counters.data();
+              fin.b_counter_blocks32 = (const int32_t* const*)sh.n32.data();
+            } else {
+              fin.b_counters = (const int64_t*)sh.gathered[g];
+            }
           }
+          if (rc == MB200_OK) rc = mb200_cosine_finish(job, &fin);
+          else mb200_cosine_abort(job);
         }
-        if (OK_SO_FAR) JOB_TRY(mb200_cosine_finish(job, &fin));
-        else mb200_cosine_abort(job);
+        const bool lost_block = rc == MB200_ERR_CUDA && attempt == 0 && strstr(mb200_last_error(ctx), "never arrived") != nullptr;
+        if (lost_block) {
+          sh.pull_retries[g] = 1;
+          continue;
+        }
+        JOB_TRY(rc);
         if (OK_SO_FAR) JOB_TRY(mb200_cosine_last_fallback_rows(ctx, &sh.fallback[g]));
+        break;
       }
       JOB_TRY(mb200_sync(ctx));
       mb200_gather_wait(ctx);
@@ -427,6 +442,7 @@ int mb200_job_item_similarity(mb200_multi* m, const int64_t* row, const int64_t*
   sh.rc.assign(G, MB200_OK);
   sh.msg.assign(G, "");
   sh.fallback.assign(G, 0);
+  sh.pull_retries.assign(G, 0);
   sh.mixed.assign(G, 0);
   sh.out_idx = out_idx;
   sh.out_sim = out_sim;
@@ -438,6 +454,10 @@ int mb200_job_item_similarity(mb200_multi* m, const int64_t* row, const int64_t*
   for (auto& t : th) t.join();
   for (int g = 0; g < G; g++)
     if (sh.rc[g] != MB200_OK) return multi_fail(m, sh.rc[g], "GPU " + std::to_string(m->devices[g]) + ": " + sh.msg[g]);
+  for (int g = 0; g < G; g++)
+    if (sh.pull_retries[g])
+      fprintf(stderr, "mb200_job_item_similarity: GPU %d repeated its cosine phase over the fully staged operand "
+                      "(a peer block had not arrived within K3's time-out)\n", m->devices[g]);
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     stats->n_gpus = G;

@@ -25,6 +25,7 @@ from . import sketch as sk
 LOCAL_COUNTERS_MAX_BYTES = 64 << 30      # PeerRows: local copies of the peers' int32 banks are held up to this size ...
 LOCAL_COUNTERS_MIN_ROWS = 16384          # ... for shards of at least this many rows (below, the copies outlast K3) ...
 LOCAL_COUNTERS_KEEP_FREE = 40 << 30      # ... and only if this much device memory stays free for the cosine workspaces
+FUSED_RETRIES = [0]                      # fused_gather_cosine: sweeps repeated after a pull-gather time-out (this process)
 NO_THRESHOLD = 4.9e-324          # RowSimilarityJob.NO_THRESHOLD = Double.MIN_VALUE (RowSimilarityJob.java:56)
 DEFAULT_MAX_SIMILAR_ITEMS_PER_ITEM = 100   # ItemSimilarityJob.java:88
 DEFAULT_MIN_PREFS_PER_USER = 1
@@ -702,21 +703,39 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
     ready = peers.pull()
     if counter_blocks is not None and precision != "tensor":
         peers.pull_counters()
-    job = backend.begin(plan, peers.rows, peers.valid, k, threshold, dtype, precision,
-                        **({"mixed_sign": True} if mixed_sign else {}))
+
+    def attempt(flags):
+        job = backend.begin(plan, peers.rows, peers.valid, k, threshold, dtype, precision,
+                            **({"mixed_sign": True} if mixed_sign else {}))
+        try:
+            job.push(peers.staging_rows, peers.staging_valid, id_mul=G, id_add=1, ready=flags, first_block=plan.rank)
+            if precision != "tensor":
+                if counter_blocks is not None:
+                    peers.fence()
+                return job.finish(a_counters=a_counters, b_counters=b_counters, b_id=(G, 1), out=out,
+                                  resident_b=(peers.staging_rows, peers.staging_valid),
+                                  counter_blocks=counter_blocks, b_count=plan.rows_per_shard,
+                                  counter_blocks32=peers.blocks32 if counter_blocks is not None else None)
+            return job.finish(out=out)
+        except BaseException:
+            job.abort()
+            raise
+
     try:
-        job.push(peers.staging_rows, peers.staging_valid, id_mul=G, id_add=1, ready=ready, first_block=plan.rank)
-        if precision != "tensor":
-            if counter_blocks is not None:
-                peers.fence()
-            res = job.finish(a_counters=a_counters, b_counters=b_counters, b_id=(G, 1), out=out,
-                             resident_b=(peers.staging_rows, peers.staging_valid),
-                             counter_blocks=counter_blocks, b_count=plan.rows_per_shard,
-                             counter_blocks32=peers.blocks32 if counter_blocks is not None else None)
-        else:
-            res = job.finish(out=out)
+        try:
+            res = attempt(ready)
+        except sk.N.NativeError as ex:
+            if "never arrived" not in str(ex):
+                raise
+            # A pull had not landed when K3 gave up (~4 s).  The peers keep their rows until the closing barrier, so
+            # this rank can recover on its own: wait for the copy stream, then sweep the fully staged operand
+            # without flags.
+            import warnings
+            warnings.warn(f"fused pull-gather: {ex}; repeating the sweep over the staged operand")
+            FUSED_RETRIES[0] += 1
+            sk.N.check(sk.N.lib().mb200_gather_wait(backend.ctx.handle), backend.ctx.handle)
+            res = attempt(None)
     except BaseException:
-        job.abort()
         # the peers are waiting at the closing barrier: meet them before the error leaves this rank, or the step
         # deadlocks (the caller is expected to fail on every rank -- see `all_ranks_ok`)
         peers.barrier()
