@@ -35,6 +35,9 @@ extern "C" {
 #define MB200_ERR_CM_DELTA (-7)  /* "delta must be between 0 and 1, exclusive"                     */
 #define MB200_ERR_CM_EPSILON (-8)
 #define MB200_ERR_UNSUPPORTED (-9)
+#define MB200_ERR_PULL_TIMEOUT (-10) /* pull-gather: a peer block had not arrived when K3 gave up (~4 s); the staged
+                                        operand completes once the copy stream drains: mb200_gather_wait, then push
+                                        again without ready_flags (what similarity.fused_gather_cosine and job.cu do) */
 
 #define MB200_MEM_HOST 0
 #define MB200_MEM_DEVICE 1

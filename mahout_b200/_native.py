@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmahout_b200.so")
 OK = 0
 BAND_PENDING = 1
 ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_INEXACT, ERR_RANGE = -1, -2, -3, -4, -5
-ERR_NO_DEVICE, ERR_CM_DELTA, ERR_CM_EPSILON, ERR_UNSUPPORTED = -6, -7, -8, -9
+ERR_NO_DEVICE, ERR_CM_DELTA, ERR_CM_EPSILON, ERR_UNSUPPORTED, ERR_PULL_TIMEOUT = -6, -7, -8, -9, -10
 MEM_HOST, MEM_DEVICE = 0, 1
 DTYPE_F16, DTYPE_BF16 = 0, 1
 PRECISION_TENSOR, PRECISION_RESCORED, PRECISION_CERTIFIED = 0, 1, 2

@@ -2935,7 +2935,7 @@ static int job_finish_locked(mb200_cosine_job* j, const mb200_cosine_args* fin) 
     MB_CUDA(ctx, cudaMemcpy(&ab, ctx->gather_abort, 4, cudaMemcpyDeviceToHost));
     if (ab) {
       cudaMemset(ctx->gather_abort, 0, 4);
-      return mb200_fail(ctx, MB200_ERR_CUDA, "mb200_cosine: a peer block never arrived (pull-gather timed out after ~4 s); results are invalid");
+      return mb200_fail(ctx, MB200_ERR_PULL_TIMEOUT, "mb200_cosine: a peer block never arrived (pull-gather timed out after ~4 s); results are invalid");
     }
   }
   return MB200_OK;

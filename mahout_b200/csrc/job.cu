@@ -242,7 +242,7 @@ void worker(Shared& sh, int g) {
       a.exclude_self = 1;
       a.mixed_sign = mixed;
       // Attempt 0: K3 starts at once and waits block by block on the arrival flags.  If a pull has not landed when
-      // K3 gives up (~4 s: MB200_ERR_CUDA from finish), attempt 1 waits for the copy stream and sweeps the fully
+      // K3 gives up (~4 s: MB200_ERR_PULL_TIMEOUT from finish), attempt 1 waits for the copy stream and sweeps the fully
       // staged operand without flags -- a local decision: the peers' rows and counters stay alive until the barrier
       // below, so no other worker needs to know.
       for (int attempt = 0; attempt < 2 && OK_SO_FAR; attempt++) {
@@ -285,7 +285,7 @@ void worker(Shared& sh, int g) {
           if (rc == MB200_OK) rc = mb200_cosine_finish(job, &fin);
           else mb200_cosine_abort(job);
         }
-        const bool lost_block = rc == MB200_ERR_CUDA && attempt == 0 && strstr(mb200_last_error(ctx), "never arrived") != nullptr;
+        const bool lost_block = rc == MB200_ERR_PULL_TIMEOUT && attempt == 0;
         if (lost_block) {
           sh.pull_retries[g] = 1;
           continue;

@@ -725,7 +725,7 @@ def fused_gather_cosine(backend, plan, peers: PeerRows, k, threshold=None, dtype
         try:
             res = attempt(ready)
         except sk.N.NativeError as ex:
-            if "never arrived" not in str(ex):
+            if getattr(ex, "code", None) != sk.N.ERR_PULL_TIMEOUT:
                 raise
             # A pull had not landed when K3 gave up (~4 s).  The peers keep their rows until the closing barrier, so
             # this rank can recover on its own: wait for the copy stream, then sweep the fully staged operand
